@@ -1,0 +1,180 @@
+/*
+ * ffc_b200.h — C ABI of libffc_b200.so: the B200 (sm_100a) kernels behind the drop-in
+ * replacements for advimman/lama's FFC inference path
+ * (reference: saicinpainting/training/modules/ffc.py).
+ *
+ * The reference has no FFI: its seam is the Python nn.Module surface, and every FLOP runs
+ * inside torch (cuFFT / cuDNN / ATen).  This library is what a maintainer binds *instead of*
+ * those torch calls; each entry point names the reference lines it replaces.  The binding
+ * itself (ctypes) is lama_b200/_lib.py and is documented in INTEGRATION.md.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++/torch types, no exceptions.
+ *  - every function returns 0 (FFCB_OK) or a negative FFCB_E* code; the message of the last
+ *    failure on the calling thread is ffcb_last_error().
+ *  - all device pointers are owned by the caller (torch's caching allocator in the Python
+ *    binding) and must stay alive until the stream work completes.  The library allocates
+ *    nothing (FFT twiddles are generated in shared memory by the kernels themselves).
+ *  - every launch goes to the caller's stream; no call synchronises or allocates, so all
+ *    entry points are CUDA-graph capturable (run each op once eagerly first: kernels that need
+ *    more than 48 KB of shared memory set their function attribute on first use).
+ *  - activations inside the path are channels-last ("NHWC"): element (b, y, x, c) of a tensor
+ *    lives at ptr + b*sb + y*sy + x*sx + c.  Strides let one allocation hold a reflect-padded
+ *    plane ([B][H+2][W+2][C], ptr at the interior origin) or a channel slice of a wider tensor
+ *    (the local|global halves of an FFC feature map share one 512-channel buffer).
+ *  - storage formats: FFCB_F32 (float) and FFCB_BF16X2 ("split" bfloat16: value = hi + lo with
+ *    hi = bf16(v), lo = bf16(v - hi); hi plane at ptr, lo plane at ptr + lo_off elements).
+ *    The split format is what the tcgen05 path multiplies (3 bf16 products, fp32 accumulate:
+ *    hi*hi + lo*hi + hi*lo, relative error ~2^-16, see DESIGN.md "precision").
+ */
+#ifndef FFC_B200_H_
+#define FFC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFCB_VERSION 100 /* 0.1.0 */
+
+enum {
+  FFCB_OK = 0,
+  FFCB_EINVAL = -1,  /* bad shape / alignment / unsupported combination */
+  FFCB_EARCH = -2,   /* device is not sm_100 */
+  FFCB_ECUDA = -3,   /* CUDA runtime / driver error (text in ffcb_last_error) */
+  FFCB_ENOMEM = -4   /* caller-provided workspace too small */
+};
+
+enum { FFCB_F32 = 0, FFCB_BF16X2 = 1 };
+enum { FFCB_ACT_NONE = 0, FFCB_ACT_RELU = 1, FFCB_ACT_SIGMOID = 2, FFCB_ACT_TANH = 3 };
+enum { FFCB_BORDER_ZERO = 0, FFCB_BORDER_REFLECT = 1 };
+/* arithmetic of the contraction kernels */
+enum {
+  FFCB_MATH_FP32 = 0,   /* CUDA-core FFMA, fp32 operands (reference-grade path) */
+  FFCB_MATH_BF16X3 = 1  /* tcgen05.mma kind::f16 on split-bf16 operands, fp32 accumulators in TMEM */
+};
+
+typedef void* ffcb_stream_t; /* cudaStream_t */
+
+/* Channels-last tensor view.  Strides are in elements of the storage type. */
+typedef struct {
+  void* ptr;       /* element (0,0,0,0); for FFCB_BF16X2 the hi plane */
+  int64_t sb, sy, sx;
+  int64_t lo_off;  /* FFCB_BF16X2: offset (elements) from the hi to the lo plane */
+  int32_t B, H, W, C;
+  int32_t fmt;     /* FFCB_F32 | FFCB_BF16X2 */
+  int32_t pad;     /* physical border pixels around the interior (0 or 1).  pad==1 and
+                      reflect_border!=0: producers also write the reflected border ring so
+                      that TMA tiles of 3x3 taps need no index math. */
+  int32_t reflect_border;
+  int32_t _reserved;
+} ffcb_tensor;
+
+/* One K-segment of an implicit-GEMM convolution: `nch` input channels starting at channel
+ * `c0` of input tensor `src`, sampled at input pixel (y*stride + dy, x*stride + dx). */
+typedef struct {
+  int32_t src, dy, dx, c0, nch;
+} ffcb_kseg;
+
+#define FFCB_MAX_KSEG 64
+
+/*
+ * v            = sum_seg sum_k in[seg.src][b, y*stride+dy, x*stride+dx, c0+k] * W[n][koff(seg)+k] + shift[n]
+ * out[b,y,x,n] = addend_post ? act(v) + addend[b,y,x,n]      (residual: id + act(bn(conv)), ffc.py:288)
+ *                            : act(v + addend[b,y,x,n])
+ *
+ * Replaces, with BatchNorm folded into W/shift by the caller (lama_b200/packing.py):
+ *   nn.Conv2d k in {1,3} of FFC.convl2l/convl2g/convg2l            ffc.py:189-196, 221, 223
+ *   SpectralTransform.conv1 (1x1 + BN + ReLU) and .conv2 (1x1)     ffc.py:128-133, 139-140, 145, 161
+ *   FourierUnit.conv_layer + bn + relu on the interleaved spectrum ffc.py:57-61, 100-101
+ *   FFC_BN_ACT.bn_l/bn_g + act                                     ffc.py:243-249, 253-254
+ *   the residual add of FFCResnetBlock                             ffc.py:288
+ *   nn.ConvTranspose2d(k3,s2,p1,op1)+BN+ReLU as four sub-pixel phases  ffc.py:350-354
+ * The out view's H,W are the output grid; input coordinates outside the input's interior are
+ * zero (FFCB_BORDER_ZERO) or reflected without edge repeat (FFCB_BORDER_REFLECT, ffc.py:189
+ * padding_mode='reflect').
+ *
+ * weight: FFCB_MATH_FP32  -> float  [Ktot][N]           (N contiguous)
+ *         FFCB_MATH_BF16X3 -> bf16  [2][N][Ktot] hi|lo   (K contiguous), Ktot = sum nch
+ */
+typedef struct {
+  ffcb_tensor in[2];
+  ffcb_tensor out;
+  ffcb_tensor addend;   /* addend.ptr == NULL: none */
+  const void* weight;
+  const float* shift;   /* [N] or NULL */
+  int32_t n_out;        /* N */
+  int32_t stride;       /* 1 or 2 */
+  int32_t border;       /* FFCB_BORDER_* */
+  int32_t act;          /* FFCB_ACT_* */
+  int32_t nseg;
+  int32_t math;         /* FFCB_MATH_* */
+  int32_t addend_post;  /* 0: addend joins the pre-activation sum; 1: added after the activation */
+  int32_t _reserved;
+  ffcb_kseg seg[FFCB_MAX_KSEG];
+} ffcb_conv_desc;
+
+int ffcb_version(void);
+const char* ffcb_last_error(void);
+/* 0 if `device` is an sm_100 part this library can run on */
+int ffcb_check_device(int device);
+void ffcb_shutdown(void);
+
+/* Generic fused convolution / pointwise contraction (see ffcb_conv_desc). */
+int ffcb_conv(const ffcb_conv_desc* desc, ffcb_stream_t stream);
+
+/*
+ * Stem: ReflectionPad2d(3) + Conv2d(Cin -> N, k7, no bias) + folded BN + ReLU.
+ * ffc.py:315-317 (FFC_BN_ACT with ratio 0/0 -> convl2l only) and :253.
+ * x: NCHW float [B][Cin][H][W] contiguous (what the caller of the generator passes);
+ * w: float [7*7*Cin][N] (k index = (ky*7+kx)*Cin + c); out: channels-last view.
+ */
+int ffcb_stem_conv7(const float* x_nchw, int B, int Cin, int H, int W, const float* w, const float* shift,
+                    int N, const ffcb_tensor* out, ffcb_stream_t stream);
+
+/*
+ * Head: ReflectionPad2d(3) + Conv2d(C -> N<=4, k7, bias) + activation, NCHW float output.
+ * ffc.py:360-363.  w: float [N][7*7][C]; bias [N]; y: [B][N][H][W].
+ */
+int ffcb_head_conv7(const ffcb_tensor* in, const float* w, const float* bias, int N, int act, float* y_nchw,
+                    ffcb_stream_t stream);
+
+/*
+ * Real 2-D FFT pair, norm='ortho', over the (H, W) axes of a channels-last tensor.
+ *   ffcb_rfft2 : torch.fft.rfftn(x, dim=(-2,-1), norm='ortho') + the stack/permute/view that
+ *                interleaves Re/Im as channels 2k / 2k+1                       ffc.py:86-89
+ *                in (B,H,W,C) real -> spec (B,H,W/2+1,2C)
+ *   ffcb_irfft2: the inverse view/permute/complex + torch.fft.irfftn(s=(H,W), norm='ortho'),
+ *                with the residual of SpectralTransform fused: out = residual + irfft2(spec)
+ *                                                                     ffc.py:103-108, 161
+ *                spec (B,H,W/2+1,2C) float -> out (B,H,W,C)
+ * The inverse transforms along H first (all W/2+1 columns, complex) and then C2R along W,
+ * ignoring Im of the k_w=0 and (even W) k_w=W/2 bins — exactly what torch/cuFFT/MKL do for the
+ * non-Hermitian post-ReLU spectrum.
+ * Power-of-two H, W in [4, 256] take the shared-memory Stockham kernels; any other size takes
+ * a direct-DFT kernel (exact same results, O(n^2)).
+ * ws: caller workspace of ffcb_fft2_workspace_bytes(B,H,W,C) bytes (row-pass intermediate).
+ */
+size_t ffcb_fft2_workspace_bytes(int B, int H, int W, int C);
+int ffcb_rfft2(const ffcb_tensor* in, const ffcb_tensor* spec, void* ws, size_t ws_bytes, ffcb_stream_t stream);
+int ffcb_irfft2(const ffcb_tensor* spec, const ffcb_tensor* residual /* nullable */, const ffcb_tensor* out,
+                void* ws, size_t ws_bytes, ffcb_stream_t stream);
+
+/* Layout/format conversion at the module boundary (the reference's tensors are NCHW float):
+ * ffc.py has no counterpart — these replace nothing, they adapt torch's layout to the path's. */
+int ffcb_nchw_to_nhwc(const float* x_nchw, int B, int C, int H, int W, const ffcb_tensor* out, ffcb_stream_t stream);
+int ffcb_nhwc_to_nchw(const ffcb_tensor* in, float* y_nchw, ffcb_stream_t stream);
+/* (re)write the reflected 1-pixel border ring of a pad==1 view from its interior */
+int ffcb_fill_reflect_border(const ffcb_tensor* t, ffcb_stream_t stream);
+
+/* number of kernel launches issued by this library on the calling thread since the last
+ * ffcb_reset_launch_count() — bench.py reports it as "gpu_launches" */
+long long ffcb_launch_count(void);
+void ffcb_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFC_B200_H_ */

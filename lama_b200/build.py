@@ -1,0 +1,67 @@
+"""In-tree build of libffc_b200.so (sm_100a only) with nvcc.
+
+``python -m lama_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles without a
+GPU; the resulting ``lama_b200/libffc_b200.so`` is git-ignored but travels to the GPU box.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+LIB_PATH = os.path.join(HERE, "libffc_b200.so")
+STAMP = LIB_PATH + ".stamp"
+
+SOURCES = ["api.cu", "fft.cu", "conv_simt.cu", "conv_tc.cu", "shell.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.isfile(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def _fingerprint():
+    h = hashlib.sha256()
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "ffc_b200.h")]
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_current() -> bool:
+    if not (os.path.isfile(LIB_PATH) and os.path.isfile(STAMP)):
+        return False
+    with open(STAMP) as fh:
+        return fh.read().strip() == _fingerprint()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the library if sources changed; returns its path."""
+    if not force and is_current():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    proc = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or proc.returncode != 0:
+        sys.stderr.write(proc.stdout)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed building libffc_b200.so:\n" + proc.stdout[-4000:])
+    with open(STAMP, "w") as fh:
+        fh.write(_fingerprint())
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,167 @@
+// extern "C" surface of libffc_b200.so (see include/ffc_b200.h) + error / launch bookkeeping.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ffcb {
+
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return FFCB_ECUDA;
+}
+
+void count_launch(int n) { g_launches += n; }
+
+int check_tensor(const ffcb_tensor* t, const char* name) {
+  FFCB_REQUIRE(t != nullptr, "%s: null tensor descriptor", name);
+  FFCB_REQUIRE(t->B >= 0 && t->H >= 0 && t->W >= 0 && t->C >= 0, "%s: negative extent", name);
+  if ((long long)t->B * t->H * t->W * t->C == 0) return FFCB_OK;
+  FFCB_REQUIRE(t->ptr != nullptr, "%s: null data pointer", name);
+  FFCB_REQUIRE(t->fmt == FFCB_F32 || t->fmt == FFCB_BF16X2, "%s: unknown storage format %d", name, t->fmt);
+  FFCB_REQUIRE(t->C % 4 == 0, "%s: channel count %d is not a multiple of 4", name, t->C);
+  const int esz = t->fmt == FFCB_F32 ? 4 : 2;
+  // 4-channel vector access: 16 B (float) / 8 B (bf16 planes)
+  const uintptr_t align = t->fmt == FFCB_F32 ? 16 : 8;
+  FFCB_REQUIRE(((uintptr_t)t->ptr % align) == 0, "%s: pointer %p not %zu-byte aligned", name, t->ptr, (size_t)align);
+  FFCB_REQUIRE(t->sx % 4 == 0 && t->sy % 4 == 0 && t->sb % 4 == 0, "%s: strides must be multiples of 4 elements",
+               name);
+  FFCB_REQUIRE(t->sx >= t->C, "%s: pixel stride %lld < C=%d", name, (long long)t->sx, t->C);
+  if (t->fmt == FFCB_BF16X2)
+    FFCB_REQUIRE(t->lo_off % 4 == 0 && t->lo_off != 0, "%s: lo_off must be a non-zero multiple of 4", name);
+  FFCB_REQUIRE(t->pad == 0 || t->pad == 1, "%s: pad must be 0 or 1", name);
+  (void)esz;
+  return FFCB_OK;
+}
+
+// implemented in the other translation units
+int conv_simt(const ffcb_conv_desc* d, cudaStream_t stream);
+int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream);
+int stem_conv7(const float*, int, int, int, int, const float*, const float*, int, const ffcb_tensor*, cudaStream_t);
+int head_conv7(const ffcb_tensor*, const float*, const float*, int, int, float*, cudaStream_t);
+size_t fft2_workspace_bytes(int B, int H, int W, int C);
+int rfft2(const ffcb_tensor*, const ffcb_tensor*, void*, size_t, cudaStream_t);
+int irfft2(const ffcb_tensor*, const ffcb_tensor*, const ffcb_tensor*, void*, size_t, cudaStream_t);
+int nchw_to_nhwc(const float*, int, int, int, int, const ffcb_tensor*, cudaStream_t);
+int nhwc_to_nchw(const ffcb_tensor*, float*, cudaStream_t);
+int fill_reflect_border(const ffcb_tensor*, cudaStream_t);
+
+static int check_conv(const ffcb_conv_desc* d) {
+  FFCB_REQUIRE(d != nullptr, "conv: null descriptor");
+  int rc;
+  if ((rc = check_tensor(&d->in[0], "conv.in[0]"))) return rc;
+  if ((rc = check_tensor(&d->out, "conv.out"))) return rc;
+  FFCB_REQUIRE(d->weight != nullptr, "conv: null weight");
+  FFCB_REQUIRE(d->n_out > 0 && d->n_out % 4 == 0, "conv: n_out=%d must be a positive multiple of 4", d->n_out);
+  FFCB_REQUIRE(d->out.C == d->n_out, "conv: out view has C=%d, n_out=%d", d->out.C, d->n_out);
+  FFCB_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
+  FFCB_REQUIRE(d->nseg >= 1 && d->nseg <= FFCB_MAX_KSEG, "conv: nseg=%d outside [1,%d]", d->nseg, FFCB_MAX_KSEG);
+  FFCB_REQUIRE(d->border == FFCB_BORDER_ZERO || d->border == FFCB_BORDER_REFLECT, "conv: bad border mode");
+  FFCB_REQUIRE(d->act >= FFCB_ACT_NONE && d->act <= FFCB_ACT_TANH, "conv: bad activation");
+  bool uses1 = false;
+  for (int i = 0; i < d->nseg; ++i) {
+    const ffcb_kseg& s = d->seg[i];
+    FFCB_REQUIRE(s.src == 0 || s.src == 1, "conv: seg %d has src=%d", i, s.src);
+    uses1 |= s.src == 1;
+    const ffcb_tensor& t = d->in[s.src];
+    FFCB_REQUIRE(s.nch > 0 && s.nch % 4 == 0 && s.c0 % 4 == 0 && s.c0 >= 0 && s.c0 + s.nch <= t.C,
+                 "conv: seg %d channel range [%d,%d) invalid for C=%d", i, s.c0, s.c0 + s.nch, t.C);
+    FFCB_REQUIRE(t.B == d->out.B, "conv: batch mismatch between in[%d] and out", s.src);
+    if (d->border == FFCB_BORDER_REFLECT) {
+      // reflect needs every sampled coordinate within one reflection of the interior
+      const int ymin = s.dy, ymax = (d->out.H - 1) * d->stride + s.dy;
+      const int xmin = s.dx, xmax = (d->out.W - 1) * d->stride + s.dx;
+      FFCB_REQUIRE(ymin > -t.H && ymax < 2 * t.H - 1 && xmin > -t.W && xmax < 2 * t.W - 1 && t.H >= 1 && t.W >= 1,
+                   "conv: seg %d tap (%d,%d) reaches beyond one reflection of a %dx%d input", i, s.dy, s.dx, t.H, t.W);
+    }
+  }
+  if (uses1 && (rc = check_tensor(&d->in[1], "conv.in[1]"))) return rc;
+  if (d->addend.ptr != nullptr) {
+    if ((rc = check_tensor(&d->addend, "conv.addend"))) return rc;
+    FFCB_REQUIRE(d->addend.B == d->out.B && d->addend.H == d->out.H && d->addend.W == d->out.W &&
+                     d->addend.C == d->n_out, "conv: addend shape differs from out");
+  }
+  return FFCB_OK;
+}
+
+}  // namespace ffcb
+
+using namespace ffcb;
+
+extern "C" {
+
+int ffcb_version(void) { return FFCB_VERSION; }
+const char* ffcb_last_error(void) { return g_err; }
+
+int ffcb_check_device(int device) {
+  cudaDeviceProp prop;
+  FFCB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libffc_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    return FFCB_EARCH;
+  }
+  return FFCB_OK;
+}
+
+void ffcb_shutdown(void) {}
+
+int ffcb_conv(const ffcb_conv_desc* d, ffcb_stream_t stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  if (d->math == FFCB_MATH_FP32) {
+    FFCB_REQUIRE(true, "");
+    return conv_simt(d, (cudaStream_t)stream);
+  }
+  if (d->math == FFCB_MATH_BF16X3) return conv_tc(d, (cudaStream_t)stream);
+  set_error("conv: unknown math mode %d", d->math);
+  return FFCB_EINVAL;
+}
+
+int ffcb_stem_conv7(const float* x, int B, int Cin, int H, int W, const float* w, const float* shift, int N,
+                    const ffcb_tensor* out, ffcb_stream_t stream) {
+  return stem_conv7(x, B, Cin, H, W, w, shift, N, out, (cudaStream_t)stream);
+}
+
+int ffcb_head_conv7(const ffcb_tensor* in, const float* w, const float* bias, int N, int act, float* y,
+                    ffcb_stream_t stream) {
+  return head_conv7(in, w, bias, N, act, y, (cudaStream_t)stream);
+}
+
+size_t ffcb_fft2_workspace_bytes(int B, int H, int W, int C) { return fft2_workspace_bytes(B, H, W, C); }
+
+int ffcb_rfft2(const ffcb_tensor* in, const ffcb_tensor* spec, void* ws, size_t ws_bytes, ffcb_stream_t stream) {
+  return rfft2(in, spec, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int ffcb_irfft2(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out, void* ws,
+                size_t ws_bytes, ffcb_stream_t stream) {
+  return irfft2(spec, residual, out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int ffcb_nchw_to_nhwc(const float* x, int B, int C, int H, int W, const ffcb_tensor* out, ffcb_stream_t stream) {
+  return nchw_to_nhwc(x, B, C, H, W, out, (cudaStream_t)stream);
+}
+
+int ffcb_nhwc_to_nchw(const ffcb_tensor* in, float* y, ffcb_stream_t stream) {
+  return nhwc_to_nchw(in, y, (cudaStream_t)stream);
+}
+
+int ffcb_fill_reflect_border(const ffcb_tensor* t, ffcb_stream_t stream) {
+  return fill_reflect_border(t, (cudaStream_t)stream);
+}
+
+long long ffcb_launch_count(void) { return g_launches; }
+void ffcb_reset_launch_count(void) { g_launches = 0; }
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+// Shared device/host helpers for libffc_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ffc_b200.h"
+
+namespace ffcb {
+
+// ---------------------------------------------------------------- error plumbing (api.cu)
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+
+#define FFCB_REQUIRE(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::ffcb::set_error(__VA_ARGS__);           \
+      return FFCB_EINVAL;                       \
+    }                                           \
+  } while (0)
+
+#define FFCB_CUDA(call)                                           \
+  do {                                                            \
+    cudaError_t _e = (call);                                      \
+    if (_e != cudaSuccess) return ::ffcb::cuda_fail(_e, #call);   \
+  } while (0)
+
+#define FFCB_LAUNCH_CHECK(name)                                   \
+  do {                                                            \
+    ::ffcb::count_launch();                                       \
+    cudaError_t _e = cudaGetLastError();                          \
+    if (_e != cudaSuccess) return ::ffcb::cuda_fail(_e, name);    \
+  } while (0)
+
+// ---------------------------------------------------------------- device view of ffcb_tensor
+struct View {
+  char* ptr;
+  long long sb, sy, sx, lo_off;
+  int B, H, W, C;
+  int fmt, pad, reflect_border;
+};
+
+inline View make_view(const ffcb_tensor& t) {
+  View v;
+  v.ptr = (char*)t.ptr;
+  v.sb = t.sb; v.sy = t.sy; v.sx = t.sx; v.lo_off = t.lo_off;
+  v.B = t.B; v.H = t.H; v.W = t.W; v.C = t.C;
+  v.fmt = t.fmt; v.pad = t.pad; v.reflect_border = t.reflect_border;
+  return v;
+}
+
+inline View null_view() {
+  View v{};
+  v.ptr = nullptr;
+  return v;
+}
+
+// Validation shared by entry points: 4-channel vector access everywhere.
+int check_tensor(const ffcb_tensor* t, const char* name);
+
+__host__ __device__ __forceinline__ long long pix_off(const View& v, int b, int y, int x) {
+  return (long long)b * v.sb + (long long)y * v.sy + (long long)x * v.sx;
+}
+
+// reflect without edge repeat: -1 -> 1, n -> n-2 (valid for |overshoot| < n)
+__host__ __device__ __forceinline__ int reflect_idx(int i, int n) {
+  i = i < 0 ? -i : i;
+  return i >= n ? 2 * n - 2 - i : i;
+}
+
+#ifdef __CUDACC__
+// split-bf16 encode/decode: v ~= hi + lo, |v - (hi+lo)| <= 2^-17 |v|
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ float bf16_bits_to_float(unsigned short u) {
+  return __uint_as_float(((unsigned)u) << 16);
+}
+
+// 4 consecutive channels at element offset `off` (multiple of 4) of a view
+__device__ __forceinline__ float4 load4(const View& v, long long off) {
+  if (v.fmt == FFCB_F32) {
+    return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(v.ptr) + off));
+  }
+  const unsigned short* p = reinterpret_cast<const unsigned short*>(v.ptr);
+  uint2 h = __ldg(reinterpret_cast<const uint2*>(p + off));
+  uint2 l = __ldg(reinterpret_cast<const uint2*>(p + off + v.lo_off));
+  float4 r;
+  r.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+  r.y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+  r.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+  r.w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+  return r;
+}
+
+__device__ __forceinline__ unsigned pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (unsigned)__bfloat16_as_ushort(a) | ((unsigned)__bfloat16_as_ushort(b) << 16);
+}
+
+__device__ __forceinline__ void store4(const View& v, long long off, float4 r) {
+  if (v.fmt == FFCB_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(v.ptr) + off) = r;
+    return;
+  }
+  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+  split_bf16(r.x, h0, l0); split_bf16(r.y, h1, l1); split_bf16(r.z, h2, l2); split_bf16(r.w, h3, l3);
+  unsigned short* p = reinterpret_cast<unsigned short*>(v.ptr);
+  *reinterpret_cast<uint2*>(p + off) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+  *reinterpret_cast<uint2*>(p + off + v.lo_off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+}
+
+// scalar access (tails, odd layouts)
+__device__ __forceinline__ float load1(const View& v, long long off) {
+  if (v.fmt == FFCB_F32) return __ldg(reinterpret_cast<const float*>(v.ptr) + off);
+  const unsigned short* p = reinterpret_cast<const unsigned short*>(v.ptr);
+  return bf16_bits_to_float(__ldg(p + off)) + bf16_bits_to_float(__ldg(p + off + v.lo_off));
+}
+
+__device__ __forceinline__ void store1(const View& v, long long off, float r) {
+  if (v.fmt == FFCB_F32) { reinterpret_cast<float*>(v.ptr)[off] = r; return; }
+  __nv_bfloat16 h, l;
+  split_bf16(r, h, l);
+  __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(v.ptr);
+  p[off] = h;
+  p[off + v.lo_off] = l;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case FFCB_ACT_RELU: return fmaxf(v, 0.f);
+    case FFCB_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    case FFCB_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+// Store one output pixel's 4 channels, plus its mirror images in the reflect border ring
+// when the view carries one (pad==1 && reflect_border): border row -1 mirrors row 1, row H
+// mirrors row H-2, likewise columns; corners follow from both.
+__device__ __forceinline__ void store4_with_border(const View& v, int b, int y, int x, int c, float4 r) {
+  store4(v, pix_off(v, b, y, x) + c, r);
+  if (v.pad && v.reflect_border) {
+    const int my = (y == 1) ? -1 : ((y == v.H - 2) ? v.H : -2);   // -2: no mirror
+    const int mx = (x == 1) ? -1 : ((x == v.W - 2) ? v.W : -2);
+    // H==2 (or W==2): pixel 0 is both "H-2" and must mirror to H; pixel 1 mirrors to -1.
+    if (my != -2) store4(v, pix_off(v, b, my, x) + c, r);
+    if (mx != -2) store4(v, pix_off(v, b, y, mx) + c, r);
+    if (my != -2 && mx != -2) store4(v, pix_off(v, b, my, mx) + c, r);
+    if (v.H == 3 && y == 1) {  // row 1 is both second and second-to-last: mirrors to -1 and H
+      store4(v, pix_off(v, b, v.H, x) + c, r);
+      if (mx != -2) store4(v, pix_off(v, b, v.H, mx) + c, r);
+    }
+    if (v.W == 3 && x == 1) {
+      store4(v, pix_off(v, b, y, v.W) + c, r);
+      if (my != -2) store4(v, pix_off(v, b, my, v.W) + c, r);
+      if (v.H == 3 && y == 1) store4(v, pix_off(v, b, v.H, v.W) + c, r);
+    }
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace ffcb

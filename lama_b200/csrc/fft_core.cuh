@@ -1,0 +1,155 @@
+// FFT arithmetic shared by the CUDA kernels (fft.cu) and the host emulation test
+// (tests/host_emul/fft_emul.cpp compiles this header with g++ and checks every size against a
+// double-precision DFT — the kernels' index algebra is verified on the CPU-only build box).
+//
+// Data layout: data[point * LS + lane], LS = lane stride (32 on the device: lane == channel).
+#pragma once
+#include <vector_functions.h>
+#include <vector_types.h>
+
+#if defined(__CUDACC__)
+#define FFCB_HD __host__ __device__ __forceinline__
+#else
+#define FFCB_HD inline
+#endif
+
+namespace ffcb {
+namespace fftc {
+
+FFCB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+FFCB_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+FFCB_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// multiply by -i (forward transform) or +i (inverse)
+template <bool INV>
+FFCB_HD float2 mul_mi(float2 a) {
+  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+template <bool INV>
+FFCB_HD void fft2(float2& a, float2& b) {
+  float2 t = a;
+  a = cadd(t, b);
+  b = csub(t, b);
+}
+
+template <bool INV>
+FFCB_HD void fft4(float2& v0, float2& v1, float2& v2, float2& v3) {
+  float2 t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3), t3 = mul_mi<INV>(csub(v1, v3));
+  v0 = cadd(t0, t2);
+  v2 = csub(t0, t2);
+  v1 = cadd(t1, t3);
+  v3 = csub(t1, t3);
+}
+
+template <bool INV>
+FFCB_HD void fft8(float2* v) {
+  fft4<INV>(v[0], v[2], v[4], v[6]);  // E[0..3] -> v[0], v[2], v[4], v[6]
+  fft4<INV>(v[1], v[3], v[5], v[7]);  // O[0..3] -> v[1], v[3], v[5], v[7]
+  const float h = 0.70710678118654752440f;
+  float2 o1, o2, o3;  // w^q * O[q], w = exp(-+ 2 pi i / 8)
+  if (INV) {
+    o1 = make_float2(h * (v[3].x - v[3].y), h * (v[3].x + v[3].y));
+    o2 = make_float2(-v[5].y, v[5].x);
+    o3 = make_float2(-h * (v[7].x + v[7].y), h * (v[7].x - v[7].y));
+  } else {
+    o1 = make_float2(h * (v[3].x + v[3].y), h * (v[3].y - v[3].x));
+    o2 = make_float2(v[5].y, -v[5].x);
+    o3 = make_float2(h * (v[7].y - v[7].x), -h * (v[7].x + v[7].y));
+  }
+  const float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+
+// Radix plan of the mixed-radix Stockham autosort, per power-of-two length.
+template <int N> struct Plan;
+template <> struct Plan<4>   { static constexpr int P = 1; static constexpr int R[3] = {4, 1, 1}; };
+template <> struct Plan<8>   { static constexpr int P = 1; static constexpr int R[3] = {8, 1, 1}; };
+template <> struct Plan<16>  { static constexpr int P = 2; static constexpr int R[3] = {4, 4, 1}; };
+template <> struct Plan<32>  { static constexpr int P = 2; static constexpr int R[3] = {8, 4, 1}; };
+template <> struct Plan<64>  { static constexpr int P = 2; static constexpr int R[3] = {8, 8, 1}; };
+template <> struct Plan<128> { static constexpr int P = 3; static constexpr int R[3] = {8, 4, 4}; };
+template <> struct Plan<256> { static constexpr int P = 3; static constexpr int R[3] = {8, 8, 4}; };
+
+template <int N, int PASS> constexpr int plan_radix() { return Plan<N>::R[PASS]; }
+template <int N, int PASS> constexpr int plan_ns() {
+  return PASS == 0 ? 1 : (PASS == 1 ? Plan<N>::R[0] : Plan<N>::R[0] * Plan<N>::R[1]);
+}
+// worker threads per transform the kernels launch with
+constexpr int workers_for(int n) { return n >= 8 ? n / 8 : 1; }
+
+// One out-of-place Stockham pass (src -> dst) for one lane, butterflies j = worker, worker+nw, ...
+// tw[t] = exp(-2 pi i t / N), t in [0, N).
+template <int N, int PASS, bool INV, int LS>
+FFCB_HD void stockham_pass(const float2* src, float2* dst, const float2* tw, int lane, int worker, int nworkers) {
+  constexpr int R = plan_radix<N, PASS>();
+  constexpr int NS = plan_ns<N, PASS>();
+  constexpr int NB = N / R;
+  for (int j = worker; j < NB; j += nworkers) {
+    const int k = j % NS;
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 x = src[(j + r * NB) * LS + lane];
+      if (NS > 1 && r > 0) {
+        float2 w = tw[r * k * (N / (NS * R))];
+        if (INV) w.y = -w.y;
+        x = cmul(x, w);
+      }
+      v[r] = x;
+    }
+    if (R == 8) fft8<INV>(v);
+    else if (R == 4) fft4<INV>(v[0], v[1], v[2], v[3]);
+    else fft2<INV>(v[0], v[1]);
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) dst[(j0 + r * NS) * LS + lane] = v[r];
+  }
+}
+
+// Direct DFT of runtime length n (src -> dst), output bins k = worker, worker+nw, ...
+template <bool INV, int LS>
+FFCB_HD void dft_pass(const float2* src, float2* dst, const float2* tw, int n, int lane, int worker, int nworkers) {
+  for (int k = worker; k < n; k += nworkers) {
+    float2 acc = make_float2(0.f, 0.f);
+    int t = 0;  // (k * m) mod n
+    for (int m = 0; m < n; ++m) {
+      float2 w = tw[t];
+      if (INV) w.y = -w.y;
+      const float2 x = src[m * LS + lane];
+      acc.x += x.x * w.x - x.y * w.y;
+      acc.y += x.x * w.y + x.y * w.x;
+      t += k;
+      if (t >= n) t -= n;
+    }
+    dst[k * LS + lane] = acc;
+  }
+}
+
+// Two-for-one real transforms.  z = row_a + i * row_b, Z = FFT(z) (length W, unnormalised):
+//   A[k] = (Z[k] + conj(Z[-k])) / 2,  B[k] = (Z[k] - conj(Z[-k])) / (2i),  k = 0 .. W/2
+template <int LS>
+FFCB_HD void r2c_pair_post(const float2* z, int W, int k, int lane, float2& a, float2& b) {
+  const float2 zk = z[k * LS + lane];
+  const float2 zm = z[((W - k) % W) * LS + lane];
+  a = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+  b = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+}
+
+// Inverse: given half-spectra X1[k], X2[k] (k = 0..W/2) build Z with z = IFFT(Z) = row_a + i*row_b.
+// Implements the C2R rule: Im of bin 0 and of the Nyquist bin (even W) is ignored.
+template <int LS>
+FFCB_HD void c2r_pair_pre(float2* z, int W, int k, int lane, float2 x1, float2 x2) {
+  if (k == 0 || 2 * k == W) {
+    z[k * LS + lane] = make_float2(x1.x, x2.x);
+  } else {
+    z[k * LS + lane] = make_float2(x1.x - x2.y, x1.y + x2.x);          // X1 + i X2
+    z[(W - k) * LS + lane] = make_float2(x1.x + x2.y, x2.x - x1.y);    // conj(X1) + i conj(X2)
+  }
+}
+
+}  // namespace fftc
+}  // namespace ffcb

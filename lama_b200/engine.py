@@ -1,0 +1,670 @@
+"""Program builder + CUDA executor behind the drop-in modules.
+
+A *program* is a straight-line list of op records over named channels-last activation buffers
+(``Buf``), built once per (module, input shape, device, math mode) from the module's parameters:
+BatchNorm folded, weights packed (``lama_b200.packing``), K-segment lists laid out, buffers
+wired so that the local|global halves of an FFC feature map share one allocation (split / concat
+are free) and residual adds, bias, BN and activations live in GEMM epilogues.
+
+The executor binds every op to one C-ABI call of ``libffc_b200.so`` with pre-built ctypes
+descriptors; replaying a program is a loop of foreign calls on the current CUDA stream (no
+allocation, no synchronisation) and is therefore CUDA-graph capturable (``GraphedProgram``).
+
+The op records are plain data so that ``tests/spec_interp.py`` can interpret the very same
+program with slow torch/numpy restatements on the CPU box — that is test infrastructure; the
+product path below only ever executes through the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import packing as P
+
+MATH_ENV = "LAMA_B200_MATH"     # "fp32" (default for now) | "bf16x3"
+
+
+def default_math() -> int:
+    return {"fp32": L.MATH_FP32, "bf16x3": L.MATH_BF16X3}[os.environ.get(MATH_ENV, "fp32").lower()]
+
+
+# ------------------------------------------------------------------------------------------- IR
+@dataclass
+class Buf:
+    """Channels-last activation buffer [B][H+2p][W+2p][C] (fp32) or [2][B][H+2p][W+2p][C] (split bf16)."""
+    name: str
+    B: int
+    H: int
+    W: int
+    C: int
+    pad: int = 0
+    fmt: int = L.F32
+    reflect_border: int = 0
+
+
+@dataclass
+class TV:
+    """View of a Buf: channel slice [c0, c0+C) and, for transposed-conv outputs, a sub-pixel phase."""
+    buf: Buf
+    c0: int = 0
+    C: Optional[int] = None
+    phase: Optional[Tuple[int, int]] = None   # (a, b): pixels (2i+a, 2j+b) of the buffer
+
+    @property
+    def channels(self) -> int:
+        return self.buf.C - self.c0 if self.C is None else self.C
+
+    @property
+    def hw(self) -> Tuple[int, int]:
+        return (self.buf.H // 2, self.buf.W // 2) if self.phase else (self.buf.H, self.buf.W)
+
+
+@dataclass
+class ToNHWC:
+    src: str          # name of an external NCHW float tensor
+    out: TV
+
+
+@dataclass
+class ToNCHW:
+    inp: TV
+    dst: str          # name of an external NCHW float output
+
+
+@dataclass
+class StemOp:
+    src: str          # external NCHW input
+    cin: int
+    w: torch.Tensor   # [(ky*7+kx)*Cin + c][N]
+    shift: torch.Tensor
+    out: TV
+
+
+@dataclass
+class HeadOp:
+    inp: TV
+    w: torch.Tensor   # [N][49][C]
+    bias: torch.Tensor
+    n_out: int
+    act: int
+    dst: str
+
+
+@dataclass
+class ConvOp:
+    packed: P.PackedConv
+    ins: List[Optional[TV]]
+    out: TV
+    addend: Optional[TV] = None
+    addend_post: bool = False
+    tag: str = ""
+
+
+@dataclass
+class RfftOp:
+    inp: TV
+    spec: TV
+
+
+@dataclass
+class IrfftOp:
+    spec: TV
+    residual: Optional[TV]
+    out: TV
+
+
+@dataclass
+class Program:
+    kind: str
+    math: int
+    bufs: List[Buf] = field(default_factory=list)
+    ops: list = field(default_factory=list)
+    inputs: Dict[str, Tuple[int, ...]] = field(default_factory=dict)    # name -> NCHW shape
+    outputs: Dict[str, Tuple[int, ...]] = field(default_factory=dict)
+
+    def buf(self, name, B, H, W, C, consumer_is_gemm=False) -> Buf:
+        # FFCB_MATH_BF16X3: operands of tcgen05 contractions are stored as split bf16 with a
+        # reflected border ring; everything else stays float32.
+        tc = self.math == L.MATH_BF16X3 and consumer_is_gemm
+        b = Buf(f"{name}#{len(self.bufs)}", B, H, W, C, pad=1 if tc else 0, fmt=L.BF16X2 if tc else L.F32,
+                reflect_border=1 if tc else 0)
+        self.bufs.append(b)
+        return b
+
+    def fft_workspace_bytes(self) -> int:
+        need = 0
+        for op in self.ops:
+            if isinstance(op, RfftOp):
+                b, (h, w), c = op.inp.buf.B, op.inp.hw, op.inp.channels
+            elif isinstance(op, IrfftOp):
+                b, (h, w), c = op.out.buf.B, op.out.hw, op.out.channels
+            else:
+                continue
+            need = max(need, 8 * b * h * (w // 2 + 1) * c)
+        return need
+
+
+# ------------------------------------------------------------------------------- support predicates
+def _act_code(m: nn.Module) -> Optional[int]:
+    if isinstance(m, nn.ReLU):
+        return L.ACT_RELU
+    if isinstance(m, nn.Identity):
+        return L.ACT_NONE
+    if isinstance(m, nn.Sigmoid):
+        return L.ACT_SIGMOID
+    if isinstance(m, nn.Tanh):
+        return L.ACT_TANH
+    return None
+
+
+def _plain_conv(conv, k_ok=(1, 3, 7)) -> bool:
+    return (isinstance(conv, nn.Conv2d) and conv.groups == 1 and conv.dilation == (1, 1) and conv.bias is None
+            and conv.kernel_size[0] == conv.kernel_size[1] and conv.kernel_size[0] in k_ok
+            and conv.stride[0] == conv.stride[1] and conv.stride[0] in (1, 2)
+            and conv.padding[0] == conv.padding[1] and isinstance(conv.padding[0], int)
+            and (conv.padding_mode == 'reflect' or conv.padding[0] == 0)
+            and conv.in_channels % 4 == 0 and conv.out_channels % 4 == 0)
+
+
+def ffc_bn_act_supported(m) -> bool:
+    f = m.ffc
+    if m.training or f.gated:
+        return False
+    convs = [c for c in (f.convl2l, f.convl2g, f.convg2l) if not isinstance(c, nn.Identity)]
+    if not convs or not all(_plain_conv(c) for c in convs):
+        return False
+    c0 = convs[0]
+    if any((c.kernel_size, c.stride, c.padding) != (c0.kernel_size, c0.stride, c0.padding) for c in convs):
+        return False
+    if c0.kernel_size[0] ** 2 + 1 > L.MAX_KSEG:
+        return False
+    if not isinstance(f.convg2g, nn.Identity):
+        if not f.convg2g.native_supported():
+            return False
+        if isinstance(f.convl2g, nn.Identity):      # global-only input is never produced by the generator
+            return False
+    for bn in (m.bn_l, m.bn_g):
+        if not isinstance(bn, (nn.BatchNorm2d, nn.Identity)):
+            return False
+    return _act_code(m.act_l) is not None and _act_code(m.act_g) is not None
+
+
+def ffc_bn_act_shapes_ok(m, x_l, x_g) -> bool:
+    f = m.ffc
+    if not torch.is_tensor(x_l) or x_l.dim() != 4:
+        return False
+    in_cg = f.global_in_num
+    if (in_cg > 0) != torch.is_tensor(x_g):
+        return False
+    if torch.is_tensor(x_g) and (x_g.shape[0] != x_l.shape[0] or x_g.shape[2:] != x_l.shape[2:]):
+        return False
+    c = next(c for c in (f.convl2l, f.convl2g, f.convg2l) if not isinstance(c, nn.Identity))
+    k, p = c.kernel_size[0], c.padding[0]
+    h, w = x_l.shape[2], x_l.shape[3]
+    if p > 0 and (h <= p or w <= p):     # reflect padding needs pad < size
+        return False
+    if h + 2 * p < k or w + 2 * p < k:
+        return False
+    if not isinstance(f.convg2g, nn.Identity) and w < 2:
+        return False
+    return True
+
+
+def _generator_layout(gen):
+    """Parse ``gen.model`` into (stem, downs, blocks, ups, head_conv, out_act) or None."""
+    from .modules import FFC_BN_ACT, FFCResnetBlock, ConcatTupleLayer
+    mods = list(gen.model)
+    i = 0
+    try:
+        if not (isinstance(mods[0], nn.ReflectionPad2d) and tuple(mods[0].padding) == (3, 3, 3, 3)):
+            return None
+        stem = mods[1]
+        if not (isinstance(stem, FFC_BN_ACT) and isinstance(stem.ffc.convl2l, nn.Conv2d)
+                and stem.ffc.convl2l.kernel_size == (7, 7) and stem.ffc.convl2l.padding == (0, 0)
+                and stem.ffc.convl2l.stride == (1, 1) and isinstance(stem.ffc.convl2g, nn.Identity)
+                and stem.ffc.global_in_num == 0 and isinstance(stem.bn_l, nn.BatchNorm2d)
+                and isinstance(stem.act_l, nn.ReLU) and stem.ffc.convl2l.bias is None
+                and stem.ffc.convl2l.groups == 1 and stem.ffc.convl2l.in_channels <= 16
+                and stem.ffc.convl2l.out_channels % 4 == 0 and not stem.ffc.gated):
+            return None
+        i = 2
+        downs = []
+        while isinstance(mods[i], FFC_BN_ACT):
+            if not mods[i].native_supported():
+                return None
+            downs.append(mods[i]); i += 1
+        blocks = []
+        while isinstance(mods[i], FFCResnetBlock):
+            if mods[i].inline or not mods[i].native_supported():
+                return None
+            blocks.append(mods[i]); i += 1
+        if not isinstance(mods[i], ConcatTupleLayer):
+            return None
+        i += 1
+        ups = []
+        while isinstance(mods[i], nn.ConvTranspose2d):
+            ct, bn, act = mods[i], mods[i + 1], mods[i + 2]
+            if not (ct.kernel_size == (3, 3) and ct.stride == (2, 2) and ct.padding == (1, 1)
+                    and ct.output_padding == (1, 1) and ct.groups == 1 and ct.dilation == (1, 1)
+                    and isinstance(bn, nn.BatchNorm2d) and isinstance(act, nn.ReLU)
+                    and ct.in_channels % 4 == 0 and ct.out_channels % 4 == 0):
+                return None
+            ups.append((ct, bn)); i += 3
+        if not (isinstance(mods[i], nn.ReflectionPad2d) and tuple(mods[i].padding) == (3, 3, 3, 3)):
+            return None
+        head = mods[i + 1]
+        if not (isinstance(head, nn.Conv2d) and head.kernel_size == (7, 7) and head.padding == (0, 0)
+                and head.stride == (1, 1) and head.groups == 1 and head.out_channels <= 4
+                and head.in_channels % 4 == 0):
+            return None
+        i += 2
+        out_act = L.ACT_NONE
+        if i < len(mods):
+            out_act = _act_code(mods[i])
+            if out_act is None:
+                return None
+            i += 1
+        if i != len(mods):
+            return None
+        return stem, downs, blocks, ups, head, out_act
+    except IndexError:
+        return None
+
+
+def generator_supported(gen, x) -> bool:
+    lay = _generator_layout(gen)
+    if lay is None or x.dim() != 4:
+        return False
+    stem, downs, _blocks, _ups, _head, _ = lay
+    b, c, h, w = x.shape
+    if c != stem.ffc.convl2l.in_channels or h < 4 or w < 4:
+        return False
+    f = 2 ** len(downs)
+    if h % f or w % f:                      # ConvTranspose doubles sizes: only exact multiples round-trip
+        return False
+    return h // f >= 2 and w // f >= 2      # reflect pad 1 at the bottleneck
+
+
+# -------------------------------------------------------------------------------------- builders
+def _fold(bn, n, device):
+    if isinstance(bn, nn.BatchNorm2d):
+        return P.bn_scale_shift(bn)
+    return torch.ones(n, dtype=torch.float64, device=device), torch.zeros(n, dtype=torch.float64, device=device)
+
+
+def emit_fourier_unit(prog: Program, fu, t: TV, out: TV, residual: Optional[TV]):
+    """FourierUnit (ffc.py:76-113): rfft2 -> [1x1 conv + BN + ReLU] on the interleaved spectrum -> irfft2,
+    optionally with the SpectralTransform residual fused into the inverse (out = residual + fu(t))."""
+    b = t.buf.B
+    h, w = t.hw
+    wf = w // 2 + 1
+    cin2, cout2 = fu.conv_layer.in_channels, fu.conv_layer.out_channels
+    S = prog.buf("spectrum", b, h, wf, cin2, consumer_is_gemm=True)
+    Z = prog.buf("spectrum_out", b, h, wf, cout2)
+    prog.ops.append(RfftOp(t, TV(S)))
+    scale, shift = P.bn_scale_shift(fu.bn)
+    pk = P.pack_conv([(fu.conv_layer.weight, 0, 0, 0)], scale, shift, act=L.ACT_RELU,
+                     device=fu.conv_layer.weight.device)
+    prog.ops.append(ConvOp(pk, [TV(S), None], TV(Z), tag="fu.conv_layer+bn+relu"))
+    prog.ops.append(IrfftOp(TV(Z), residual, out))
+
+
+def emit_spectral_transform(prog: Program, st, x: TV, u_consumer=None) -> Tuple[TV, P.PackedConv]:
+    """SpectralTransform (ffc.py:142-163) up to, but not including, conv2: returns the view holding
+    ``x1 + fu(x1)`` and lets the caller fuse conv2 into its own contraction."""
+    b = x.buf.B
+    h, w = x.hw
+    c = st.conv1[0].out_channels
+    dev = st.conv2.weight.device
+    T = prog.buf("st.t", b, h, w, c)
+    U = prog.buf("st.u", b, h, w, c, consumer_is_gemm=True)
+    s1, b1 = P.bn_scale_shift(st.conv1[1])
+    pk1 = P.pack_conv([(st.conv1[0].weight, 0, x.c0, 0)], s1, b1, act=L.ACT_RELU, device=dev)
+    prog.ops.append(ConvOp(pk1, [TV(x.buf), None], TV(T), tag="st.conv1+bn+relu"))
+    emit_fourier_unit(prog, st.fu, TV(T), TV(U), residual=TV(T))
+    return TV(U)
+
+
+def emit_ffc_bn_act(prog: Program, m, X: Buf, in_cl: int, in_cg: int, residual: Optional[Buf] = None,
+                    Y: Optional[Buf] = None) -> Tuple[Buf, int, int]:
+    """FFC + BN + activation (ffc.py:205-225, 251-255) reading [x_l | x_g] from ``X`` and writing
+    [y_l | y_g] into ``Y`` (allocated here unless given).  With ``residual`` the block identity
+    (ffc.py:288) is added after the activation in the same epilogues.
+    Returns (Y, out_cl, out_cg)."""
+    f = m.ffc
+    dev = next(m.parameters()).device
+    conv0 = next(c for c in (f.convl2l, f.convl2g, f.convg2l) if not isinstance(c, nn.Identity))
+    k, s, p = conv0.kernel_size[0], conv0.stride[0], conv0.padding[0]
+    out_cl = f.convl2l.out_channels if not isinstance(f.convl2l, nn.Identity) else (
+        f.convg2l.out_channels if not isinstance(f.convg2l, nn.Identity) else 0)
+    out_cg = f.convl2g.out_channels if not isinstance(f.convl2g, nn.Identity) else 0
+    ho, wo = (X.H + 2 * p - k) // s + 1, (X.W + 2 * p - k) // s + 1
+    if Y is None:
+        Y = prog.buf("ffc.out", X.B, ho, wo, out_cl + out_cg, consumer_is_gemm=True)
+    act_l, act_g = _act_code(m.act_l), _act_code(m.act_g)
+    sl, bl = _fold(m.bn_l, out_cl, dev)
+    sg, bg = _fold(m.bn_g, out_cg, dev)
+    has_spectral = not isinstance(f.convg2g, nn.Identity)
+    res_l = TV(residual, 0, out_cl) if residual is not None else None
+    res_g = TV(residual, out_cl, out_cg) if residual is not None else None
+
+    if in_cg == 0 and out_cl > 0 and out_cg > 0 and act_l == act_g:
+        # local input only (stem-like / downsample-to-global): convl2l and convl2g read the same
+        # pixels, so they are ONE contraction with N = out_cl + out_cg.
+        wcat = torch.cat([f.convl2l.weight, f.convl2g.weight], dim=0)
+        pk = P.pack_conv([(wcat, 0, 0, p)], torch.cat([sl, sg]), torch.cat([bl, bg]), stride=s, act=act_l, device=dev)
+        prog.ops.append(ConvOp(pk, [TV(X, 0, in_cl), None], TV(Y), addend=TV(residual) if residual else None,
+                               addend_post=True, tag="convl2l|convl2g+bn+act"))
+        return Y, out_cl, out_cg
+
+    if out_cl > 0:
+        # y_l = act(bn_l(convl2l(x_l) + convg2l(x_g))): x_l|x_g are adjacent channels of X, so the
+        # two convolutions are one contraction over C = in_cl + in_cg.
+        ws = [f.convl2l.weight] + ([f.convg2l.weight] if in_cg > 0 else [])
+        pk = P.pack_conv([(torch.cat(ws, dim=1), 0, 0, p)], sl, bl, stride=s, act=act_l, device=dev)
+        prog.ops.append(ConvOp(pk, [TV(X), None], TV(Y, 0, out_cl), addend=res_l, addend_post=True,
+                               tag="convl2l+convg2l+bn_l+act"))
+    if out_cg > 0:
+        parts = [(f.convl2g.weight, 0, 0, p)]     # ffc_bn_act_supported() guarantees convl2g exists
+        ins = [TV(X), None]
+        if has_spectral:
+            U = emit_spectral_transform(prog, f.convg2g, TV(X, in_cl, in_cg))
+            parts.append((f.convg2g.conv2.weight, 1, 0, 0))
+            ins[1] = U
+        # y_g = act(bn_g(convl2g(x_l) + conv2(x1 + fu(x1)))): conv2 rides as one more K-segment.
+        pk = P.pack_conv(parts, sg, bg, stride=s, act=act_g, device=dev)
+        prog.ops.append(ConvOp(pk, ins, TV(Y, out_cl, out_cg), addend=res_g, addend_post=True,
+                               tag="convl2g+st.conv2+bn_g+act"))
+    return Y, out_cl, out_cg
+
+
+def emit_resnet_block(prog: Program, blk, X: Buf, cl: int, cg: int, in_place: bool) -> Buf:
+    """FFCResnetBlock (ffc.py:277-292): X <- X + conv2(conv1(X)).  With ``in_place`` the second
+    FFC_BN_ACT writes its result over X (each output pixel only reads its own residual pixel)."""
+    Y, ycl, ycg = emit_ffc_bn_act(prog, blk.conv1, X, cl, cg)
+    out = X if in_place else prog.buf("block.out", X.B, X.H, X.W, X.C, consumer_is_gemm=True)
+    emit_ffc_bn_act(prog, blk.conv2, Y, ycl, ycg, residual=X, Y=out)
+    return out
+
+
+def build_module_program(module, kind: str, shapes: Sequence[Optional[Tuple[int, ...]]], math: int) -> Program:
+    """Programs for stand-alone module calls: NCHW float in -> channels-last inside -> NCHW float out."""
+    prog = Program(kind=kind, math=math)
+    if kind == "fourier_unit":
+        b, c, h, w = shapes[0]
+        prog.inputs["x0"] = shapes[0]
+        X = prog.buf("in", b, h, w, c)
+        prog.ops.append(ToNHWC("x0", TV(X)))
+        co = module.conv_layer.out_channels // 2
+        O = prog.buf("out", b, h, w, co)
+        emit_fourier_unit(prog, module, TV(X), TV(O), residual=None)
+        prog.ops.append(ToNCHW(TV(O), "y0")); prog.outputs["y0"] = (b, co, h, w)
+    elif kind == "spectral_transform":
+        b, c, h, w = shapes[0]
+        prog.inputs["x0"] = shapes[0]
+        X = prog.buf("in", b, h, w, c, consumer_is_gemm=True)
+        prog.ops.append(ToNHWC("x0", TV(X)))
+        U = emit_spectral_transform(prog, module, TV(X))
+        co = module.conv2.out_channels
+        O = prog.buf("out", b, h, w, co)
+        pk = P.pack_conv([(module.conv2.weight, 0, 0, 0)], None, None, device=module.conv2.weight.device)
+        prog.ops.append(ConvOp(pk, [U, None], TV(O), tag="st.conv2"))
+        prog.ops.append(ToNCHW(TV(O), "y0")); prog.outputs["y0"] = (b, co, h, w)
+    elif kind in ("ffc_bn_act", "resnet_block"):
+        sl, sg = shapes
+        b, cl, h, w = sl
+        cg = sg[1] if sg is not None else 0
+        prog.inputs["x0"] = sl
+        X = prog.buf("in", b, h, w, cl + cg, consumer_is_gemm=True)
+        prog.ops.append(ToNHWC("x0", TV(X, 0, cl)))
+        if cg:
+            prog.inputs["x1"] = sg
+            prog.ops.append(ToNHWC("x1", TV(X, cl, cg)))
+        if kind == "ffc_bn_act":
+            Y, ocl, ocg = emit_ffc_bn_act(prog, module, X, cl, cg)
+        else:
+            Y = emit_resnet_block(prog, module, X, cl, cg, in_place=False)
+            ocl, ocg = cl, cg
+        if ocl:
+            prog.ops.append(ToNCHW(TV(Y, 0, ocl), "y0")); prog.outputs["y0"] = (b, ocl, Y.H, Y.W)
+        if ocg:
+            prog.ops.append(ToNCHW(TV(Y, ocl, ocg), "y1")); prog.outputs["y1"] = (b, ocg, Y.H, Y.W)
+    elif kind == "generator":
+        build_generator_program(prog, module, shapes[0])
+    else:
+        raise ValueError(kind)
+    return prog
+
+
+def build_generator_program(prog: Program, gen, shape):
+    """FFCResNetGenerator (ffc.py:306-367) as one program: stem -> stride-2 convs -> residual blocks
+    (in place on one 512-channel buffer) -> sub-pixel transposed convs -> head."""
+    stem, downs, blocks, ups, head, out_act = _generator_layout(gen)
+    b, cin, h, w = shape
+    dev = head.weight.device
+    prog.inputs["x0"] = tuple(shape)
+    conv = stem.ffc.convl2l
+    n0 = conv.out_channels
+    s0, b0 = P.bn_scale_shift(stem.bn_l)
+    wst, shst = P.pack_stem(conv.weight, s0, b0, device=dev)
+    X = prog.buf("stem", b, h, w, n0, consumer_is_gemm=True)
+    prog.ops.append(StemOp("x0", cin, wst, shst, TV(X)))
+    cl, cg = n0, 0
+    for d in downs:
+        X, cl, cg = emit_ffc_bn_act(prog, d, X, cl, cg)
+    for blk in blocks:
+        X = emit_resnet_block(prog, blk, X, cl, cg, in_place=True)
+    # ConcatTupleLayer (ffc.py:295-302) is free: x_l | x_g already share X.
+    for ct, bn in ups:
+        sc, sh = P.bn_scale_shift(bn)
+        Yb = prog.buf("up", b, X.H * 2, X.W * 2, ct.out_channels, consumer_is_gemm=True)
+        for a, bb, pk in P.pack_conv_transpose_phases(ct.weight, ct.bias, sc, sh, act=L.ACT_RELU, device=dev):
+            prog.ops.append(ConvOp(pk, [TV(X), None], TV(Yb, phase=(a, bb)), tag=f"convT phase {a}{bb}+bn+relu"))
+        X = Yb
+    wh, bh = P.pack_head(head.weight, head.bias, device=dev)
+    prog.ops.append(HeadOp(TV(X), wh, bh, head.out_channels, out_act, "y0"))
+    prog.outputs["y0"] = (b, head.out_channels, h, w)
+
+
+# ------------------------------------------------------------------------------------- executor
+class CudaExecutor:
+    """Binds a Program to device buffers and pre-built C-ABI calls."""
+
+    def __init__(self, prog: Program, device: torch.device):
+        self.prog = prog
+        self.device = device
+        self.lib = L.get_lib()
+        L.check(self.lib.ffcb_check_device(device.index if device.index is not None else torch.cuda.current_device()),
+                "ffcb_check_device")
+        self.storage: Dict[str, torch.Tensor] = {}
+        for b in prog.bufs:
+            shape = (b.B, b.H + 2 * b.pad, b.W + 2 * b.pad, b.C)
+            if b.fmt == L.F32:
+                self.storage[b.name] = torch.empty(shape, dtype=torch.float32, device=device)
+            else:
+                self.storage[b.name] = torch.zeros((2,) + shape, dtype=torch.bfloat16, device=device)
+        ws_bytes = prog.fft_workspace_bytes()
+        self.ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=device)
+        self.ws_bytes = ws_bytes
+        self.outputs = {k: torch.empty(v, dtype=torch.float32, device=device) for k, v in prog.outputs.items()}
+        self._keep = []          # ctypes objects / tensors that must outlive the calls
+        self.calls = []          # (fn, args) with a trailing stream argument appended at run time
+        self.input_slots: Dict[str, List[Tuple[int, int]]] = {}   # input name -> [(call idx, arg idx)]
+        for op in prog.ops:
+            self._bind(op)
+
+    # -- view construction
+    def tensor(self, tv: TV) -> L.Tensor:
+        b = tv.buf
+        st = self.storage[b.name]
+        es = 4 if b.fmt == L.F32 else 2
+        wp, hp = b.W + 2 * b.pad, b.H + 2 * b.pad
+        sx, sy, sb = b.C, wp * b.C, hp * wp * b.C
+        off = (b.pad * wp + b.pad) * b.C + tv.c0
+        h, w = b.H, b.W
+        if tv.phase is not None:
+            a, bb = tv.phase
+            off += a * sy + bb * sx
+            sy, sx, h, w = 2 * sy, 2 * sx, b.H // 2, b.W // 2
+        t = L.Tensor()
+        t.ptr = st.data_ptr() + off * es
+        t.sb, t.sy, t.sx = sb, sy, sx
+        t.lo_off = b.B * hp * wp * b.C if b.fmt == L.BF16X2 else 0
+        t.B, t.H, t.W, t.C = b.B, h, w, tv.channels
+        t.fmt, t.pad, t.reflect_border = b.fmt, b.pad, b.reflect_border
+        return t
+
+    def _ref(self, obj):
+        self._keep.append(obj)
+        return obj
+
+    def _bind(self, op):
+        lib = self.lib
+        if isinstance(op, ToNHWC):
+            bb, c, h, w = self.prog.inputs[op.src]
+            t = self._ref(self.tensor(op.out))
+            self.input_slots.setdefault(op.src, []).append((len(self.calls), 0))
+            self.calls.append(("ffcb_nchw_to_nhwc", lib.ffcb_nchw_to_nhwc, [None, bb, c, h, w, C.byref(t)]))
+        elif isinstance(op, ToNCHW):
+            t = self._ref(self.tensor(op.inp))
+            self.calls.append(("ffcb_nhwc_to_nchw", lib.ffcb_nhwc_to_nchw,
+                               [C.byref(t), self.outputs[op.dst].data_ptr()]))
+        elif isinstance(op, StemOp):
+            bb, c, h, w = self.prog.inputs[op.src]
+            t = self._ref(self.tensor(op.out))
+            self._keep += [op.w, op.shift]
+            self.input_slots.setdefault(op.src, []).append((len(self.calls), 0))
+            self.calls.append(("ffcb_stem_conv7", lib.ffcb_stem_conv7,
+                               [None, bb, c, h, w, op.w.data_ptr(), op.shift.data_ptr(), op.w.shape[1], C.byref(t)]))
+        elif isinstance(op, HeadOp):
+            t = self._ref(self.tensor(op.inp))
+            self._keep += [op.w, op.bias]
+            self.calls.append(("ffcb_head_conv7", lib.ffcb_head_conv7,
+                               [C.byref(t), op.w.data_ptr(), op.bias.data_ptr(), op.n_out, op.act,
+                                self.outputs[op.dst].data_ptr()]))
+        elif isinstance(op, ConvOp):
+            d = self._ref(L.ConvDesc())
+            pk = op.packed
+            d.inp[0] = self.tensor(op.ins[0])
+            if op.ins[1] is not None:
+                d.inp[1] = self.tensor(op.ins[1])
+            d.out = self.tensor(op.out)
+            if op.addend is not None:
+                d.addend = self.tensor(op.addend)
+            if self.prog.math == L.MATH_BF16X3:
+                wt = pk.split_weights()
+            else:
+                wt = pk.w_kn
+            self._keep.append(wt)
+            d.weight = wt.data_ptr()
+            if pk.shift is not None:
+                self._keep.append(pk.shift)
+                d.shift = pk.shift.data_ptr()
+            d.n_out, d.stride, d.border, d.act = pk.n_out, pk.stride, pk.border, pk.act
+            d.nseg, d.math, d.addend_post = len(pk.segs), self.prog.math, int(op.addend_post)
+            for i, s in enumerate(pk.segs):
+                d.seg[i] = L.KSeg(s.src, s.dy, s.dx, s.c0, s.nch)
+            self.calls.append(("ffcb_conv:" + op.tag, lib.ffcb_conv, [C.byref(d)]))
+        elif isinstance(op, RfftOp):
+            a, s = self._ref(self.tensor(op.inp)), self._ref(self.tensor(op.spec))
+            self.calls.append(("ffcb_rfft2", lib.ffcb_rfft2, [C.byref(a), C.byref(s), self.ws.data_ptr(), self.ws_bytes]))
+        elif isinstance(op, IrfftOp):
+            s, o = self._ref(self.tensor(op.spec)), self._ref(self.tensor(op.out))
+            r = C.byref(self._ref(self.tensor(op.residual))) if op.residual is not None else None
+            self.calls.append(("ffcb_irfft2", lib.ffcb_irfft2, [C.byref(s), r, C.byref(o), self.ws.data_ptr(), self.ws_bytes]))
+        else:
+            raise TypeError(op)
+
+    def run(self, inputs: Dict[str, torch.Tensor], stream: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """Issue every call on ``stream`` (default: torch's current stream).  Outputs are the
+        executor's own tensors (overwritten by the next run)."""
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        for name, slots in self.input_slots.items():
+            t = inputs[name]
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == tuple(
+                self.prog.inputs[name]), f"input {name}: expected contiguous float32 {self.prog.inputs[name]}"
+            for ci, ai in slots:
+                self.calls[ci][2][ai] = t.data_ptr()
+        for name, fn, args in self.calls:
+            rc = fn(*args, stream)
+            if rc != 0:
+                L.check(rc, name)
+        return self.outputs
+
+    @property
+    def launches_per_run(self) -> int:
+        n = 0
+        for name, _fn, _a in self.calls:
+            n += 2 if name in ("ffcb_rfft2", "ffcb_irfft2") else 1
+        return n
+
+
+class GraphedProgram:
+    """CUDA-graph replay of an executor with static input tensors (bench / serving path)."""
+
+    def __init__(self, ex: CudaExecutor, warmup: int = 2):
+        self.ex = ex
+        self.static_in = {k: torch.empty(v, dtype=torch.float32, device=ex.device) for k, v in ex.prog.inputs.items()}
+        side = torch.cuda.Stream(device=ex.device)
+        side.wait_stream(torch.cuda.current_stream(ex.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                ex.run(self.static_in)
+        torch.cuda.current_stream(ex.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            ex.run(self.static_in)
+
+    def __call__(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        for k, t in inputs.items():
+            self.static_in[k].copy_(t, non_blocking=True)
+        self.graph.replay()
+        return self.ex.outputs
+
+
+# ---------------------------------------------------------------------------- module entry point
+def _weights_signature(module) -> Tuple:
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+def get_executor(module, kind: str, tensors, math: Optional[int] = None) -> CudaExecutor:
+    math = default_math() if math is None else math
+    shapes = tuple(tuple(t.shape) if torch.is_tensor(t) else None for t in tensors)
+    dev = next(t for t in tensors if torch.is_tensor(t)).device
+    key = (kind, shapes, str(dev), math)
+    cache = module.__dict__.setdefault("_ffcb_programs", {})
+    sig = _weights_signature(module)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    with torch.no_grad():
+        prog = build_module_program(module, kind, shapes, math)
+    ex = CudaExecutor(prog, dev)
+    if len(cache) > 8:
+        cache.clear()
+    cache[key] = (sig, ex)
+    return ex
+
+
+def run_module(module, kind: str, tensors):
+    """Execute ``module`` natively on NCHW float CUDA tensors; returns fresh tensors (or the int 0
+    for an empty FFC side)."""
+    ex = get_executor(module, kind, tensors)
+    feed = {}
+    i = 0
+    for t in tensors:
+        if torch.is_tensor(t):
+            feed[f"x{i}"] = t.contiguous()
+            i += 1
+    outs = ex.run(feed)
+    y0 = outs["y0"].clone() if "y0" in outs else 0
+    if kind in ("ffc_bn_act", "resnet_block"):
+        return y0, (outs["y1"].clone() if "y1" in outs else 0)
+    return (y0,)

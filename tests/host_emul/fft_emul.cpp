@@ -1,0 +1,145 @@
+// Host emulation of the FFT kernels' arithmetic (lama_b200/csrc/fft_core.cuh compiled with g++).
+// For each (H, W) it runs rfft2 -> spectrum and spectrum -> irfft2 the way fft.cu orchestrates
+// the passes (two-for-one rows, column pass, C2R rule) for ONE lane and checks against a
+// double-precision DFT.  Exit code 0 = all sizes within tolerance.  Usage: fft_emul [verbose]
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../lama_b200/csrc/fft_core.cuh"
+
+using namespace ffcb::fftc;
+typedef std::complex<double> cd;
+
+static std::vector<float2> twiddles(int n) {
+  std::vector<float2> tw(n);
+  for (int t = 0; t < n; ++t) {
+    // device: sincospif(2t/n) in float
+    float a = 2.0f * (float)t / (float)n;
+    tw[t] = make_float2((float)cos(M_PI * (double)a), (float)-sin(M_PI * (double)a));
+  }
+  return tw;
+}
+
+template <int N, bool INV>
+static float2* run_pow2(float2* a, float2* b, const float2* tw) {
+  const int nw = workers_for(N);
+  for (int w = 0; w < nw; ++w) stockham_pass<N, 0, INV, 1>(a, b, tw, 0, w, nw);
+  if (Plan<N>::P == 1) return b;
+  for (int w = 0; w < nw; ++w) stockham_pass<N, 1, INV, 1>(b, a, tw, 0, w, nw);
+  if (Plan<N>::P == 2) return a;
+  for (int w = 0; w < nw; ++w) stockham_pass<N, 2, INV, 1>(a, b, tw, 0, w, nw);
+  return b;
+}
+
+template <bool INV>
+static float2* run_any(int n, float2* a, float2* b, const float2* tw) {
+  bool pow2 = (n & (n - 1)) == 0 && n >= 4 && n <= 256;
+  if (pow2) {
+    switch (n) {
+      case 4: return run_pow2<4, INV>(a, b, tw);
+      case 8: return run_pow2<8, INV>(a, b, tw);
+      case 16: return run_pow2<16, INV>(a, b, tw);
+      case 32: return run_pow2<32, INV>(a, b, tw);
+      case 64: return run_pow2<64, INV>(a, b, tw);
+      case 128: return run_pow2<128, INV>(a, b, tw);
+      case 256: return run_pow2<256, INV>(a, b, tw);
+    }
+  }
+  const int nw = 8;
+  for (int w = 0; w < nw; ++w) dft_pass<INV, 1>(a, b, tw, n, 0, w, nw);
+  return b;
+}
+
+static double check(int H, int W, bool verbose) {
+  const int wf = W / 2 + 1;
+  std::vector<float> x(H * W);
+  for (auto& v : x) v = (float)(rand() / (double)RAND_MAX * 2.0 - 1.0);
+  // ---- forward (rfft_rows_kernel + fft_cols_fwd_kernel)
+  std::vector<float2> ws(H * wf), spec(H * wf);
+  auto tww = twiddles(W), twh = twiddles(H);
+  std::vector<float2> a(std::max(H, W)), b(std::max(H, W));
+  for (int y0 = 0; y0 < H; y0 += 2) {
+    const bool row1 = y0 + 1 < H;
+    for (int xx = 0; xx < W; ++xx) a[xx] = make_float2(x[y0 * W + xx], row1 ? x[(y0 + 1) * W + xx] : 0.f);
+    const float2* r = run_any<false>(W, a.data(), b.data(), tww.data());
+    for (int k = 0; k < wf; ++k) {
+      float2 p, q;
+      r2c_pair_post<1>(r, W, k, 0, p, q);
+      ws[y0 * wf + k] = p;
+      if (row1) ws[(y0 + 1) * wf + k] = q;
+    }
+  }
+  const float scale = (float)(1.0 / std::sqrt((double)H * W));
+  for (int k = 0; k < wf; ++k) {
+    for (int y = 0; y < H; ++y) a[y] = ws[y * wf + k];
+    const float2* r = run_any<false>(H, a.data(), b.data(), twh.data());
+    for (int y = 0; y < H; ++y) spec[y * wf + k] = make_float2(r[y].x * scale, r[y].y * scale);
+  }
+  double err_f = 0, mag = 0;
+  for (int ky = 0; ky < H; ++ky)
+    for (int kx = 0; kx < wf; ++kx) {
+      cd acc = 0;
+      for (int y = 0; y < H; ++y)
+        for (int xx = 0; xx < W; ++xx)
+          acc += (double)x[y * W + xx] * std::polar(1.0, -2 * M_PI * ((double)ky * y / H + (double)kx * xx / W));
+      acc /= std::sqrt((double)H * W);
+      err_f = std::max(err_f, std::abs(acc - cd(spec[ky * wf + kx].x, spec[ky * wf + kx].y)));
+      mag = std::max(mag, std::abs(acc));
+    }
+  // ---- inverse on a NON-Hermitian spectrum (post-ReLU like): fft_cols_inv_kernel + irfft_rows_kernel
+  std::vector<float2> z(H * wf);
+  for (auto& v : z) v = make_float2(std::max(0.f, (float)(rand() / (double)RAND_MAX * 2 - 1)),
+                                    std::max(0.f, (float)(rand() / (double)RAND_MAX * 2 - 1)));
+  for (int k = 0; k < wf; ++k) {
+    for (int y = 0; y < H; ++y) a[y] = z[y * wf + k];
+    const float2* r = run_any<true>(H, a.data(), b.data(), twh.data());
+    for (int y = 0; y < H; ++y) ws[y * wf + k] = r[y];
+  }
+  std::vector<float> out(H * W);
+  for (int y0 = 0; y0 < H; y0 += 2) {
+    const bool row1 = y0 + 1 < H;
+    for (int k = 0; k < wf; ++k)
+      c2r_pair_pre<1>(a.data(), W, k, 0, ws[y0 * wf + k], row1 ? ws[(y0 + 1) * wf + k] : make_float2(0.f, 0.f));
+    const float2* r = run_any<true>(W, a.data(), b.data(), tww.data());
+    for (int xx = 0; xx < W; ++xx) {
+      out[y0 * W + xx] = r[xx].x * scale;
+      if (row1) out[(y0 + 1) * W + xx] = r[xx].y * scale;
+    }
+  }
+  // reference: inverse along H (all columns), then C2R along W dropping Im of bins 0 and W/2
+  double err_i = 0, mag_i = 0;
+  std::vector<cd> t(H * wf);
+  for (int k = 0; k < wf; ++k)
+    for (int y = 0; y < H; ++y) {
+      cd acc = 0;
+      for (int q = 0; q < H; ++q) acc += cd(z[q * wf + k].x, z[q * wf + k].y) * std::polar(1.0, 2 * M_PI * (double)q * y / H);
+      t[y * wf + k] = acc / std::sqrt((double)H);
+    }
+  for (int y = 0; y < H; ++y)
+    for (int n = 0; n < W; ++n) {
+      double acc = t[y * wf].real();
+      const int last = (W % 2 == 0) ? wf - 1 : wf;
+      for (int k = 1; k < last; ++k) acc += 2.0 * (t[y * wf + k] * std::polar(1.0, 2 * M_PI * (double)k * n / W)).real();
+      if (W % 2 == 0) acc += t[y * wf + wf - 1].real() * ((n % 2) ? -1.0 : 1.0);
+      acc /= std::sqrt((double)W);
+      err_i = std::max(err_i, std::abs(acc - (double)out[y * W + n]));
+      mag_i = std::max(mag_i, std::abs(acc));
+    }
+  const double rel = std::max(err_f / mag, err_i / mag_i);
+  if (verbose) printf("H=%3d W=%3d  fwd %.2e / %.2e   inv %.2e / %.2e\n", H, W, err_f, mag, err_i, mag_i);
+  return rel;
+}
+
+int main(int argc, char** argv) {
+  const bool verbose = argc > 1;
+  const int sizes[][2] = {{4, 4}, {8, 8}, {16, 16}, {32, 32}, {64, 64}, {128, 128}, {256, 256}, {8, 32}, {64, 16},
+                          {256, 4}, {15, 15}, {6, 9}, {20, 24}, {5, 9}, {7, 6}, {3, 2}, {1, 8}, {2, 2}, {125, 188},
+                          {64, 33}, {9, 64}};
+  double worst = 0;
+  for (auto& s : sizes) worst = std::max(worst, check(s[0], s[1], verbose));
+  printf("worst relative error %.3e\n", worst);
+  return worst < 2e-6 ? 0 : 1;
+}

@@ -1,0 +1,75 @@
+"""TEST INFRASTRUCTURE: interpret a ``lama_b200.engine.Program`` on the CPU with slow torch
+restatements of each op's contract (include/ffc_b200.h).  This checks the *host logic* of the
+product — BN folding, weight packing, K-segment lists, buffer wiring, residual placement,
+sub-pixel phases — against the goldens on the GPU-less build box.  It is not a fallback: the
+product only executes programs through libffc_b200.so (lama_b200.engine.CudaExecutor).
+"""
+import torch
+
+from lama_b200 import _lib as L
+from lama_b200 import engine as E
+from lama_b200.packing import apply_packed_reference
+
+
+class SpecInterpreter:
+    def __init__(self, prog: E.Program):
+        self.prog = prog
+        self.mem = {b.name: torch.full((b.B, b.H, b.W, b.C), float("nan"), dtype=torch.float64) for b in prog.bufs}
+
+    def read(self, tv: E.TV) -> torch.Tensor:
+        t = self.mem[tv.buf.name]
+        if tv.phase is not None:
+            a, b = tv.phase
+            t = t[:, a::2, b::2]
+        return t[..., tv.c0:tv.c0 + tv.channels]
+
+    def write(self, tv: E.TV, val: torch.Tensor):
+        t = self.mem[tv.buf.name]
+        if tv.phase is not None:
+            a, b = tv.phase
+            t[:, a::2, b::2, tv.c0:tv.c0 + tv.channels] = val
+        else:
+            t[..., tv.c0:tv.c0 + tv.channels] = val
+
+    def run(self, inputs):
+        out = {}
+        for op in self.prog.ops:
+            if isinstance(op, E.ToNHWC):
+                self.write(op.out, inputs[op.src].double().permute(0, 2, 3, 1))
+            elif isinstance(op, E.ToNCHW):
+                out[op.dst] = self.read(op.inp).permute(0, 3, 1, 2).contiguous()
+            elif isinstance(op, E.StemOp):
+                x = torch.nn.functional.pad(inputs[op.src].double(), (3, 3, 3, 3), mode="reflect")
+                cin = op.cin
+                w = op.w.double().reshape(7, 7, cin, -1).permute(3, 2, 0, 1)       # [N, Cin, 7, 7]
+                y = torch.nn.functional.conv2d(x, w) + op.shift.double()[None, :, None, None]
+                self.write(op.out, y.clamp_min(0).permute(0, 2, 3, 1))
+            elif isinstance(op, E.HeadOp):
+                x = self.read(op.inp).permute(0, 3, 1, 2)
+                x = torch.nn.functional.pad(x, (3, 3, 3, 3), mode="reflect")
+                w = op.w.double().reshape(op.n_out, 7, 7, -1).permute(0, 3, 1, 2)
+                y = torch.nn.functional.conv2d(x, w, op.bias.double())
+                y = {L.ACT_NONE: y, L.ACT_RELU: y.clamp_min(0), L.ACT_SIGMOID: torch.sigmoid(y),
+                     L.ACT_TANH: torch.tanh(y)}[op.act]
+                out[op.dst] = y
+            elif isinstance(op, E.ConvOp):
+                ins = [self.read(tv) if tv is not None else None for tv in op.ins]
+                assert all(not torch.isnan(t).any() for t in ins if t is not None), f"{op.tag}: reads unwritten data"
+                add = self.read(op.addend).clone() if op.addend is not None else None
+                y = apply_packed_reference(op.packed, ins, op.out.hw, addend=add, addend_post=op.addend_post)
+                self.write(op.out, y)
+            elif isinstance(op, E.RfftOp):
+                x = self.read(op.inp)                                            # [B,H,W,C]
+                f = torch.fft.rfftn(x, dim=(1, 2), norm="ortho")                 # [B,H,Wf,C]
+                self.write(op.spec, torch.view_as_real(f).reshape(*f.shape[:3], -1))   # channel 2c=Re, 2c+1=Im
+            elif isinstance(op, E.IrfftOp):
+                z = self.read(op.spec)
+                zc = torch.view_as_complex(z.reshape(*z.shape[:3], -1, 2).contiguous())
+                h, w = op.out.hw
+                y = torch.fft.irfftn(zc, s=(h, w), dim=(1, 2), norm="ortho")
+                if op.residual is not None:
+                    y = y + self.read(op.residual)
+                self.write(op.out, y)
+            else:
+                raise TypeError(op)
+        return out

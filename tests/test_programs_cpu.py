@@ -1,0 +1,107 @@
+"""Host logic of the product (program building, BN folding, weight packing, buffer wiring) checked
+on the CPU box: programs built by lama_b200.engine from the drop-in modules are interpreted by
+tests/spec_interp.py and compared with the goldens generated from the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from lama_b200 import _lib as L
+from lama_b200 import engine as E
+from lama_b200 import modules as M
+from lama_b200.testing import small_lama_kwargs
+from spec_interp import SpecInterpreter
+
+
+def _load(module, sd):
+    missing, unexpected = module.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing), (missing, unexpected)
+    return module.eval()
+
+
+def _run(module, kind, tensors):
+    shapes = tuple(tuple(t.shape) if torch.is_tensor(t) else None for t in tensors)
+    with torch.no_grad():
+        prog = E.build_module_program(module, kind, shapes, L.MATH_FP32)
+    feed = {f"x{i}": t for i, t in enumerate(t for t in tensors if torch.is_tensor(t))}
+    return SpecInterpreter(prog).run(feed), prog
+
+
+def _close(got, ref, rel=2e-6):
+    scale = float(np.abs(ref).max()) or 1.0
+    err = float(np.abs(got.numpy() - ref.astype(np.float64)).max())
+    assert err <= rel * scale, f"{err:.3e} > {rel:g}*{scale:.3e}"
+
+
+@pytest.mark.parametrize("name,ci,co", [("fu_c8_16x16", 8, 8), ("fu_c4to6_8x32", 4, 6), ("fu_c16_32x32", 16, 16),
+                                        ("fu_c4_15x15", 4, 4), ("fu_c4_6x9", 4, 4)])
+def test_fourier_unit_program(name, ci, co):
+    a, sd = load_golden(name)
+    m = _load(M.FourierUnit(ci, co), sd)
+    if not m.native_supported():
+        pytest.skip("channel count outside the native path")
+    out, _ = _run(m, "fourier_unit", (torch.from_numpy(a["x"]),))
+    _close(out["y0"], a["y"])
+
+
+def test_spectral_transform_program():
+    a, sd = load_golden("st_16to24_8x8")
+    m = _load(M.SpectralTransform(16, 24, enable_lfu=False), sd)
+    assert m.native_supported()
+    out, _ = _run(m, "spectral_transform", (torch.from_numpy(a["x"]),))
+    _close(out["y0"], a["y"])
+
+
+@pytest.mark.parametrize("name,kw,has_g", [
+    ("ffcbnact_32_k3_075", dict(in_channels=32, out_channels=32, kernel_size=3, ratio_gin=0.75, ratio_gout=0.75,
+                                padding=1), True),
+    ("ffcbnact_4to8_k7_local", dict(in_channels=4, out_channels=8, kernel_size=7, ratio_gin=0, ratio_gout=0,
+                                    padding=0), False),
+    ("ffcbnact_16to32_s2_to_global", dict(in_channels=16, out_channels=32, kernel_size=3, ratio_gin=0,
+                                          ratio_gout=0.75, stride=2, padding=1), False),
+])
+def test_ffc_bn_act_program(name, kw, has_g):
+    a, sd = load_golden(name)
+    m = _load(M.FFC_BN_ACT(activation_layer=torch.nn.ReLU, enable_lfu=False, **kw), sd)
+    assert m.native_supported()
+    xl = torch.from_numpy(a["x_l"]); xg = torch.from_numpy(a["x_g"]) if has_g else 0
+    assert E.ffc_bn_act_shapes_ok(m, xl, xg)
+    out, _ = _run(m, "ffc_bn_act", (xl, xg))
+    _close(out["y0"], a["y_l"])
+    if "y_g" in a:
+        _close(out["y1"], a["y_g"])
+
+
+def test_resnet_block_program():
+    a, sd = load_golden("resblock_32_16x16")
+    m = _load(M.FFCResnetBlock(32, padding_type="reflect", norm_layer=torch.nn.BatchNorm2d,
+                               activation_layer=torch.nn.ReLU, ratio_gin=0.75, ratio_gout=0.75, enable_lfu=False), sd)
+    assert m.native_supported()
+    out, prog = _run(m, "resnet_block", (torch.from_numpy(a["x_l"]), torch.from_numpy(a["x_g"])))
+    _close(out["y0"], a["y_l"]); _close(out["y1"], a["y_g"])
+    # two FFC_BN_ACT = 2 x (local conv, conv1, fu conv, global conv) contractions, 2 FFT pairs
+    assert sum(isinstance(o, E.ConvOp) for o in prog.ops) == 8
+    assert sum(isinstance(o, E.RfftOp) for o in prog.ops) == 2
+
+
+@pytest.mark.parametrize("name", ["generator_ngf8_b2_64x64", "generator_ngf8_b2_40x72"])
+def test_generator_program(name):
+    a, _ = load_golden(name)
+    _, sd = load_golden("generator_ngf8_b2_64x64")
+    g = _load(M.FFCResNetGenerator(**small_lama_kwargs(ngf=8, n_blocks=2)), sd)
+    x = torch.from_numpy(a["x"])
+    assert E.generator_supported(g, x)
+    out, prog = _run(g, "generator", (x,))
+    assert float(np.abs(out["y0"].numpy() - a["y"]).max()) < 2e-6
+    # residual blocks run in place on one bottleneck buffer: no per-block output allocation
+    assert not any(b.name.startswith("block.out") for b in prog.bufs)
+
+
+def test_unsupported_options_are_not_native():
+    assert not M.FourierUnit(8, 8, spectral_pos_encoding=True).eval().native_supported()
+    assert not M.FourierUnit(8, 8, fft_norm="backward").eval().native_supported()
+    assert not M.SpectralTransform(16, 16, enable_lfu=True).eval().native_supported()
+    assert not M.FFC_BN_ACT(16, 16, 3, 0.5, 0.5, padding=1, enable_lfu=False, gated=True).eval().native_supported()
+    assert not M.FFC_BN_ACT(16, 16, 3, 0.5, 0.5, padding=2, dilation=2, enable_lfu=False).eval().native_supported()
+    m = M.FFC_BN_ACT(16, 16, 3, 0.5, 0.5, padding=1, enable_lfu=False)
+    assert not m.train().native_supported() and m.eval().native_supported()
