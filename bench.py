@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the big-lama FFCResNetGenerator @512x512 bs32 per GPU (BASELINE.json
+metric), through the drop-in modules -> libffc_b200.so.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--math fp32|bf16x3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one forward pass of the generator over one batch of 32 synthetic 512x512 (image, mask)
+pairs per GPU (weak scaling: every rank runs its own shard, no data-path collective; NCCL is used
+only for the barrier and the max-over-ranks of the device time).
+
+Reported on one JSON line by rank 0:
+  value        images/s, inputs resident in HBM, CUDA-graph replay of the whole program, CUDA events
+  e2e          same metric through the public module call with HOST (pinned) inputs: H2D of the
+               (B,4,512,512) float input and D2H of the (B,3,512,512) result inside the timed region
+  roofline     dominant kernel (the resblock local 3x3 contraction) vs the measured tensor peak, plus
+               "fourier_unit": the FU sub-path (rfft2 -> pointwise GEMM -> irfft2) vs the HBM roofline
+               with SURVEY.md §8(d)'s algorithmic bytes
+  cpu_baseline the oracle's torch-CPU port (the reference's own operator sequence) on this box's host cores
+`--impl reference` times that CPU port alone (bounded sample per step) as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 32
+SIZE = 512
+METRIC = "images/sec FFCResNetGenerator @512x512 bs32"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        mx = max(int(float(r[2])) for r in self.rows if len(r) >= 8)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 8 and r[4 + i].lower().startswith("active")
+                                                         for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_step(images, threads=None):
+    """One bounded sample of the workload on the host: the oracle's torch-CPU port of the reference
+    generator on `images` 512x512 inputs.  Returns (seconds, n_images)."""
+    import torch
+    from oracle import ffc_torch_cpu as otc
+    from lama_b200.testing import BIG_LAMA_KWARGS
+    st = cpu_reference_step.state
+    x = st["x"][:images]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        otc.ffc_resnet_generator(x, st["sd"], **BIG_LAMA_KWARGS)
+    return time.perf_counter() - t0, images
+
+
+def _cpu_setup():
+    import torch
+    from lama_b200 import modules as M
+    from lama_b200.testing import BIG_LAMA_KWARGS, seeded_parameters_, synthetic_image_mask, generator_input
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = seeded_parameters_(M.FFCResNetGenerator(**BIG_LAMA_KWARGS).eval(), 0)
+    img, mask = synthetic_image_mask(4, SIZE, 0)
+    cpu_reference_step.state = {"sd": {k: v for k, v in g.state_dict().items()}, "x": generator_input(img, mask)}
+    return cores
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU path (oracle torch-CPU port; the reference tree itself cannot
+    travel to the GPU box) on all host threads.  Rank 0 only."""
+    if rank != 0:
+        return
+    cores = _cpu_setup()
+    per_step = 2          # images per step: bounded so K steps finish within minutes
+    for _ in range(args.warmup):
+        cpu_reference_step(1)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _n = cpu_reference_step(per_step)
+        t += dt
+    v = per_step * args.steps / t
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "big-lama FFCResNetGenerator fwd, 512x512, seeded random weights",
+                   "per_step_images": per_step, "device": "cpu"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} images/step x {args.steps} steps, torch-CPU port of ffc.py (oracle/ffc_torch_cpu.py)"},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--math", default=os.environ.get("LAMA_B200_MATH", "fp32"), choices=["fp32", "bf16x3"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--size", type=int, default=SIZE)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    os.environ["LAMA_B200_MATH"] = args.math
+    os.environ["LAMA_B200_STRICT"] = "1"
+    from lama_b200 import _lib as L
+    from lama_b200 import engine as E
+    from lama_b200 import modules as M
+    from lama_b200.testing import BIG_LAMA_KWARGS, seeded_parameters_, synthetic_image_mask, generator_input
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    lib = L.get_lib()
+    math = {"fp32": L.MATH_FP32, "bf16x3": L.MATH_BF16X3}[args.math]
+    B, S = args.batch, args.size
+
+    gen = seeded_parameters_(M.FFCResNetGenerator(**BIG_LAMA_KWARGS).eval(), 0).to(dev)
+    img, mask = synthetic_image_mask(B, S, seed=rank)
+    x_host = generator_input(img, mask).pin_memory()
+    x_dev = x_host.to(dev)
+    y_host = torch.empty(B, 3, S, S).pin_memory()
+
+    ex = E.get_executor(gen, "generator", (x_dev,), math=math)
+    graphed = E.GraphedProgram(ex, warmup=2)
+    graphed.static_in["x0"].copy_(x_dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident throughput (graph replay of the whole program)
+    for _ in range(args.warmup):
+        graphed.graph.replay()
+    with ClockSampler(local) as clk:
+        ms = timed(graphed.graph.replay, args.steps)
+    clocks = clk.summary()
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public module call with host buffers
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        with torch.no_grad():
+            y = gen(xd)
+        y_host.copy_(y, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+
+    # ---- dominant kernel + FourierUnit sub-path, timed alone with CUDA events on the launch stream
+    conv_idx = [i for i, (n, _f, _a) in enumerate(ex.calls) if n.startswith("ffcb_conv:convl2l+convg2l")]
+    fu_idx = [i for i, (n, _f, _a) in enumerate(ex.calls) if n == "ffcb_rfft2"]
+    sc = stream.cuda_stream
+
+    def run_calls(idx):
+        for i in idx:
+            n, fn, a = ex.calls[i]
+            rc = fn(*a, sc)
+            if rc:
+                L.check(rc, n)
+    peaks = _peaks()
+    roof = None
+    if conv_idx and rank == 0:
+        i0 = conv_idx[len(conv_idx) // 2]
+        reps = 10
+        run_calls([i0] * 3)
+        ms_c = timed(lambda: run_calls([i0]), reps) / reps
+        h = S // 8
+        flops = 2.0 * B * h * h * 128 * (9 * 512)
+        ach = flops / (ms_c * 1e-3) / 1e12
+        roof = {"kernel": "conv_simt_kernel" if math == L.MATH_FP32 else "conv_tc_kernel",
+                "op": "resblock local 3x3 contraction (convl2l+convg2l+bn_l+relu): M=B*64*64, N=128, K=9*512",
+                "bound": "tensor", "achieved": ach, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_burst"], "traffic": None, "ms_per_launch": ms_c,
+                "algorithmic_flops_per_launch": flops, "peak_source": peaks["source"] + ", bf16 burst",
+                "note": "fp32 CUDA-core arm (FFCB_MATH_FP32)" if math == L.MATH_FP32 else
+                        "bf16x3 tcgen05 arm: 3 bf16 products per algorithmic MAC"}
+        if fu_idx:
+            j = fu_idx[len(fu_idx) // 2]
+            fu_calls = [j, j + 1, j + 2]       # rfft2, fu conv, irfft2 (emit_fourier_unit order)
+            run_calls(fu_calls * 3)
+            ms_f = timed(lambda: run_calls(fu_calls), reps) / reps
+            c = 192
+            fu_bytes = 4.0 * B * h * h * (c + c) + 4.0 * (2 * c) * (2 * c) + 8.0 * (2 * c)
+            gbs = fu_bytes / (ms_f * 1e-3) / 1e9
+            roof["fourier_unit"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": gbs / peaks["hbm_gbs"], "ms": ms_f, "algorithmic_bytes": fu_bytes,
+                                    "shape": [B, c, h, h], "launches": 5,
+                                    "note": "warm L2 between repetitions of the same FU; intermediates (spectrum) not counted"}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample on all host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = _cpu_setup()
+        cpu_reference_step(1)
+        n_img, t = 0, 0.0
+        while t < 10.0 and n_img < 16:
+            dt, n = cpu_reference_step(2)
+            t += dt; n_img += n
+        cpu = {"value": n_img / t, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"{n_img} images of 512x512 in batches of 2, torch-CPU port of the reference ops "
+                         f"(oracle/ffc_torch_cpu.py), {cores} threads"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if math == L.MATH_FP32 else "bf16x3(f32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": f"big-lama FFCResNetGenerator fwd (configs[2]), bs{B}/GPU {S}x{S}, seeded random weights",
+                       "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "math": args.math, "l2": "inputs+activations (>4 GB/step) exceed the 126 MB L2; no explicit flush",
+                       "cuda_graph": True},
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 * 1,
+                    "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": ex.launches_per_run * args.steps,
+            "launches_per_step": ex.launches_per_run,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -524,6 +524,12 @@ class CudaExecutor:
         self._keep.append(obj)
         return obj
 
+    def _dev(self, t: torch.Tensor) -> torch.Tensor:
+        """Packed parameter on the executor's device, kept alive with the executor."""
+        t = t.to(self.device).contiguous()
+        self._keep.append(t)
+        return t
+
     def _bind(self, op):
         lib = self.lib
         if isinstance(op, ToNHWC):
@@ -538,15 +544,15 @@ class CudaExecutor:
         elif isinstance(op, StemOp):
             bb, c, h, w = self.prog.inputs[op.src]
             t = self._ref(self.tensor(op.out))
-            self._keep += [op.w, op.shift]
+            wd, sd = self._dev(op.w), self._dev(op.shift)
             self.input_slots.setdefault(op.src, []).append((len(self.calls), 0))
             self.calls.append(("ffcb_stem_conv7", lib.ffcb_stem_conv7,
-                               [None, bb, c, h, w, op.w.data_ptr(), op.shift.data_ptr(), op.w.shape[1], C.byref(t)]))
+                               [None, bb, c, h, w, wd.data_ptr(), sd.data_ptr(), wd.shape[1], C.byref(t)]))
         elif isinstance(op, HeadOp):
             t = self._ref(self.tensor(op.inp))
-            self._keep += [op.w, op.bias]
+            wd, bd = self._dev(op.w), self._dev(op.bias)
             self.calls.append(("ffcb_head_conv7", lib.ffcb_head_conv7,
-                               [C.byref(t), op.w.data_ptr(), op.bias.data_ptr(), op.n_out, op.act,
+                               [C.byref(t), wd.data_ptr(), bd.data_ptr(), op.n_out, op.act,
                                 self.outputs[op.dst].data_ptr()]))
         elif isinstance(op, ConvOp):
             d = self._ref(L.ConvDesc())
@@ -561,11 +567,9 @@ class CudaExecutor:
                 wt = pk.split_weights()
             else:
                 wt = pk.w_kn
-            self._keep.append(wt)
-            d.weight = wt.data_ptr()
+            d.weight = self._dev(wt).data_ptr()
             if pk.shift is not None:
-                self._keep.append(pk.shift)
-                d.shift = pk.shift.data_ptr()
+                d.shift = self._dev(pk.shift).data_ptr()
             d.n_out, d.stride, d.border, d.act = pk.n_out, pk.stride, pk.border, pk.act
             d.nseg, d.math, d.addend_post = len(pk.segs), self.prog.math, int(op.addend_post)
             for i, s in enumerate(pk.segs):

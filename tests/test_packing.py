@@ -1,0 +1,92 @@
+"""CPU: weight packing / BN folding / sub-pixel phase decomposition against torch's own operators,
+and the drop-in modules' state_dict schema against the reference's."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lama_b200 import _lib as L
+from lama_b200 import modules as M
+from lama_b200 import packing as P
+from lama_b200.testing import BIG_LAMA_KWARGS, seeded_parameters_
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_conv_transpose_phases_equal_torch():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 8, 5, 7, generator=g, dtype=torch.float64)
+    ct = torch.nn.ConvTranspose2d(8, 12, 3, stride=2, padding=1, output_padding=1).double()
+    bn = torch.nn.BatchNorm2d(12).double()
+    seeded_parameters_(bn, 1); seeded_parameters_(ct, 2, gain=1.0)
+    bn.eval()
+    want = torch.relu(bn(ct(x)))
+    sc, sh = P.bn_scale_shift(bn)
+    got = torch.zeros(2, 10, 14, 12, dtype=torch.float64)
+    for a, b, pk in P.pack_conv_transpose_phases(ct.weight, ct.bias, sc, sh, act=L.ACT_RELU):
+        got[:, a::2, b::2] = P.apply_packed_reference(pk, [x.permute(0, 2, 3, 1), None], (5, 7))
+    np.testing.assert_allclose(got.permute(0, 3, 1, 2).detach().numpy(), want.detach().numpy(), atol=2e-6)
+
+
+def test_pack_conv_reflect_stride2_equals_torch():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 8, 10, 12, generator=g, dtype=torch.float64)
+    conv = torch.nn.Conv2d(8, 16, 3, stride=2, padding=1, padding_mode="reflect", bias=False).double()
+    bn = seeded_parameters_(torch.nn.BatchNorm2d(16).double(), 3).eval()
+    want = torch.relu(bn(conv(x)))
+    sc, sh = P.bn_scale_shift(bn)
+    pk = P.pack_conv([(conv.weight, 0, 0, 1)], sc, sh, stride=2, act=L.ACT_RELU)
+    got = P.apply_packed_reference(pk, [x.permute(0, 2, 3, 1), None], (5, 6))
+    np.testing.assert_allclose(got.permute(0, 3, 1, 2).detach().numpy(), want.detach().numpy(), atol=2e-6)
+
+
+def test_split_bf16_precision():
+    x = torch.randn(10000, generator=torch.Generator().manual_seed(2)) * 37.0
+    s = P.split_bf16(x)
+    rec = s[0].float() + s[1].float()
+    assert float(((rec - x).abs() / x.abs().clamp_min(1e-30)).max()) <= 2.0 ** -16
+
+
+def test_state_dict_schema_matches_reference():
+    """989 generator entries for big-lama; load_checkpoint uses strict=False, so
+    key/shape drift would be silent — compare against the reference class when its tree is present,
+    and always against the committed schema."""
+    g = M.FFCResNetGenerator(**BIG_LAMA_KWARGS)
+    ours = {k: tuple(v.shape) for k, v in g.state_dict().items()}
+    assert len(ours) == 989
+    schema_path = os.path.join(ROOT, "tests", "golden", "big_lama_state_dict_schema.json")
+    from oracle import ref_import
+    if ref_import.available():
+        ref = ref_import.load_reference_ffc().FFCResNetGenerator(**BIG_LAMA_KWARGS)
+        theirs = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+        assert ours == theirs
+        ref.load_state_dict(g.state_dict(), strict=True)
+        g.load_state_dict(ref.state_dict(), strict=True)
+        if not os.path.isfile(schema_path):
+            with open(schema_path, "w") as fh:
+                json.dump({k: list(v) for k, v in theirs.items()}, fh)
+    with open(schema_path) as fh:
+        committed = {k: tuple(v) for k, v in json.load(fh).items()}
+    assert ours == committed
+    assert g.model[5].conv1.ffc.global_in_num == 384        # read by ffc.py:279 / refinement
+    assert isinstance(g.model, torch.nn.Sequential) and len(g.model) == 36
+
+
+def test_module_torch_composition_matches_reference_on_cpu():
+    """Feature-fallback path (CPU tensors / unsupported options) is the reference's operator sequence."""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    ffc = ref_import.load_reference_ffc()
+    kw = dict(in_channels=32, out_channels=32, kernel_size=3, ratio_gin=0.75, ratio_gout=0.75, padding=1,
+              activation_layer=torch.nn.ReLU, enable_lfu=True)
+    ref = seeded_parameters_(ffc.FFC_BN_ACT(**kw).eval(), 5)
+    ours = M.FFC_BN_ACT(**kw).eval()
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    xl, xg = torch.randn(1, 8, 8, 8), torch.randn(1, 24, 8, 8)
+    with torch.no_grad():
+        a, b = ref((xl, xg)); c, d = ours((xl, xg))
+    assert torch.allclose(a, c, atol=1e-6) and torch.allclose(b, d, atol=1e-6)
