@@ -1,8 +1,502 @@
-// tcgen05 arm of ffcb_conv() — placeholder until the TMA/tcgen05 kernel lands.
+// tcgen05 arm of ffcb_conv() (FFCB_MATH_BF16X3): implicit-GEMM convolution on the 5th-gen tensor
+// cores of sm_100a.
+//
+//   D[128 pixels x BN] (fp32, TMEM)  +=  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo        per 64-channel K block
+//
+// Operands are "split bf16" (value = hi + lo, include/ffc_b200.h): three bf16 products with fp32
+// accumulation carry ~16 mantissa bits per operand (vs 8 for plain bf16, 11 for tf32) at 1.5x the
+// tensor-pipe time of one TF32 product and the same operand bytes as fp32.
+//
+// Data movement: every operand tile is one TMA box (cp.async.bulk.tensor, 128-byte swizzle) —
+//   activations: 5-D map (C, W+2p, H+2p, B, plane) over the reflect-ring-padded NHWC buffer; the tile of
+//                tap (dy,dx) is the same box shifted by (dx,dy); stride-2 convs use elementStrides=2;
+//                zero-border convs map the interior only and let TMA zero-fill out-of-bounds;
+//                dense 1x1 inputs (spectra, W/2+1 columns) use a flat 3-D map (C, B*H*W, plane);
+//   weights    : 3-D map (Kpad, N, plane), K-major.
+// Warp roles (256 threads, persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = MMA issuer
+// (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> shift /
+// addend / activation -> split-bf16 or fp32 NHWC stores, incl. the reflect ring).  Two TMEM accumulator
+// stages let the epilogue of tile i overlap the main loop of tile i+1.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace ffcb {
-int conv_tc(const ffcb_conv_desc*, cudaStream_t) {
-  set_error("conv: FFCB_MATH_BF16X3 not available in this build");
-  return FFCB_EINVAL;
+namespace {
+
+constexpr int BM = 128;          // pixels per tile (UMMA M)
+constexpr int BK = 64;           // bf16 channels per K block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;
+constexpr int kTileABytes = BM * BK * 2;   // 16 KB per plane
+constexpr int kMaxStages = 8;
+constexpr int kAccStages = 2;
+constexpr int kAccStride = 256;  // TMEM columns between accumulator stages
+
+struct TcParams {
+  View out, addend;
+  const float* shift;
+  int N, act, addend_post;
+  int BN, num_n_tiles;
+  long long num_m_tiles;
+  int stages;
+  int flat;                  // 1: M = B*H*W flattened (dense 1x1), 0: spatial TW x TH tiles
+  int TW, TH, tiles_x, tiles_y;
+  int stride;
+  int coord_off[2];          // +1 when in[src] is mapped with its border ring
+  int nseg;
+  ffcb_kseg seg[FFCB_MAX_KSEG];
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (sm_100: version 1).
+// rows are 128 B apart, 8-row core-matrix groups 1024 B apart (SBO); LBO unused for swizzled K-major.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);         // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                           // leading byte offset (ignored)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN.
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+struct TileCoord {
+  int b, y0, x0;       // spatial: first output pixel of the tile
+  long long m0;        // flat: first flattened pixel
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, long long m_tile) {
+  TileCoord t;
+  if (p.flat) {
+    t.m0 = m_tile * BM;
+    t.b = 0; t.y0 = 0; t.x0 = 0;
+  } else {
+    const int per_img = p.tiles_x * p.tiles_y;
+    t.b = (int)(m_tile / per_img);
+    const int r = (int)(m_tile - (long long)t.b * per_img);
+    t.y0 = (r / p.tiles_x) * p.TH;
+    t.x0 = (r % p.tiles_x) * p.TW;
+    t.m0 = 0;
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap map_in0,
+               const __grid_constant__ CUtensorMap map_in1, const __grid_constant__ CUtensorMap map_w) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: stages of [A_hi | A_lo | W_hi | W_lo], then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int w_bytes = p.BN * BK * 2;
+  const int stage_bytes = 2 * kTileABytes + 2 * w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* acc_full = bars + 2 * kMaxStages;
+  uint64_t* acc_empty = acc_full + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_in0);
+    prefetch_tmap(&map_in1);
+    prefetch_tmap(&map_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < kAccStages; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // K blocks of the whole contraction
+  int total_kblocks = 0;
+  for (int s = 0; s < p.nseg; ++s) total_kblocks += (p.seg[s].nch + BK - 1) / BK;
+  const long long num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer (one lane)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_tile = (int)(t / p.num_m_tiles);
+        const TileCoord tc = tile_coord(p, t % p.num_m_tiles);
+        int kb = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const ffcb_kseg g = p.seg[s];
+          const CUtensorMap* map = g.src ? &map_in1 : &map_in0;
+          const int nblk = (g.nch + BK - 1) / BK;
+          const int cx = tc.x0 * p.stride + g.dx + p.coord_off[g.src];
+          const int cy = tc.y0 * p.stride + g.dy + p.coord_off[g.src];
+          for (int j = 0; j < nblk; ++j, ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* st = smem + (size_t)stage * stage_bytes;
+            mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+            const int cc = g.c0 + j * BK;
+            if (p.flat) {
+              tma_load_3d(st, map, &full[stage], cc, (int)tc.m0, 0);
+              tma_load_3d(st + kTileABytes, map, &full[stage], cc, (int)tc.m0, 1);
+            } else {
+              tma_load_5d(st, map, &full[stage], cc, cx, cy, tc.b, 0);
+              tma_load_5d(st + kTileABytes, map, &full[stage], cc, cx, cy, tc.b, 1);
+            }
+            tma_load_3d(st + 2 * kTileABytes, &map_w, &full[stage], kb * BK, n_tile * p.BN, 0);
+            tma_load_3d(st + 2 * kTileABytes + w_bytes, &map_w, &full[stage], kb * BK, n_tile * p.BN, 1);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (one lane)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+        for (int kb = 0; kb < total_kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t a_hi = make_smem_desc(st);
+          const uint64_t a_lo = make_smem_desc(st + kTileABytes);
+          const uint64_t w_hi = make_smem_desc(st + 2 * kTileABytes);
+          const uint64_t w_lo = make_smem_desc(st + 2 * kTileABytes + w_bytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per UMMA_K inside the swizzle row
+            umma_bf16(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+            umma_bf16(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
+            umma_bf16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+          }
+          umma_commit(&empty[stage]);                 // smem stage reusable once these MMAs retire
+          if (kb == total_kblocks - 1) umma_commit(&acc_full[acc]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================ epilogue (128 threads = 128 TMEM lanes)
+    const int wq = warp - 4;                 // TMEM lane quarter this warp may access
+    const int row = wq * 32 + lane;          // accumulator row = pixel within the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int HW = p.out.H * p.out.W;
+    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int n_tile = (int)(t / p.num_m_tiles);
+      const TileCoord tc = tile_coord(p, t % p.num_m_tiles);
+      int b, y, x;
+      bool valid;
+      if (p.flat) {
+        const long long m = tc.m0 + row;
+        valid = m < (long long)p.out.B * HW;
+        const long long mm = valid ? m : 0;
+        b = (int)(mm / HW);
+        const int r = (int)(mm - (long long)b * HW);
+        y = r / p.out.W;
+        x = r - y * p.out.W;
+      } else {
+        b = tc.b;
+        y = tc.y0 + row / p.TW;
+        x = tc.x0 + row % p.TW;
+        valid = y < p.out.H && x < p.out.W;
+      }
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kAccStride);
+      const long long o_out = valid ? pix_off(p.out, b, y, x) : 0;
+      const long long o_add = (valid && p.addend.ptr) ? pix_off(p.addend, b, y, x) : 0;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + (uint32_t)c0, r);
+        const int nbase = n_tile * p.BN + c0;
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int n = nbase + 4 * q;
+            if (n < p.N) {
+              float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                     __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+              if (p.shift != nullptr) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(p.shift + n));
+                v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+              }
+              float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.addend.ptr != nullptr) ad = load4(p.addend, o_add + n);
+              if (!p.addend_post) { v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w; }
+              v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
+              v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+              if (p.addend_post) { v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w; }
+              if (p.out.pad && p.out.reflect_border) store4_with_border(p.out, b, y, x, n, v);
+              else store4(p.out, o_out + n, v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[acc]);
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int encode(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+           const cuuint32_t* box, const cuuint32_t* estr, const char* what) {
+  EncodeTiledFn fn = get_encode();
+  if (fn == nullptr) {
+    set_error("conv(tc): cuTensorMapEncodeTiled entry point unavailable");
+    return FFCB_ECUDA;
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv(tc): cuTensorMapEncodeTiled(%s) failed with CUresult %d (rank %d, dims %llu %llu %llu, box %u %u %u)",
+              what, (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
+    return FFCB_ECUDA;
+  }
+  return FFCB_OK;
+}
+
+int pick_bn(int n) {
+  if (n <= 256) return (n + 31) / 32 * 32;
+  if (n % 192 == 0) return 192;
+  return 256;
+}
+
+}  // namespace
+
+int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
+  // ---- requirements of this arm (the fp32 arm has none of them)
+  FFCB_REQUIRE(d->out.B > 0, "conv(tc): empty batch");
+  bool used[2] = {false, false}, taps[2] = {false, false};
+  for (int i = 0; i < d->nseg; ++i) {
+    used[d->seg[i].src] = true;
+    if (d->seg[i].dx != 0 || d->seg[i].dy != 0) taps[d->seg[i].src] = true;
+    FFCB_REQUIRE(d->seg[i].c0 % 8 == 0, "conv(tc): segment %d starts at channel %d (must be a multiple of 8)", i,
+                 d->seg[i].c0);
+  }
+  for (int s = 0; s < 2; ++s) {
+    if (!used[s]) continue;
+    const ffcb_tensor& t = d->in[s];
+    FFCB_REQUIRE(t.fmt == FFCB_BF16X2, "conv(tc): in[%d] must be split bf16 (FFCB_BF16X2)", s);
+    FFCB_REQUIRE(t.sx % 8 == 0 && t.sy % 8 == 0 && t.sb % 8 == 0 && t.lo_off % 8 == 0 && ((uintptr_t)t.ptr % 16) == 0,
+                 "conv(tc): in[%d] strides / pointer not 16-byte aligned", s);
+    if (taps[s] && d->border == FFCB_BORDER_REFLECT)
+      FFCB_REQUIRE(t.pad == 1 && t.reflect_border, "conv(tc): in[%d] needs a reflected border ring (pad=1)", s);
+  }
+
+  TcParams p;
+  p.out = make_view(d->out);
+  p.addend = d->addend.ptr ? make_view(d->addend) : null_view();
+  p.shift = d->shift;
+  p.N = d->n_out; p.act = d->act; p.addend_post = d->addend_post;
+  p.BN = pick_bn(d->n_out);
+  p.num_n_tiles = (d->n_out + p.BN - 1) / p.BN;
+  p.stride = d->stride;
+  p.nseg = d->nseg;
+  int kpad = 0;
+  for (int i = 0; i < d->nseg; ++i) {
+    p.seg[i] = d->seg[i];
+    kpad += (d->seg[i].nch + BK - 1) / BK * BK;
+  }
+
+  // ---- tiling: flat when every tap is (0,0) on dense unit-stride inputs, else spatial TW x TH
+  const int H = d->out.H, W = d->out.W;
+  bool flat = d->stride == 1 && !taps[0] && !taps[1];
+  for (int s = 0; s < 2 && flat; ++s) {
+    if (!used[s]) continue;
+    const ffcb_tensor& t = d->in[s];
+    flat = t.H == H && t.W == W && t.sy == (int64_t)W * t.sx && t.sb == (int64_t)H * t.sy;
+  }
+  p.flat = flat ? 1 : 0;
+  if (flat) {
+    p.TW = BM; p.TH = 1; p.tiles_x = p.tiles_y = 1;
+    p.num_m_tiles = ((long long)d->out.B * H * W + BM - 1) / BM;
+  } else {
+    int tw = 1;
+    while (tw < W && tw < BM) tw <<= 1;      // smallest power of two >= W, capped at 128
+    p.TW = tw; p.TH = BM / tw;
+    p.tiles_x = (W + p.TW - 1) / p.TW;
+    p.tiles_y = (H + p.TH - 1) / p.TH;
+    p.num_m_tiles = (long long)d->out.B * p.tiles_x * p.tiles_y;
+    FFCB_REQUIRE(p.TW * d->stride <= 256 && p.TH * d->stride <= 256, "conv(tc): tile exceeds the TMA box limit");
+  }
+
+  // ---- tensor maps
+  alignas(64) CUtensorMap maps[3];
+  int rc;
+  for (int s = 0; s < 2; ++s) {
+    if (!used[s]) { maps[s] = maps[0]; p.coord_off[s] = 0; continue; }
+    const ffcb_tensor& t = d->in[s];
+    const cuuint64_t esz = 2;
+    if (flat) {
+      cuuint64_t dims[3] = {(cuuint64_t)t.C, (cuuint64_t)t.B * t.H * t.W, 2};
+      cuuint64_t str[2] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.lo_off * esz};
+      cuuint32_t box[3] = {BK, BM, 1}, es[3] = {1, 1, 1};
+      p.coord_off[s] = 0;
+      if ((rc = encode(&maps[s], t.ptr, 3, dims, str, box, es, "flat activations"))) return rc;
+    } else {
+      const bool ring = taps[s] && d->border == FFCB_BORDER_REFLECT;
+      const int off = ring ? 1 : 0;
+      char* base = (char*)t.ptr - (ring ? ((int64_t)t.sy + t.sx) * (int64_t)esz : 0);
+      cuuint64_t dims[5] = {(cuuint64_t)t.C, (cuuint64_t)(t.W + 2 * off), (cuuint64_t)(t.H + 2 * off),
+                            (cuuint64_t)t.B, 2};
+      cuuint64_t str[4] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.sy * esz, (cuuint64_t)t.sb * esz,
+                           (cuuint64_t)t.lo_off * esz};
+      cuuint32_t box[5] = {BK, (cuuint32_t)(p.TW * d->stride), (cuuint32_t)(p.TH * d->stride), 1, 1};
+      cuuint32_t es[5] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1, 1};
+      p.coord_off[s] = off;
+      if ((rc = encode(&maps[s], base, 5, dims, str, box, es, "spatial activations"))) return rc;
+    }
+  }
+  if (!used[0]) maps[0] = maps[1];
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)kpad, (cuuint64_t)d->n_out, 2};
+    cuuint64_t str[2] = {(cuuint64_t)kpad * 2, (cuuint64_t)kpad * d->n_out * 2};
+    cuuint32_t box[3] = {BK, (cuuint32_t)p.BN, 1}, es[3] = {1, 1, 1};
+    FFCB_REQUIRE(((uintptr_t)d->weight % 16) == 0, "conv(tc): weight pointer not 16-byte aligned");
+    if ((rc = encode(&maps[2], const_cast<void*>(d->weight), 3, dims, str, box, es, "weights"))) return rc;
+  }
+
+  // ---- launch
+  const int stage_bytes = 2 * kTileABytes + 2 * p.BN * BK * 2;
+  const int bar_bytes = (2 * kMaxStages + 2 * kAccStages) * 8 + 16;
+  int stages = (227 * 1024 - 1024 - bar_bytes) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  FFCB_REQUIRE(stages >= 2, "conv(tc): BN=%d leaves fewer than 2 pipeline stages", p.BN);
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + bar_bytes + 1024;
+  FFCB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  int dev = 0, sms = 148;
+  FFCB_CUDA(cudaGetDevice(&dev));
+  FFCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  conv_tc_kernel<<<grid, kThreads, smem, stream>>>(p, maps[0], maps[1], maps[2]);
+  FFCB_LAUNCH_CHECK("conv_tc_kernel");
+  return FFCB_OK;
+}
+
 }  // namespace ffcb

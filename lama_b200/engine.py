@@ -120,6 +120,12 @@ class IrfftOp:
 
 
 @dataclass
+class BorderOp:
+    """(Re)build the reflected ring of a padded buffer after a producer that does not write it."""
+    view: TV
+
+
+@dataclass
 class Program:
     kind: str
     math: int
@@ -128,12 +134,14 @@ class Program:
     inputs: Dict[str, Tuple[int, ...]] = field(default_factory=dict)    # name -> NCHW shape
     outputs: Dict[str, Tuple[int, ...]] = field(default_factory=dict)
 
-    def buf(self, name, B, H, W, C, consumer_is_gemm=False) -> Buf:
-        # FFCB_MATH_BF16X3: operands of tcgen05 contractions are stored as split bf16 with a
-        # reflected border ring; everything else stays float32.
-        tc = self.math == L.MATH_BF16X3 and consumer_is_gemm
-        b = Buf(f"{name}#{len(self.bufs)}", B, H, W, C, pad=1 if tc else 0, fmt=L.BF16X2 if tc else L.F32,
-                reflect_border=1 if tc else 0)
+    def buf(self, name, B, H, W, C, gemm=False, halo=False) -> Buf:
+        """``gemm``: the buffer is an operand of a contraction; ``halo``: that contraction has spatial taps.
+        FFCB_MATH_BF16X3 stores gemm operands as split bf16, and gives halo buffers a reflected border
+        ring so that the TMA box of tap (dy,dx) is the tile shifted by (dx,dy); everything else (FFT
+        inputs, spectra leaving the GEMM, the head's input) stays float32 without padding."""
+        tc = self.math == L.MATH_BF16X3 and gemm
+        ring = 1 if (tc and halo) else 0
+        b = Buf(f"{name}#{len(self.bufs)}", B, H, W, C, pad=ring, fmt=L.BF16X2 if tc else L.F32, reflect_border=ring)
         self.bufs.append(b)
         return b
 
@@ -305,7 +313,7 @@ def emit_fourier_unit(prog: Program, fu, t: TV, out: TV, residual: Optional[TV])
     h, w = t.hw
     wf = w // 2 + 1
     cin2, cout2 = fu.conv_layer.in_channels, fu.conv_layer.out_channels
-    S = prog.buf("spectrum", b, h, wf, cin2, consumer_is_gemm=True)
+    S = prog.buf("spectrum", b, h, wf, cin2, gemm=True)
     Z = prog.buf("spectrum_out", b, h, wf, cout2)
     prog.ops.append(RfftOp(t, TV(S)))
     scale, shift = P.bn_scale_shift(fu.bn)
@@ -323,7 +331,7 @@ def emit_spectral_transform(prog: Program, st, x: TV, u_consumer=None) -> Tuple[
     c = st.conv1[0].out_channels
     dev = st.conv2.weight.device
     T = prog.buf("st.t", b, h, w, c)
-    U = prog.buf("st.u", b, h, w, c, consumer_is_gemm=True)
+    U = prog.buf("st.u", b, h, w, c, gemm=True)
     s1, b1 = P.bn_scale_shift(st.conv1[1])
     pk1 = P.pack_conv([(st.conv1[0].weight, 0, x.c0, 0)], s1, b1, act=L.ACT_RELU, device=dev)
     prog.ops.append(ConvOp(pk1, [TV(x.buf), None], TV(T), tag="st.conv1+bn+relu"))
@@ -346,7 +354,7 @@ def emit_ffc_bn_act(prog: Program, m, X: Buf, in_cl: int, in_cg: int, residual: 
     out_cg = f.convl2g.out_channels if not isinstance(f.convl2g, nn.Identity) else 0
     ho, wo = (X.H + 2 * p - k) // s + 1, (X.W + 2 * p - k) // s + 1
     if Y is None:
-        Y = prog.buf("ffc.out", X.B, ho, wo, out_cl + out_cg, consumer_is_gemm=True)
+        Y = prog.buf("ffc.out", X.B, ho, wo, out_cl + out_cg, gemm=True, halo=True)
     act_l, act_g = _act_code(m.act_l), _act_code(m.act_g)
     sl, bl = _fold(m.bn_l, out_cl, dev)
     sg, bg = _fold(m.bn_g, out_cg, dev)
@@ -388,7 +396,7 @@ def emit_resnet_block(prog: Program, blk, X: Buf, cl: int, cg: int, in_place: bo
     """FFCResnetBlock (ffc.py:277-292): X <- X + conv2(conv1(X)).  With ``in_place`` the second
     FFC_BN_ACT writes its result over X (each output pixel only reads its own residual pixel)."""
     Y, ycl, ycg = emit_ffc_bn_act(prog, blk.conv1, X, cl, cg)
-    out = X if in_place else prog.buf("block.out", X.B, X.H, X.W, X.C, consumer_is_gemm=True)
+    out = X if in_place else prog.buf("block.out", X.B, X.H, X.W, X.C, gemm=True, halo=True)
     emit_ffc_bn_act(prog, blk.conv2, Y, ycl, ycg, residual=X, Y=out)
     return out
 
@@ -408,7 +416,7 @@ def build_module_program(module, kind: str, shapes: Sequence[Optional[Tuple[int,
     elif kind == "spectral_transform":
         b, c, h, w = shapes[0]
         prog.inputs["x0"] = shapes[0]
-        X = prog.buf("in", b, h, w, c, consumer_is_gemm=True)
+        X = prog.buf("in", b, h, w, c, gemm=True)
         prog.ops.append(ToNHWC("x0", TV(X)))
         U = emit_spectral_transform(prog, module, TV(X))
         co = module.conv2.out_channels
@@ -421,7 +429,7 @@ def build_module_program(module, kind: str, shapes: Sequence[Optional[Tuple[int,
         b, cl, h, w = sl
         cg = sg[1] if sg is not None else 0
         prog.inputs["x0"] = sl
-        X = prog.buf("in", b, h, w, cl + cg, consumer_is_gemm=True)
+        X = prog.buf("in", b, h, w, cl + cg, gemm=True, halo=True)
         prog.ops.append(ToNHWC("x0", TV(X, 0, cl)))
         if cg:
             prog.inputs["x1"] = sg
@@ -439,6 +447,9 @@ def build_module_program(module, kind: str, shapes: Sequence[Optional[Tuple[int,
         build_generator_program(prog, module, shapes[0])
     else:
         raise ValueError(kind)
+    if math == L.MATH_BF16X3 and not tc_compatible(prog):
+        return build_module_program(module, kind, shapes, L.MATH_FP32)
+    insert_border_ops(prog)
     return prog
 
 
@@ -453,7 +464,7 @@ def build_generator_program(prog: Program, gen, shape):
     n0 = conv.out_channels
     s0, b0 = P.bn_scale_shift(stem.bn_l)
     wst, shst = P.pack_stem(conv.weight, s0, b0, device=dev)
-    X = prog.buf("stem", b, h, w, n0, consumer_is_gemm=True)
+    X = prog.buf("stem", b, h, w, n0, gemm=True, halo=True)
     prog.ops.append(StemOp("x0", cin, wst, shst, TV(X)))
     cl, cg = n0, 0
     for d in downs:
@@ -461,15 +472,53 @@ def build_generator_program(prog: Program, gen, shape):
     for blk in blocks:
         X = emit_resnet_block(prog, blk, X, cl, cg, in_place=True)
     # ConcatTupleLayer (ffc.py:295-302) is free: x_l | x_g already share X.
-    for ct, bn in ups:
+    for iu, (ct, bn) in enumerate(ups):
         sc, sh = P.bn_scale_shift(bn)
-        Yb = prog.buf("up", b, X.H * 2, X.W * 2, ct.out_channels, consumer_is_gemm=True)
+        last = iu == len(ups) - 1          # the head is a CUDA-core kernel: keep its input float32
+        Yb = prog.buf("up", b, X.H * 2, X.W * 2, ct.out_channels, gemm=not last, halo=not last)
         for a, bb, pk in P.pack_conv_transpose_phases(ct.weight, ct.bias, sc, sh, act=L.ACT_RELU, device=dev):
             prog.ops.append(ConvOp(pk, [TV(X), None], TV(Yb, phase=(a, bb)), tag=f"convT phase {a}{bb}+bn+relu"))
         X = Yb
     wh, bh = P.pack_head(head.weight, head.bias, device=dev)
     prog.ops.append(HeadOp(TV(X), wh, bh, head.out_channels, out_act, "y0"))
     prog.outputs["y0"] = (b, head.out_channels, h, w)
+
+
+def tc_compatible(prog: Program) -> bool:
+    """The tcgen05 arm needs 16-byte aligned bf16 pixels/slices: channel counts and slice starts in
+    multiples of 8.  Programs that do not qualify run the fp32 CUDA-core arm (still native)."""
+    for op in prog.ops:
+        if isinstance(op, ConvOp):
+            for tv in op.ins:
+                if tv is not None and (tv.buf.C % 8 or tv.c0 % 8):
+                    return False
+            if any(sg.c0 % 8 for sg in op.packed.segs):
+                return False
+    return True
+
+
+def insert_border_ops(prog: Program):
+    """Append a BorderOp after every producer that leaves the reflected ring of a padded buffer stale:
+    layout conversions, the stem, FFT outputs, and sub-pixel (phase) convolutions.  tcgen05 convolutions
+    writing whole rows/columns refresh the ring in their own epilogue."""
+    out = []
+    ops = prog.ops
+    for i, op in enumerate(ops):
+        out.append(op)
+        tv = None
+        if isinstance(op, (ToNHWC, StemOp)):
+            tv = op.out
+        elif isinstance(op, IrfftOp):
+            tv = op.out
+        elif isinstance(op, RfftOp):
+            tv = op.spec
+        elif isinstance(op, ConvOp) and (op.out.phase is not None or prog.math == L.MATH_FP32):
+            nxt = ops[i + 1] if i + 1 < len(ops) else None
+            same = isinstance(nxt, ConvOp) and nxt.out.buf is op.out.buf and nxt.out.phase is not None
+            tv = None if (op.out.phase is not None and same) else op.out
+        if tv is not None and tv.buf.reflect_border:
+            out.append(BorderOp(TV(tv.buf)))
+    prog.ops = out
 
 
 # ------------------------------------------------------------------------------------- executor
@@ -518,6 +567,8 @@ class CudaExecutor:
         t.lo_off = b.B * hp * wp * b.C if b.fmt == L.BF16X2 else 0
         t.B, t.H, t.W, t.C = b.B, h, w, tv.channels
         t.fmt, t.pad, t.reflect_border = b.fmt, b.pad, b.reflect_border
+        if tv.phase is not None:     # a sub-pixel phase is not a contiguous image: no ring semantics
+            t.pad, t.reflect_border = 0, 0
         return t
 
     def _ref(self, obj):
@@ -575,6 +626,9 @@ class CudaExecutor:
             for i, s in enumerate(pk.segs):
                 d.seg[i] = L.KSeg(s.src, s.dy, s.dx, s.c0, s.nch)
             self.calls.append(("ffcb_conv:" + op.tag, lib.ffcb_conv, [C.byref(d)]))
+        elif isinstance(op, BorderOp):
+            t = self._ref(self.tensor(op.view))
+            self.calls.append(("ffcb_fill_reflect_border", lib.ffcb_fill_reflect_border, [C.byref(t)]))
         elif isinstance(op, RfftOp):
             a, s = self._ref(self.tensor(op.inp)), self._ref(self.tensor(op.spec))
             self.calls.append(("ffcb_rfft2", lib.ffcb_rfft2, [C.byref(a), C.byref(s), self.ws.data_ptr(), self.ws_bytes]))

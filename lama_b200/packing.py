@@ -56,8 +56,19 @@ class PackedConv:
         return sum(s.nch for s in self.segs)
 
     def split_weights(self) -> torch.Tensor:
+        """bf16 [2][N][Kpad]: K-major, every segment zero-padded to a multiple of 64 channels (one
+        128-byte swizzle row per K block of the tcgen05 arm)."""
         if self.w_split is None:
-            self.w_split = split_bf16(self.w_kn.t().contiguous())
+            w_nk = self.w_kn.t()
+            cols, k0 = [], 0
+            for s in self.segs:
+                blk = w_nk[:, k0:k0 + s.nch]
+                padk = (-s.nch) % 64
+                if padk:
+                    blk = torch.cat([blk, blk.new_zeros(blk.shape[0], padk)], dim=1)
+                cols.append(blk)
+                k0 += s.nch
+            self.w_split = split_bf16(torch.cat(cols, dim=1).contiguous())
         return self.w_split
 
 
@@ -102,6 +113,8 @@ def pack_conv(parts: Sequence[Tuple[torch.Tensor, int, int, int]], scale: Option
         w_kn = w_kn.to(device)
         sh = sh.to(device) if sh is not None else None
     assert len(segs) <= L.MAX_KSEG, f"{len(segs)} K-segments exceed FFCB_MAX_KSEG"
+    if all(pad == 0 for _w, _s, _c, pad in parts):
+        border = L.BORDER_ZERO      # no tap ever leaves the interior; the border mode is moot
     return PackedConv(segs=segs, n_out=n_out, w_kn=w_kn, shift=sh, stride=stride, border=border, act=act)
 
 

@@ -58,6 +58,8 @@ class SpecInterpreter:
                 add = self.read(op.addend).clone() if op.addend is not None else None
                 y = apply_packed_reference(op.packed, ins, op.out.hw, addend=add, addend_post=op.addend_post)
                 self.write(op.out, y)
+            elif isinstance(op, E.BorderOp):
+                pass        # the interpreter's buffers have no physical ring (taps use index math)
             elif isinstance(op, E.RfftOp):
                 x = self.read(op.inp)                                            # [B,H,W,C]
                 f = torch.fft.rfftn(x, dim=(1, 2), norm="ortho")                 # [B,H,Wf,C]

@@ -105,3 +105,42 @@ def test_unsupported_options_are_not_native():
     assert not M.FFC_BN_ACT(16, 16, 3, 0.5, 0.5, padding=2, dilation=2, enable_lfu=False).eval().native_supported()
     m = M.FFC_BN_ACT(16, 16, 3, 0.5, 0.5, padding=1, enable_lfu=False)
     assert not m.train().native_supported() and m.eval().native_supported()
+
+
+def test_bf16x3_program_layout_and_semantics():
+    """FFCB_MATH_BF16X3 programs: GEMM operands are split-bf16, 3x3 operands carry a reflected ring,
+    FFT inputs / spectra leaving the GEMM / the head input stay float32, ring-less producers are
+    followed by a BorderOp — and the op list still computes the golden output."""
+    a, sd = load_golden("generator_ngf8_b2_64x64")
+    g = _load(M.FFCResNetGenerator(**small_lama_kwargs(ngf=8, n_blocks=2)), sd)
+    x = torch.from_numpy(a["x"])
+    with torch.no_grad():
+        prog = E.build_module_program(g, "generator", (tuple(x.shape),), L.MATH_BF16X3)
+    assert prog.math == L.MATH_BF16X3 and E.tc_compatible(prog)
+    by = {b.name.split("#")[0]: b for b in prog.bufs}
+    assert by["stem"].fmt == L.BF16X2 and by["stem"].pad == 1 and by["stem"].reflect_border == 1
+    assert by["spectrum"].fmt == L.BF16X2 and by["spectrum"].pad == 0
+    assert by["st.u"].fmt == L.BF16X2 and by["st.u"].pad == 0
+    assert by["st.t"].fmt == L.F32 and by["spectrum_out"].fmt == L.F32
+    assert prog.bufs[-1].name.startswith("up") and prog.bufs[-1].fmt == L.F32      # head input
+    ops = prog.ops
+    assert isinstance(ops[0], E.StemOp) and isinstance(ops[1], E.BorderOp)
+    n_border = sum(isinstance(o, E.BorderOp) for o in ops)
+    assert n_border == 1 + 2        # stem + the two split transposed-conv outputs (4 phases each)
+    out = SpecInterpreter(prog).run({"x0": x})
+    assert float(np.abs(out["y0"].numpy() - a["y"]).max()) < 2e-6
+    # weights of the tcgen05 arm: [2][N][Kpad], K padded per segment to 64
+    conv = next(o for o in ops if isinstance(o, E.ConvOp))
+    ws = conv.packed.split_weights()
+    assert ws.dtype == torch.bfloat16 and ws.shape[0] == 2 and ws.shape[2] == 64 * len(conv.packed.segs)
+    rec = (ws[0].float() + ws[1].float())[:, :conv.packed.segs[0].nch]
+    assert torch.allclose(rec, conv.packed.w_kn.t()[:, :conv.packed.segs[0].nch], rtol=2 ** -15, atol=1e-9)
+
+
+def test_tc_incompatible_program_downgrades_to_fp32():
+    a, sd = load_golden("ffcbnact_4to8_k7_local")
+    m = _load(M.FFC_BN_ACT(in_channels=4, out_channels=8, kernel_size=7, ratio_gin=0, ratio_gout=0, padding=0,
+                           activation_layer=torch.nn.ReLU, enable_lfu=False), sd)
+    with torch.no_grad():
+        prog = E.build_module_program(m, "ffc_bn_act", ((1, 4, 22, 22), None), L.MATH_BF16X3)
+    assert prog.math == L.MATH_FP32
