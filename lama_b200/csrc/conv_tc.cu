@@ -32,6 +32,8 @@ constexpr int kTileABytes = BM * BK * 2;   // 16 KB per plane
 constexpr int kMaxStages = 8;
 constexpr int kAccStages = 2;
 constexpr int kAccStride = 256;  // TMEM columns between accumulator stages
+constexpr int kBarBytes = 256;   // mbarriers + TMEM slot (2*8 + 2*2 barriers of 8 B, padded)
+constexpr int kEpiBytes = 4 * 4096;
 
 struct TcParams {
   View out, addend;
@@ -174,6 +176,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   uint64_t* acc_full = bars + 2 * kMaxStages;
   uint64_t* acc_empty = acc_full + kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+  uint8_t* stage_tile = reinterpret_cast<uint8_t*>(bars) + kBarBytes;     // 4 x 4 KB epilogue transposes
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -273,61 +276,79 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
     }
   } else if (warp >= 4) {
     // ================================================================ epilogue (128 threads = 128 TMEM lanes)
+    // TMEM -> registers gives every lane one accumulator ROW (pixel) x 32 columns; writing that out
+    // directly would make each warp store touch 32 different cache lines.  Each warp therefore
+    // transposes the 32x32 block through a private 4 KB swizzled staging tile so that 8 lanes cover the
+    // 128 contiguous bytes of ONE pixel: lane -> (pixel 4i + lane/8, channel quad lane%8), i = 0..7.
     const int wq = warp - 4;                 // TMEM lane quarter this warp may access
-    const int row = wq * 32 + lane;          // accumulator row = pixel within the tile
+    float4* stg = reinterpret_cast<float4*>(stage_tile + (size_t)wq * 4096);
+    const int sub = lane >> 3, cq = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int HW = p.out.H * p.out.W;
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_tile = (int)(t / p.num_m_tiles);
       const TileCoord tc = tile_coord(p, t % p.num_m_tiles);
-      int b, y, x;
-      bool valid;
-      if (p.flat) {
-        const long long m = tc.m0 + row;
-        valid = m < (long long)p.out.B * HW;
-        const long long mm = valid ? m : 0;
-        b = (int)(mm / HW);
-        const int r = (int)(mm - (long long)b * HW);
-        y = r / p.out.W;
-        x = r - y * p.out.W;
-      } else {
-        b = tc.b;
-        y = tc.y0 + row / p.TW;
-        x = tc.x0 + row % p.TW;
-        valid = y < p.out.H && x < p.out.W;
+      // the 8 pixels this lane finishes: accumulator rows wq*32 + 4i + sub
+      int pyx[8];
+      int pb[8];
+      unsigned vmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = wq * 32 + 4 * i + sub;
+        int b, y, x;
+        bool valid;
+        if (p.flat) {
+          const long long m = tc.m0 + row;
+          valid = m < (long long)p.out.B * HW;
+          const long long mm = valid ? m : 0;
+          b = (int)(mm / HW);
+          const int r = (int)(mm - (long long)b * HW);
+          y = r / p.out.W;
+          x = r - y * p.out.W;
+        } else {
+          b = tc.b;
+          y = tc.y0 + row / p.TW;
+          x = tc.x0 + row % p.TW;
+          valid = y < p.out.H && x < p.out.W;
+        }
+        pb[i] = b;
+        pyx[i] = (y << 16) | x;
+        if (valid) vmask |= 1u << i;
       }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kAccStride);
-      const long long o_out = valid ? pix_off(p.out, b, y, x) : 0;
-      const long long o_add = (valid && p.addend.ptr) ? pix_off(p.addend, b, y, x) : 0;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_row + (uint32_t)c0, r);
-        const int nbase = n_tile * p.BN + c0;
-        if (valid) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int n = nbase + 4 * q;
-            if (n < p.N) {
-              float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                     __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-              if (p.shift != nullptr) {
-                const float4 s = __ldg(reinterpret_cast<const float4*>(p.shift + n));
-                v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
-              }
-              float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.addend.ptr != nullptr) ad = load4(p.addend, o_add + n);
-              if (!p.addend_post) { v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w; }
-              v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
-              v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-              if (p.addend_post) { v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w; }
-              if (p.out.pad && p.out.reflect_border) store4_with_border(p.out, b, y, x, n, v);
-              else store4(p.out, o_out + n, v);
-            }
+        for (int j = 0; j < 8; ++j)
+          stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                         __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        const int n = n_tile * p.BN + c0 + 4 * cq;
+        if (n < p.N) {
+          float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.shift != nullptr) sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (!((vmask >> i) & 1u)) continue;
+            const int rr = 4 * i + sub;
+            float4 v = stg[rr * 8 + (cq ^ (rr & 7))];
+            const int y = pyx[i] >> 16, x = pyx[i] & 0xffff;
+            v.x += sh.x; v.y += sh.y; v.z += sh.z; v.w += sh.w;
+            float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.addend.ptr != nullptr) ad = load4(p.addend, pix_off(p.addend, pb[i], y, x) + n);
+            if (!p.addend_post) { v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w; }
+            v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
+            v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+            if (p.addend_post) { v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w; }
+            if (p.out.pad && p.out.reflect_border) store4_with_border(p.out, pb[i], y, x, n, v);
+            else store4(p.out, pix_off(p.out, pb[i], y, x) + n, v);
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
@@ -379,10 +400,13 @@ int encode(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const
   return FFCB_OK;
 }
 
+// N-tile width.  Pipeline depth matters more than tile area here: every stage carries 32 KB of
+// activations (hi+lo) plus 256 B per output column, so BN=128 leaves 3 stages in flight, BN>=192 only 2
+// (measured: 74% vs 35% tensor-pipe utilisation, profiles/r01_launches_bf16x3_v1.txt).
 int pick_bn(int n) {
-  if (n <= 256) return (n + 31) / 32 * 32;
-  if (n % 192 == 0) return 192;
-  return 256;
+  if (n <= 128) return (n + 31) / 32 * 32;
+  if (n == 192) return 96;
+  return 128;
 }
 
 }  // namespace
@@ -482,7 +506,7 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
 
   // ---- launch
   const int stage_bytes = 2 * kTileABytes + 2 * p.BN * BK * 2;
-  const int bar_bytes = (2 * kMaxStages + 2 * kAccStages) * 8 + 16;
+  const int bar_bytes = kBarBytes + kEpiBytes;
   int stages = (227 * 1024 - 1024 - bar_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   FFCB_REQUIRE(stages >= 2, "conv(tc): BN=%d leaves fewer than 2 pipeline stages", p.BN);
