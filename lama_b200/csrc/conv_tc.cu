@@ -27,13 +27,14 @@ namespace {
 constexpr int BM = 128;          // pixels per tile (UMMA M)
 constexpr int BK = 64;           // bf16 channels per K block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;      // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
 constexpr int kTileABytes = BM * BK * 2;   // 16 KB per plane
 constexpr int kMaxStages = 8;
 constexpr int kAccStages = 2;
 constexpr int kAccStride = 256;  // TMEM columns between accumulator stages
 constexpr int kBarBytes = 256;   // mbarriers + TMEM slot (2*8 + 2*2 barriers of 8 B, padded)
-constexpr int kEpiBytes = 4 * 4096;
+constexpr int kEpiBytes = kEpiWarps * 4096;
 
 struct TcParams {
   View out, addend;
@@ -187,7 +188,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < kAccStages; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+    for (int a = 0; a < kAccStages; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], kEpiWarps * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -212,8 +213,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int n_tile = (int)(t / p.num_m_tiles);
-        const TileCoord tc = tile_coord(p, t % p.num_m_tiles);
+        // tile order: N tiles of one pixel tile are adjacent, so the CTAs working on them run
+        // concurrently and share the activation tile through L2 (one DRAM read instead of num_n_tiles)
+        const int n_tile = (int)(t % p.num_n_tiles);
+        const TileCoord tc = tile_coord(p, t / p.num_n_tiles);
         int kb = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const ffcb_kseg g = p.seg[s];
@@ -275,23 +278,28 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       }
     }
   } else if (warp >= 4) {
-    // ================================================================ epilogue (128 threads = 128 TMEM lanes)
-    // TMEM -> registers gives every lane one accumulator ROW (pixel) x 32 columns; writing that out
-    // directly would make each warp store touch 32 different cache lines.  Each warp therefore
-    // transposes the 32x32 block through a private 4 KB swizzled staging tile so that 8 lanes cover the
-    // 128 contiguous bytes of ONE pixel: lane -> (pixel 4i + lane/8, channel quad lane%8), i = 0..7.
-    const int wq = warp - 4;                 // TMEM lane quarter this warp may access
-    float4* stg = reinterpret_cast<float4*>(stage_tile + (size_t)wq * 4096);
+    // ================================================================ epilogue (8 warps)
+    // tcgen05.ld gives every lane one accumulator ROW (pixel) x 32 columns; storing that directly would
+    // make each warp store touch 32 different cache lines.  Each warp therefore transposes its 32x32
+    // block through a private 4 KB swizzled staging tile so that 8 lanes cover the 128 contiguous bytes
+    // of ONE pixel: lane -> (pixel 4i + lane/8, channel quad lane%8), i = 0..7.  Warps e and e+4 share a
+    // TMEM lane quarter and alternate over the 32-column chunks.  Loads (addend), math and stores of
+    // the 8 pixels are branch-free so that the 8 (16 for split bf16) global loads are in flight together.
+    const int e = warp - 4;
+    const int wq = e & 3;                    // TMEM lane quarter (== warp id % 4, the hardware rule)
+    const int half = e >> 2;
+    float4* stg = reinterpret_cast<float4*>(stage_tile + (size_t)e * 4096);
     const int sub = lane >> 3, cq = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int HW = p.out.H * p.out.W;
+    const bool has_add = p.addend.ptr != nullptr;
+    const bool ring = p.out.pad && p.out.reflect_border;
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int n_tile = (int)(t / p.num_m_tiles);
-      const TileCoord tc = tile_coord(p, t % p.num_m_tiles);
+      const int n_tile = (int)(t % p.num_n_tiles);
+      const TileCoord tc = tile_coord(p, t / p.num_n_tiles);
       // the 8 pixels this lane finishes: accumulator rows wq*32 + 4i + sub
-      int pyx[8];
-      int pb[8];
+      int pyx[8], pb[8];
       unsigned vmask = 0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -311,6 +319,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           y = tc.y0 + row / p.TW;
           x = tc.x0 + row % p.TW;
           valid = y < p.out.H && x < p.out.W;
+          if (!valid) { y = 0; x = 0; }
         }
         pb[i] = b;
         pyx[i] = (y << 16) | x;
@@ -319,7 +328,18 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kAccStride);
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
+        const int n = n_tile * p.BN + c0 + 4 * cq;
+        const bool n_ok = n < p.N;
+        float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n_ok && p.shift != nullptr) sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
+        float4 ad[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_add && n_ok && ((vmask >> i) & 1u))
+            ad[i] = load4(p.addend, pix_off(p.addend, pb[i], pyx[i] >> 16, pyx[i] & 0xffff) + n);
+        }
         uint32_t r[32];
         tmem_ld32(t_row + (uint32_t)c0, r);
 #pragma unroll
@@ -327,28 +347,26 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                          __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         __syncwarp();
-        const int n = n_tile * p.BN + c0 + 4 * cq;
-        if (n < p.N) {
-          float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.shift != nullptr) sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
+        float4 v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (!((vmask >> i) & 1u)) continue;
-            const int rr = 4 * i + sub;
-            float4 v = stg[rr * 8 + (cq ^ (rr & 7))];
-            const int y = pyx[i] >> 16, x = pyx[i] & 0xffff;
-            v.x += sh.x; v.y += sh.y; v.z += sh.z; v.w += sh.w;
-            float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.addend.ptr != nullptr) ad = load4(p.addend, pix_off(p.addend, pb[i], y, x) + n);
-            if (!p.addend_post) { v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w; }
-            v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
-            v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-            if (p.addend_post) { v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w; }
-            if (p.out.pad && p.out.reflect_border) store4_with_border(p.out, pb[i], y, x, n, v);
-            else store4(p.out, pix_off(p.out, pb[i], y, x) + n, v);
-          }
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + sub;
+          v[i] = stg[rr * 8 + (cq ^ (rr & 7))];
         }
         __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 w = v[i];
+          w.x += sh.x; w.y += sh.y; w.z += sh.z; w.w += sh.w;
+          if (!p.addend_post) { w.x += ad[i].x; w.y += ad[i].y; w.z += ad[i].z; w.w += ad[i].w; }
+          w.x = apply_act(w.x, p.act); w.y = apply_act(w.y, p.act);
+          w.z = apply_act(w.z, p.act); w.w = apply_act(w.w, p.act);
+          if (p.addend_post) { w.x += ad[i].x; w.y += ad[i].y; w.z += ad[i].z; w.w += ad[i].w; }
+          if (n_ok && ((vmask >> i) & 1u)) {
+            if (ring) store4_with_border(p.out, pb[i], pyx[i] >> 16, pyx[i] & 0xffff, n, w);
+            else store4(p.out, pix_off(p.out, pb[i], pyx[i] >> 16, pyx[i] & 0xffff) + n, w);
+          }
+        }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);

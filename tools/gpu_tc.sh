@@ -18,3 +18,7 @@ tail -30 $OUT/pytest.log | tee -a $OUT/summary.txt
 echo "== bench bf16x3" | tee -a $OUT/summary.txt
 timeout 600 python bench.py --steps 5 --warmup 3 --math bf16x3 --no-cpu-baseline > $OUT/bench_tc.json 2> $OUT/bench_tc.err; echo "bench rc=$?" | tee -a $OUT/summary.txt
 cat $OUT/bench_tc.json | tee -a $OUT/summary.txt; tail -5 $OUT/bench_tc.err | tee -a $OUT/summary.txt
+if [ "${LAUNCHES:-1}" = "1" ]; then
+  timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv python tools/profile_step.py bf16x3 32 > $OUT/prof1.log 2>&1
+  echo "launch list rc=$?" | tee -a $OUT/summary.txt
+fi
