@@ -18,6 +18,7 @@
 // addend / activation -> split-bf16 or fp32 NHWC stores, incl. the reflect ring).  Two TMEM accumulator
 // stages let the epilogue of tile i overlap the main loop of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -48,6 +49,8 @@ struct TcParams {
   int stride;
   int coord_off[2];          // +1 when in[src] is mapped with its border ring
   int nseg;
+  int debug;                 // bring-up knobs (FFCB_TC_DEBUG): 1 no global ld/st in epilogue, 2 no epilogue work,
+                             // 4 no MMA issue, 8 no activation loads
   ffcb_kseg seg[FFCB_MAX_KSEG];
 };
 
@@ -227,9 +230,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           for (int j = 0; j < nblk; ++j, ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* st = smem + (size_t)stage * stage_bytes;
-            mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+            const bool skip_a = (p.debug & 8) != 0;
+            mbar_expect_tx(&full[stage], (uint32_t)(skip_a ? 2 * w_bytes : stage_bytes));
             const int cc = g.c0 + j * BK;
-            if (p.flat) {
+            if (skip_a) {
+            } else if (p.flat) {
               tma_load_3d(st, map, &full[stage], cc, (int)tc.m0, 0);
               tma_load_3d(st + kTileABytes, map, &full[stage], cc, (int)tc.m0, 1);
             } else {
@@ -264,7 +269,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           const uint64_t w_hi = make_smem_desc(st + 2 * kTileABytes);
           const uint64_t w_lo = make_smem_desc(st + 2 * kTileABytes + w_bytes);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
+          for (int k = 0; k < ((p.debug & 4) ? 0 : BK / UMMA_K); ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per UMMA_K inside the swizzle row
             umma_bf16(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
             umma_bf16(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
@@ -328,9 +333,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kAccStride);
-      for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
+      for (int c0 = half * 32; c0 < ((p.debug & 2) ? 0 : p.BN); c0 += 64) {
         const int n = n_tile * p.BN + c0 + 4 * cq;
-        const bool n_ok = n < p.N;
+        const bool n_ok = n < p.N && !(p.debug & 1);
         float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (n_ok && p.shift != nullptr) sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
         float4 ad[8];
@@ -458,6 +463,10 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   p.num_n_tiles = (d->n_out + p.BN - 1) / p.BN;
   p.stride = d->stride;
   p.nseg = d->nseg;
+  {
+    const char* dbg = getenv("FFCB_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   int kpad = 0;
   for (int i = 0; i < d->nseg; ++i) {
     p.seg[i] = d->seg[i];
