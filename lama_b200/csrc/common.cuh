@@ -138,28 +138,24 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-// Store one output pixel's 4 channels, plus its mirror images in the reflect border ring
-// when the view carries one (pad==1 && reflect_border): border row -1 mirrors row 1, row H
-// mirrors row H-2, likewise columns; corners follow from both.
-__device__ __forceinline__ void store4_with_border(const View& v, int b, int y, int x, int c, float4 r) {
-  store4(v, pix_off(v, b, y, x) + c, r);
-  if (v.pad && v.reflect_border) {
-    const int my = (y == 1) ? -1 : ((y == v.H - 2) ? v.H : -2);   // -2: no mirror
-    const int mx = (x == 1) ? -1 : ((x == v.W - 2) ? v.W : -2);
-    // H==2 (or W==2): pixel 0 is both "H-2" and must mirror to H; pixel 1 mirrors to -1.
-    if (my != -2) store4(v, pix_off(v, b, my, x) + c, r);
-    if (mx != -2) store4(v, pix_off(v, b, y, mx) + c, r);
-    if (my != -2 && mx != -2) store4(v, pix_off(v, b, my, mx) + c, r);
-    if (v.H == 3 && y == 1) {  // row 1 is both second and second-to-last: mirrors to -1 and H
-      store4(v, pix_off(v, b, v.H, x) + c, r);
-      if (mx != -2) store4(v, pix_off(v, b, v.H, mx) + c, r);
-    }
-    if (v.W == 3 && x == 1) {
-      store4(v, pix_off(v, b, y, v.W) + c, r);
-      if (my != -2) store4(v, pix_off(v, b, my, v.W) + c, r);
-      if (v.H == 3 && y == 1) store4(v, pix_off(v, b, v.H, v.W) + c, r);
-    }
-  }
+// Mirror targets of an interior pixel in the reflected border ring of a pad==1 view (H, W >= 4):
+// row 1 also lands on row -1, row H-2 on row H, likewise columns; corners follow from both.
+// Returns false for the ~94% of pixels that have no mirror image.
+__device__ __forceinline__ bool ring_mirrors(const View& v, int y, int x, int& my, int& mx) {
+  my = (y == 1) ? -1 : ((y == v.H - 2) ? v.H : -2);   // -2: none
+  mx = (x == 1) ? -1 : ((x == v.W - 2) ? v.W : -2);
+  return (my != -2) | (mx != -2);
+}
+
+// Out-of-line (keeps the hot epilogue small: the tcgen05 kernel is instruction-cache sensitive).
+static __device__ __noinline__ void store4_ring_copies(const View& v, int b, int y, int x, int my, int mx, int c, float4 r) {
+  if (my != -2) store4(v, pix_off(v, b, my, x) + c, r);
+  if (mx != -2) store4(v, pix_off(v, b, y, mx) + c, r);
+  if (my != -2 && mx != -2) store4(v, pix_off(v, b, my, mx) + c, r);
+}
+
+static __device__ __noinline__ float slow_act(float v, int act) {
+  return act == FFCB_ACT_SIGMOID ? 1.f / (1.f + __expf(-v)) : tanhf(v);
 }
 #endif  // __CUDACC__
 

@@ -15,8 +15,8 @@
 //   weights    : 3-D map (Kpad, N, plane), K-major.
 // Warp roles (256 threads, persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = MMA issuer
 // (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> shift /
-// addend / activation -> split-bf16 or fp32 NHWC stores, incl. the reflect ring).  Two TMEM accumulator
-// stages let the epilogue of tile i overlap the main loop of tile i+1.
+// addend / activation -> split-bf16 or fp32 NHWC stores, incl. the reflect ring).  TMEM accumulator
+// stages (a ring of four 128-column accumulators) let the MMA issuer run up to three tiles ahead of the epilogue.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -32,8 +32,8 @@ constexpr int kThreads = 384;      // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
 constexpr int kTileABytes = BM * BK * 2;   // 16 KB per plane
 constexpr int kMaxStages = 8;
-constexpr int kAccStages = 2;
-constexpr int kAccStride = 256;  // TMEM columns between accumulator stages
+constexpr int kAccStages = 4;     // TMEM accumulator ring: the MMA issuer may run 3 tiles ahead of the epilogue
+constexpr int kAccStride = 128;   // TMEM columns per accumulator stage (BN <= 128)
 constexpr int kBarBytes = 256;   // mbarriers + TMEM slot (2*8 + 2*2 barriers of 8 B, padded)
 constexpr int kEpiBytes = kEpiWarps * 4096;
 
@@ -299,7 +299,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
     uint32_t acc_phase = 0;
     const int HW = p.out.H * p.out.W;
     const bool has_add = p.addend.ptr != nullptr;
-    const bool ring = p.out.pad && p.out.reflect_border;
+    const bool ring = p.out.pad && p.out.reflect_border && p.out.H >= 4 && p.out.W >= 4;   // tiny planes: BorderOp
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_tile = (int)(t % p.num_n_tiles);
       const TileCoord tc = tile_coord(p, t / p.num_n_tiles);
@@ -312,13 +312,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         int b, y, x;
         bool valid;
         if (p.flat) {
-          const long long m = tc.m0 + row;
-          valid = m < (long long)p.out.B * HW;
-          const long long mm = valid ? m : 0;
-          b = (int)(mm / HW);
-          const int r = (int)(mm - (long long)b * HW);
-          y = r / p.out.W;
-          x = r - y * p.out.W;
+          const unsigned m = (unsigned)tc.m0 + (unsigned)row;          // host guarantees B*H*W < 2^31
+          valid = m < (unsigned)(p.out.B * HW);
+          const unsigned mm = valid ? m : 0u;
+          b = (int)(mm / (unsigned)HW);
+          const unsigned r = mm - (unsigned)b * (unsigned)HW;
+          y = (int)(r / (unsigned)p.out.W);
+          x = (int)(r - (unsigned)y * (unsigned)p.out.W);
         } else {
           b = tc.b;
           y = tc.y0 + row / p.TW;
@@ -330,21 +330,25 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         pyx[i] = (y << 16) | x;
         if (valid) vmask |= 1u << i;
       }
+      // addend (residual) loads do not depend on the accumulator: put the first chunk's in flight
+      // before waiting for the MMAs, and the next chunk's while the current one is being stored.
+      const int n_first = n_tile * p.BN + half * 32 + 4 * cq;
+      const int c_end = (p.debug & 2) ? 0 : p.BN;
+      float4 ad[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_add && half * 32 < c_end && n_first < p.N && !(p.debug & 1) && ((vmask >> i) & 1u))
+          ad[i] = load4(p.addend, pix_off(p.addend, pb[i], pyx[i] >> 16, pyx[i] & 0xffff) + n_first);
+      }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kAccStride);
-      for (int c0 = half * 32; c0 < ((p.debug & 2) ? 0 : p.BN); c0 += 64) {
+      for (int c0 = half * 32; c0 < c_end; c0 += 64) {
         const int n = n_tile * p.BN + c0 + 4 * cq;
         const bool n_ok = n < p.N && !(p.debug & 1);
         float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (n_ok && p.shift != nullptr) sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
-        float4 ad[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_add && n_ok && ((vmask >> i) & 1u))
-            ad[i] = load4(p.addend, pix_off(p.addend, pb[i], pyx[i] >> 16, pyx[i] & 0xffff) + n);
-        }
         uint32_t r[32];
         tmem_ld32(t_row + (uint32_t)c0, r);
 #pragma unroll
@@ -352,26 +356,38 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                          __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         __syncwarp();
-        float4 v[8];
+        float4 ad_next[8];
+        const bool more = has_add && (c0 + 64 < c_end) && (n + 64 < p.N) && !(p.debug & 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          ad_next[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (more && ((vmask >> i) & 1u))
+            ad_next[i] = load4(p.addend, pix_off(p.addend, pb[i], pyx[i] >> 16, pyx[i] & 0xffff) + n + 64);
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = 4 * i + sub;
-          v[i] = stg[rr * 8 + (cq ^ (rr & 7))];
+          float4 w = stg[rr * 8 + (cq ^ (rr & 7))];
+          w.x += sh.x; w.y += sh.y; w.z += sh.z; w.w += sh.w;
+          const float4 a = p.addend_post ? make_float4(0.f, 0.f, 0.f, 0.f) : ad[i];
+          w.x += a.x; w.y += a.y; w.z += a.z; w.w += a.w;
+          if (p.act == FFCB_ACT_RELU) {
+            w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f);
+          } else if (p.act != FFCB_ACT_NONE) {
+            w.x = slow_act(w.x, p.act); w.y = slow_act(w.y, p.act);
+            w.z = slow_act(w.z, p.act); w.w = slow_act(w.w, p.act);
+          }
+          if (p.addend_post) { w.x += ad[i].x; w.y += ad[i].y; w.z += ad[i].z; w.w += ad[i].w; }
+          if (n_ok && ((vmask >> i) & 1u)) {
+            const int y = pyx[i] >> 16, x = pyx[i] & 0xffff;
+            store4(p.out, pix_off(p.out, pb[i], y, x) + n, w);
+            int my, mx;
+            if (ring && ring_mirrors(p.out, y, x, my, mx)) store4_ring_copies(p.out, pb[i], y, x, my, mx, n, w);
+          }
         }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 w = v[i];
-          w.x += sh.x; w.y += sh.y; w.z += sh.z; w.w += sh.w;
-          if (!p.addend_post) { w.x += ad[i].x; w.y += ad[i].y; w.z += ad[i].z; w.w += ad[i].w; }
-          w.x = apply_act(w.x, p.act); w.y = apply_act(w.y, p.act);
-          w.z = apply_act(w.z, p.act); w.w = apply_act(w.w, p.act);
-          if (p.addend_post) { w.x += ad[i].x; w.y += ad[i].y; w.z += ad[i].z; w.w += ad[i].w; }
-          if (n_ok && ((vmask >> i) & 1u)) {
-            if (ring) store4_with_border(p.out, pb[i], pyx[i] >> 16, pyx[i] & 0xffff, n, w);
-            else store4(p.out, pix_off(p.out, pb[i], pyx[i] >> 16, pyx[i] & 0xffff) + n, w);
-          }
-        }
+        for (int i = 0; i < 8; ++i) ad[i] = ad_next[i];
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
@@ -437,6 +453,7 @@ int pick_bn(int n) {
 int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   // ---- requirements of this arm (the fp32 arm has none of them)
   FFCB_REQUIRE(d->out.B > 0, "conv(tc): empty batch");
+  FFCB_REQUIRE((long long)d->out.B * d->out.H * d->out.W < (1ll << 31), "conv(tc): more than 2^31 output pixels");
   bool used[2] = {false, false}, taps[2] = {false, false};
   for (int i = 0; i < d->nseg; ++i) {
     used[d->seg[i].src] = true;

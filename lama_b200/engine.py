@@ -512,7 +512,8 @@ def insert_border_ops(prog: Program):
             tv = op.out
         elif isinstance(op, RfftOp):
             tv = op.spec
-        elif isinstance(op, ConvOp) and (op.out.phase is not None or prog.math == L.MATH_FP32):
+        elif isinstance(op, ConvOp) and (op.out.phase is not None or prog.math == L.MATH_FP32
+                                         or op.out.buf.H < 4 or op.out.buf.W < 4):
             nxt = ops[i + 1] if i + 1 < len(ops) else None
             same = isinstance(nxt, ConvOp) and nxt.out.buf is op.out.buf and nxt.out.phase is not None
             tv = None if (op.out.phase is not None and same) else op.out
