@@ -27,11 +27,11 @@ import torch.nn as nn
 from . import _lib as L
 from . import packing as P
 
-MATH_ENV = "LAMA_B200_MATH"     # "fp32" (default for now) | "bf16x3"
+MATH_ENV = "LAMA_B200_MATH"     # "bf16x3" (default: tcgen05 arm) | "fp32" (CUDA-core arm)
 
 
 def default_math() -> int:
-    return {"fp32": L.MATH_FP32, "bf16x3": L.MATH_BF16X3}[os.environ.get(MATH_ENV, "fp32").lower()]
+    return {"fp32": L.MATH_FP32, "bf16x3": L.MATH_BF16X3}[os.environ.get(MATH_ENV, "bf16x3").lower()]
 
 
 # ------------------------------------------------------------------------------------------- IR
