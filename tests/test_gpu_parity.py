@@ -18,8 +18,6 @@ from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
-os.environ["LAMA_B200_STRICT"] = "1"   # an unexpected torch fallback is a test failure
-
 from lama_b200 import _lib as L                      # noqa: E402
 from lama_b200 import engine as E                    # noqa: E402
 from lama_b200 import modules as M                   # noqa: E402
@@ -39,8 +37,10 @@ TOL = {"fp32": 2e-5, "bf16x3": 2e-4}
 def math_mode(request):
     """Every module-level test runs in both arithmetic modes of the library (LAMA_B200_MATH)."""
     os.environ["LAMA_B200_MATH"] = request.param
+    os.environ["LAMA_B200_STRICT"] = "1"      # an unexpected torch fallback is a test failure
     yield request.param
-    os.environ["LAMA_B200_MATH"] = "fp32"
+    os.environ.pop("LAMA_B200_MATH", None)
+    os.environ.pop("LAMA_B200_STRICT", None)
 
 
 def _fp32_only(mode):
