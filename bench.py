@@ -195,7 +195,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev,
+                                timeout=datetime.timedelta(seconds=180))
     lib = L.get_lib()
     math = {"fp32": L.MATH_FP32, "bf16x3": L.MATH_BF16X3}[args.math]
     B, S = args.batch, args.size
@@ -217,16 +219,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
+    def timed(fn, steps, collective=True):
+        """CUDA-event time of `steps` calls.  collective=True (every rank must call it): barrier +
+        synchronize on both sides and the MAX over ranks; collective=False: rank-local measurement
+        (the rank-0-only roofline microbenchmarks — no rank may wait on a collective there)."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
+        if collective:
+            barrier()
+        else:
+            torch.cuda.synchronize(dev)
         e0.record(stream)
         for _ in range(steps):
             fn()
         e1.record(stream)
-        barrier()
+        if collective:
+            barrier()
+        else:
+            torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)
-        if world > 1:
+        if collective and world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
@@ -268,7 +279,7 @@ def main():
         i0 = conv_idx[len(conv_idx) // 2]
         reps = 10
         run_calls([i0] * 3)
-        ms_c = timed(lambda: run_calls([i0]), reps) / reps
+        ms_c = timed(lambda: run_calls([i0]), reps, collective=False) / reps
         h = S // 8
         flops = 2.0 * B * h * h * 128 * (9 * 512)
         ach = flops / (ms_c * 1e-3) / 1e12
@@ -283,7 +294,7 @@ def main():
             j = fu_idx[len(fu_idx) // 2]
             fu_calls = [j, j + 1, j + 2]       # rfft2, fu conv, irfft2 (emit_fourier_unit order)
             run_calls(fu_calls * 3)
-            ms_f = timed(lambda: run_calls(fu_calls), reps) / reps
+            ms_f = timed(lambda: run_calls(fu_calls), reps, collective=False) / reps
             c = 192
             fu_bytes = 4.0 * B * h * h * (c + c) + 4.0 * (2 * c) * (2 * c) + 8.0 * (2 * c)
             gbs = fu_bytes / (ms_f * 1e-3) / 1e9
@@ -322,6 +333,7 @@ def main():
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
