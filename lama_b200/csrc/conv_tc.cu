@@ -34,7 +34,7 @@ constexpr int kTileABytes = BM * BK * 2;   // 16 KB per plane
 constexpr int kMaxStages = 8;
 constexpr int kAccStages = 4;     // TMEM accumulator ring: the MMA issuer may run 3 tiles ahead of the epilogue
 constexpr int kAccStride = 128;   // TMEM columns per accumulator stage (BN <= 128)
-constexpr int kBarBytes = 256;   // mbarriers + TMEM slot (2*8 + 2*2 barriers of 8 B, padded)
+constexpr int kBarBytes = 1024;  // mbarriers + TMEM slot, padded so that the staging tiles stay 1024-byte aligned
 constexpr int kEpiBytes = kEpiWarps * 4096;
 
 struct TcParams {
@@ -48,6 +48,7 @@ struct TcParams {
   int TW, TH, tiles_x, tiles_y;
   int stride;
   int coord_off[2];          // +1 when in[src] is mapped with its border ring
+  int obw, obh;              // epilogue store box of one warp: obw x obh pixels (obw*obh == 32)
   int nseg;
   int debug;                 // bring-up knobs (FFCB_TC_DEBUG): 1 no global ld/st in epilogue, 2 no epilogue work,
                              // 4 no MMA issue, 8 no activation loads
@@ -92,6 +93,20 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -168,7 +183,8 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, long long m_t
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap map_in0,
-               const __grid_constant__ CUtensorMap map_in1, const __grid_constant__ CUtensorMap map_w) {
+               const __grid_constant__ CUtensorMap map_in1, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: stages of [A_hi | A_lo | W_hi | W_lo], then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -180,7 +196,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   uint64_t* acc_full = bars + 2 * kMaxStages;
   uint64_t* acc_empty = acc_full + kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
-  uint8_t* stage_tile = reinterpret_cast<uint8_t*>(bars) + kBarBytes;     // 4 x 4 KB epilogue transposes
+  uint8_t* stage_tile = reinterpret_cast<uint8_t*>(bars) + kBarBytes;     // 8 x 4 KB epilogue staging (1024-B aligned)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -188,6 +204,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
     prefetch_tmap(&map_in0);
     prefetch_tmap(&map_in1);
     prefetch_tmap(&map_w);
+    prefetch_tmap(&map_out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -284,115 +301,132 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
     }
   } else if (warp >= 4) {
     // ================================================================ epilogue (8 warps)
-    // tcgen05.ld gives every lane one accumulator ROW (pixel) x 32 columns; storing that directly would
-    // make each warp store touch 32 different cache lines.  Each warp therefore transposes its 32x32
-    // block through a private 4 KB swizzled staging tile so that 8 lanes cover the 128 contiguous bytes
-    // of ONE pixel: lane -> (pixel 4i + lane/8, channel quad lane%8), i = 0..7.  Warps e and e+4 share a
-    // TMEM lane quarter and alternate over the 32-column chunks.  Loads (addend), math and stores of
-    // the 8 pixels are branch-free so that the 8 (16 for split bf16) global loads are in flight together.
+    // lane == accumulator row == pixel.  Per 32-column chunk: TMEM -> registers, + shift (+ residual),
+    // activation, convert to the output storage (split bf16 hi|lo or fp32) and write the lane's row into
+    // a swizzled 4 KB staging tile; one elected lane then issues ONE TMA store for the warp's
+    // 32-pixel x 32-channel box.  The output tensor map does all address arithmetic, clips partial
+    // tiles / channel tails, and keeps this code small (the kernel is instruction-fetch sensitive).
+    // Warps e and e+4 share a TMEM lane quarter and alternate over the chunks.
     const int e = warp - 4;
     const int wq = e & 3;                    // TMEM lane quarter (== warp id % 4, the hardware rule)
     const int half = e >> 2;
-    float4* stg = reinterpret_cast<float4*>(stage_tile + (size_t)e * 4096);
-    const int sub = lane >> 3, cq = lane & 7;
+    uint8_t* stg = stage_tile + (size_t)e * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int HW = p.out.H * p.out.W;
-    const bool has_add = p.addend.ptr != nullptr;
-    const bool ring = p.out.pad && p.out.reflect_border && p.out.H >= 4 && p.out.W >= 4;   // tiny planes: BorderOp
+    const bool has_add = p.addend.ptr != nullptr && !(p.debug & 1);
+    const bool out_split = p.out.fmt == FFCB_BF16X2;
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_tile = (int)(t % p.num_n_tiles);
       const TileCoord tc = tile_coord(p, t / p.num_n_tiles);
-      // the 8 pixels this lane finishes: accumulator rows wq*32 + 4i + sub
-      int pyx[8], pb[8];
-      unsigned vmask = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = wq * 32 + 4 * i + sub;
-        int b, y, x;
-        bool valid;
-        if (p.flat) {
-          const unsigned m = (unsigned)tc.m0 + (unsigned)row;          // host guarantees B*H*W < 2^31
-          valid = m < (unsigned)(p.out.B * HW);
-          const unsigned mm = valid ? m : 0u;
-          b = (int)(mm / (unsigned)HW);
-          const unsigned r = mm - (unsigned)b * (unsigned)HW;
-          y = (int)(r / (unsigned)p.out.W);
-          x = (int)(r - (unsigned)y * (unsigned)p.out.W);
-        } else {
-          b = tc.b;
-          y = tc.y0 + row / p.TW;
-          x = tc.x0 + row % p.TW;
-          valid = y < p.out.H && x < p.out.W;
-          if (!valid) { y = 0; x = 0; }
-        }
-        pb[i] = b;
-        pyx[i] = (y << 16) | x;
-        if (valid) vmask |= 1u << i;
+      // this lane's pixel (for the residual load) and this warp's store box origin
+      const int row = wq * 32 + lane;
+      int b, y, x;
+      bool valid;
+      if (p.flat) {
+        const unsigned m = (unsigned)tc.m0 + (unsigned)row;            // host guarantees B*H*W < 2^31
+        valid = m < (unsigned)(p.out.B * HW);
+        const unsigned mm = valid ? m : 0u;
+        b = (int)(mm / (unsigned)HW);
+        const unsigned r = mm - (unsigned)b * (unsigned)HW;
+        y = (int)(r / (unsigned)p.out.W);
+        x = (int)(r - (unsigned)y * (unsigned)p.out.W);
+      } else {
+        b = tc.b;
+        y = tc.y0 + row / p.TW;
+        x = tc.x0 + row % p.TW;
+        valid = y < p.out.H && x < p.out.W;
       }
-      // addend (residual) loads do not depend on the accumulator: put the first chunk's in flight
-      // before waiting for the MMAs, and the next chunk's while the current one is being stored.
-      const int n_first = n_tile * p.BN + half * 32 + 4 * cq;
+      const long long o_add = (has_add && valid) ? pix_off(p.addend, b, y, x) : 0;
+      const int box_x = tc.x0 + (wq * 32) % p.TW, box_y = tc.y0 + (wq * 32) / p.TW;
       const int c_end = (p.debug & 2) ? 0 : p.BN;
-      float4 ad[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_add && half * 32 < c_end && n_first < p.N && !(p.debug & 1) && ((vmask >> i) & 1u))
-          ad[i] = load4(p.addend, pix_off(p.addend, pb[i], pyx[i] >> 16, pyx[i] & 0xffff) + n_first);
-      }
+
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kAccStride);
       for (int c0 = half * 32; c0 < c_end; c0 += 64) {
-        const int n = n_tile * p.BN + c0 + 4 * cq;
-        const bool n_ok = n < p.N && !(p.debug & 1);
-        float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (n_ok && p.shift != nullptr) sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
+        const int n0 = n_tile * p.BN + c0;
+        // residual / addend row of this pixel: 32 channels, independent 16-byte loads
+        float ad[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ad[j] = 0.f;
+        if (has_add && valid) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (n0 + 4 * q < p.N) {
+              const float4 a = load4(p.addend, o_add + n0 + 4 * q);
+              ad[4 * q] = a.x; ad[4 * q + 1] = a.y; ad[4 * q + 2] = a.z; ad[4 * q + 3] = a.w;
+            }
+          }
+        }
         uint32_t r[32];
         tmem_ld32(t_row + (uint32_t)c0, r);
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                         __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        __syncwarp();
-        float4 ad_next[8];
-        const bool more = has_add && (c0 + 64 < c_end) && (n + 64 < p.N) && !(p.debug & 1);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          ad_next[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (more && ((vmask >> i) & 1u))
-            ad_next[i] = load4(p.addend, pix_off(p.addend, pb[i], pyx[i] >> 16, pyx[i] & 0xffff) + n + 64);
+        for (int q = 0; q < 8; ++q) {
+          float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.shift != nullptr && n0 + 4 * q < p.N) sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + 4 * q));
+          v[4 * q] = __uint_as_float(r[4 * q]) + sh.x;
+          v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + sh.y;
+          v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + sh.z;
+          v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + sh.w;
         }
+        if (!p.addend_post) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + sub;
-          float4 w = stg[rr * 8 + (cq ^ (rr & 7))];
-          w.x += sh.x; w.y += sh.y; w.z += sh.z; w.w += sh.w;
-          const float4 a = p.addend_post ? make_float4(0.f, 0.f, 0.f, 0.f) : ad[i];
-          w.x += a.x; w.y += a.y; w.z += a.z; w.w += a.w;
-          if (p.act == FFCB_ACT_RELU) {
-            w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f);
-          } else if (p.act != FFCB_ACT_NONE) {
-            w.x = slow_act(w.x, p.act); w.y = slow_act(w.y, p.act);
-            w.z = slow_act(w.z, p.act); w.w = slow_act(w.w, p.act);
-          }
-          if (p.addend_post) { w.x += ad[i].x; w.y += ad[i].y; w.z += ad[i].z; w.w += ad[i].w; }
-          if (n_ok && ((vmask >> i) & 1u)) {
-            const int y = pyx[i] >> 16, x = pyx[i] & 0xffff;
-            store4(p.out, pix_off(p.out, pb[i], y, x) + n, w);
-            int my, mx;
-            if (ring && ring_mirrors(p.out, y, x, my, mx)) store4_ring_copies(p.out, pb[i], y, x, my, mx, n, w);
-          }
+          for (int j = 0; j < 32; ++j) v[j] += ad[j];
         }
-        __syncwarp();
+        if (p.act == FFCB_ACT_RELU) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ad[i] = ad_next[i];
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.act != FFCB_ACT_NONE) {
+          for (int j = 0; j < 32; ++j) v[j] = slow_act(v[j], p.act);
+        }
+        if (p.addend_post) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += ad[j];
+        }
+        // the previous TMA store of this warp must have finished reading the staging tile
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        if (out_split) {
+          // [plane][32 rows][32 bf16] = 64-byte rows, TMA SWIZZLE_64B: 16-byte chunk c of row r lives at c ^ ((r>>1)&3)
+          uint4* hi = reinterpret_cast<uint4*>(stg) + lane * 4;
+          uint4* lo = reinterpret_cast<uint4*>(stg + 2048) + lane * 4;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            unsigned h[4], l[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(v[8 * c + 2 * k], h0, l0);
+              split_bf16(v[8 * c + 2 * k + 1], h1, l1);
+              h[k] = pack_bf16(h0, h1);
+              l[k] = pack_bf16(l0, l1);
+            }
+            hi[c ^ sw] = make_uint4(h[0], h[1], h[2], h[3]);
+            lo[c ^ sw] = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+        } else {
+          // [32 rows][32 floats] = 128-byte rows, TMA SWIZZLE_128B: chunk c of row r lives at c ^ (r & 7)
+          float4* dst = reinterpret_cast<float4*>(stg) + lane * 8;
+          const int sw = lane & 7;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) dst[c ^ sw] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0 && !(p.debug & 1)) {
+          if (p.flat) tma_store_3d(&map_out, stg, n0, (int)tc.m0 + wq * 32, 0);
+          else tma_store_5d(&map_out, stg, n0, box_x, box_y, tc.b, 0);
+          tma_store_commit();
+        }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -420,16 +454,16 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int encode(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-           const cuuint32_t* box, const cuuint32_t* estr, const char* what) {
+int encode_typed(CUtensorMap* map, void* base, CUtensorMapDataType dt, CUtensorMapSwizzle sw, int rank,
+                 const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* estr,
+                 const char* what) {
   EncodeTiledFn fn = get_encode();
   if (fn == nullptr) {
     set_error("conv(tc): cuTensorMapEncodeTiled entry point unavailable");
     return FFCB_ECUDA;
   }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, dt, (cuuint32_t)rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("conv(tc): cuTensorMapEncodeTiled(%s) failed with CUresult %d (rank %d, dims %llu %llu %llu, box %u %u %u)",
               what, (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
@@ -442,6 +476,12 @@ int encode(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const
 // N-tile width.  Pipeline depth matters more than tile area here: every stage carries 32 KB of
 // activations (hi+lo) plus 256 B per output column, so BN=128 leaves 3 stages in flight, BN>=192 only 2
 // (measured: 74% vs 35% tensor-pipe utilisation, profiles/r01_launches_bf16x3_v1.txt).
+int encode(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+           const cuuint32_t* box, const cuuint32_t* estr, const char* what) {
+  return encode_typed(map, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, rank, dims, strides_bytes,
+                      box, estr, what);
+}
+
 int pick_bn(int n) {
   if (n <= 128) return (n + 31) / 32 * 32;
   if (n == 192) return 96;
@@ -498,6 +538,8 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     const ffcb_tensor& t = d->in[s];
     flat = t.H == H && t.W == W && t.sy == (int64_t)W * t.sx && t.sb == (int64_t)H * t.sy;
   }
+  // the epilogue stores 32-pixel boxes through a tensor map: a flattened pixel axis needs a dense output too
+  flat = flat && d->out.sy == (int64_t)W * d->out.sx && d->out.sb == (int64_t)H * d->out.sy;
   p.flat = flat ? 1 : 0;
   if (flat) {
     p.TW = BM; p.TH = 1; p.tiles_x = p.tiles_y = 1;
@@ -512,8 +554,11 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     FFCB_REQUIRE(p.TW * d->stride <= 256 && p.TH * d->stride <= 256, "conv(tc): tile exceeds the TMA box limit");
   }
 
+  p.obw = p.TW < 32 ? p.TW : 32;
+  p.obh = 32 / p.obw;
+
   // ---- tensor maps
-  alignas(64) CUtensorMap maps[3];
+  alignas(64) CUtensorMap maps[4];
   int rc;
   for (int s = 0; s < 2; ++s) {
     if (!used[s]) { maps[s] = maps[0]; p.coord_off[s] = 0; continue; }
@@ -548,6 +593,31 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     if ((rc = encode(&maps[2], const_cast<void*>(d->weight), 3, dims, str, box, es, "weights"))) return rc;
   }
 
+  {
+    // output: fp32 rows of 128 B (SWIZZLE_128B) or split bf16 rows of 64 B per plane (SWIZZLE_64B)
+    const ffcb_tensor& t = d->out;
+    const bool split = t.fmt == FFCB_BF16X2;
+    const cuuint64_t esz = split ? 2 : 4;
+    FFCB_REQUIRE(((uintptr_t)t.ptr % 16) == 0 && (t.sx * esz) % 16 == 0 && (t.sy * esz) % 16 == 0 &&
+                     (t.sb * esz) % 16 == 0 && (!split || (t.lo_off * esz) % 16 == 0),
+                 "conv(tc): out strides / pointer not 16-byte aligned (C must be a multiple of %d)", split ? 8 : 4);
+    const CUtensorMapDataType dt = split ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapSwizzle sw = split ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    if (flat) {
+      cuuint64_t dims[3] = {(cuuint64_t)t.C, (cuuint64_t)t.B * t.H * t.W, (cuuint64_t)(split ? 2 : 1)};
+      cuuint64_t str[2] = {(cuuint64_t)t.sx * esz, (cuuint64_t)(split ? t.lo_off * esz : (cuuint64_t)t.sx * esz * t.B * t.H * t.W)};
+      cuuint32_t box[3] = {32, 32, (cuuint32_t)(split ? 2 : 1)}, es[3] = {1, 1, 1};
+      if ((rc = encode_typed(&maps[3], t.ptr, dt, sw, 3, dims, str, box, es, "flat output"))) return rc;
+    } else {
+      cuuint64_t dims[5] = {(cuuint64_t)t.C, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)t.B, (cuuint64_t)(split ? 2 : 1)};
+      cuuint64_t str[4] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.sy * esz, (cuuint64_t)t.sb * esz,
+                           (cuuint64_t)(split ? t.lo_off * esz : (cuuint64_t)t.sb * esz * t.B)};
+      cuuint32_t box[5] = {32, (cuuint32_t)p.obw, (cuuint32_t)p.obh, 1, (cuuint32_t)(split ? 2 : 1)};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      if ((rc = encode_typed(&maps[3], t.ptr, dt, sw, 5, dims, str, box, es, "spatial output"))) return rc;
+    }
+  }
+
   // ---- launch
   const int stage_bytes = 2 * kTileABytes + 2 * p.BN * BK * 2;
   const int bar_bytes = kBarBytes + kEpiBytes;
@@ -562,7 +632,7 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   FFCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  conv_tc_kernel<<<grid, kThreads, smem, stream>>>(p, maps[0], maps[1], maps[2]);
+  conv_tc_kernel<<<grid, kThreads, smem, stream>>>(p, maps[0], maps[1], maps[2], maps[3]);
   FFCB_LAUNCH_CHECK("conv_tc_kernel");
   return FFCB_OK;
 }

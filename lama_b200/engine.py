@@ -494,31 +494,31 @@ def tc_compatible(prog: Program) -> bool:
                     return False
             if any(sg.c0 % 8 for sg in op.packed.segs):
                 return False
+            if op.out.buf.fmt == L.BF16X2 and (op.out.buf.C % 8 or op.out.c0 % 8):
+                return False
     return True
 
 
 def insert_border_ops(prog: Program):
-    """Append a BorderOp after every producer that leaves the reflected ring of a padded buffer stale:
-    layout conversions, the stem, FFT outputs, and sub-pixel (phase) convolutions.  tcgen05 convolutions
-    writing whole rows/columns refresh the ring in their own epilogue."""
-    out = []
-    ops = prog.ops
-    for i, op in enumerate(ops):
+    """Producers never write the reflected ring of a padded buffer (the tcgen05 epilogue stores through a
+    tensor map of the interior; layout conversions, the stem and the FFT kernels write pixels only).  Insert
+    a BorderOp lazily: right before the first contraction that reads a buffer whose interior changed since
+    its ring was last rebuilt.  For the in-place residual blocks that is one ring refresh per FFC_BN_ACT."""
+    out, dirty = [], {}
+    for op in prog.ops:
+        if isinstance(op, ConvOp):
+            for tv in op.ins:
+                if tv is not None and tv.buf.reflect_border and id(tv.buf) in dirty:
+                    out.append(BorderOp(TV(tv.buf)))
+                    del dirty[id(tv.buf)]
         out.append(op)
-        tv = None
-        if isinstance(op, (ToNHWC, StemOp)):
-            tv = op.out
-        elif isinstance(op, IrfftOp):
-            tv = op.out
+        wrote = None
+        if isinstance(op, (ToNHWC, StemOp, IrfftOp, ConvOp)):
+            wrote = op.out
         elif isinstance(op, RfftOp):
-            tv = op.spec
-        elif isinstance(op, ConvOp) and (op.out.phase is not None or prog.math == L.MATH_FP32
-                                         or op.out.buf.H < 4 or op.out.buf.W < 4):
-            nxt = ops[i + 1] if i + 1 < len(ops) else None
-            same = isinstance(nxt, ConvOp) and nxt.out.buf is op.out.buf and nxt.out.phase is not None
-            tv = None if (op.out.phase is not None and same) else op.out
-        if tv is not None and tv.buf.reflect_border:
-            out.append(BorderOp(TV(tv.buf)))
+            wrote = op.spec
+        if wrote is not None and wrote.buf.reflect_border:
+            dirty[id(wrote.buf)] = wrote.buf
     prog.ops = out
 
 

@@ -125,8 +125,23 @@ def test_bf16x3_program_layout_and_semantics():
     assert prog.bufs[-1].name.startswith("up") and prog.bufs[-1].fmt == L.F32      # head input
     ops = prog.ops
     assert isinstance(ops[0], E.StemOp) and isinstance(ops[1], E.BorderOp)
+    # ring discipline: whenever a contraction reads a ring buffer, the last op that touched that buffer
+    # before it is a BorderOp (no producer writes rings), and no BorderOp is redundant.
+    last = {}
+    for o in ops:
+        if isinstance(o, E.ConvOp):
+            for tv in o.ins:
+                if tv is not None and tv.buf.reflect_border:
+                    assert last.get(tv.buf.name) == "border", f"{o.tag} reads a stale ring of {tv.buf.name}"
+        if isinstance(o, E.BorderOp):
+            assert last.get(o.view.buf.name) == "write"
+            last[o.view.buf.name] = "border"
+        else:
+            w = getattr(o, "out", None) or getattr(o, "spec", None)
+            if isinstance(w, E.TV) and w.buf.reflect_border:
+                last[w.buf.name] = "write"
     n_border = sum(isinstance(o, E.BorderOp) for o in ops)
-    assert n_border == 1 + 2        # stem + the two split transposed-conv outputs (4 phases each)
+    assert n_border == 4 + 2 * 2 + 2      # stem + 3 stride-2 outputs | 2 blocks x (Y, X) | 2 split up-sampled outputs
     out = SpecInterpreter(prog).run({"x0": x})
     assert float(np.abs(out["y0"].numpy() - a["y"]).max()) < 2e-6
     # weights of the tcgen05 arm: [2][N][Kpad], K padded per segment to 64
