@@ -10,99 +10,123 @@
 namespace ffcb {
 namespace {
 
-constexpr int TILE = 16;          // output pixels per CTA edge
-constexpr int HALO = 3;           // 7x7
-constexpr int PT = TILE + 2 * HALO;  // 22
+constexpr int HALO = 3;            // 7x7
+constexpr int TX = 32, TY = 16;    // output tile per CTA: 32 columns (lane == column) x 16 rows
+constexpr int PW = TX + 2 * HALO;  // 38
+constexpr int PH = TY + 2 * HALO;  // 22
+constexpr int kShellThreads = 128; // 4 warps: warp w owns rows {w, w+4, w+8, w+12} (stem) / {4w..4w+3} (head)
 
 // ---------------------------------------------------------------------------------------- stem
-// One thread = one output pixel, NACC output channels per CTA pass (grid.z walks channel groups).
-// smem: patch[Cin][22][22] floats, then w[49*Cin][NACC].
-template <int NACC>
-__global__ void __launch_bounds__(TILE * TILE) stem_conv7_kernel(const float* __restrict__ x, int B, int Cin, int H,
-                                                                 int W, const float* __restrict__ w,
-                                                                 const float* __restrict__ shift, int N, View out) {
+// Register tile: 4 pixels (same column, rows w + 4r) x 16 output channels per thread; blockIdx.z walks
+// the output channels 16 at a time.  Per (tap, input channel): 4 conflict-free scalar patch reads +
+// 4 broadcast float4 weight reads feed 64 FMAs, so the kernel is FMA-issue bound rather than
+// shared-memory bound.  smem: patch[Cin][22][38], w[49*Cin][16].
+constexpr int SN = 16;
+__global__ void __launch_bounds__(kShellThreads) stem_conv7_kernel(const float* __restrict__ x, int B, int Cin, int H,
+                                                                   int W, const float* __restrict__ w,
+                                                                   const float* __restrict__ shift, int N, View out) {
   extern __shared__ __align__(16) float smem[];
   float* patch = smem;
-  float* ws = smem + ((Cin * PT * PT + 3) & ~3);
-  const int tx = threadIdx.x % TILE, ty = threadIdx.x / TILE;
-  const int tiles_x = (W + TILE - 1) / TILE;
-  const int x0 = (blockIdx.x % tiles_x) * TILE, y0 = (blockIdx.x / tiles_x) * TILE;
+  float* ws = smem + ((Cin * PH * PW + 3) & ~3);
+  const int tx = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int tiles_x = (W + TX - 1) / TX;
+  const int x0 = (blockIdx.x % tiles_x) * TX, y0 = (blockIdx.x / tiles_x) * TY;
   const int b = blockIdx.y;
-  const int n0 = blockIdx.z * NACC;
+  const int n0 = blockIdx.z * SN;
   const int K = 49 * Cin;
 
-  for (int i = threadIdx.x; i < Cin * PT * PT; i += blockDim.x) {
-    const int c = i / (PT * PT), r = i % (PT * PT);
-    const int yy = reflect_idx(y0 + r / PT - HALO, H), xx = reflect_idx(x0 + r % PT - HALO, W);
-    // tiles hanging over the image edge: clamp (values unused by in-range pixels)
-    const int yc = min(max(yy, 0), H - 1), xc = min(max(xx, 0), W - 1);
-    patch[i] = __ldg(x + (((long long)b * Cin + c) * H + yc) * W + xc);
+  for (int i = threadIdx.x; i < Cin * PH * PW; i += blockDim.x) {
+    const int c = i / (PH * PW), r = i % (PH * PW);
+    // reflect, then clamp for tiles hanging over the image edge (those values feed no in-range pixel)
+    const int yy = min(max(reflect_idx(y0 + r / PW - HALO, H), 0), H - 1);
+    const int xx = min(max(reflect_idx(x0 + r % PW - HALO, W), 0), W - 1);
+    patch[i] = __ldg(x + (((long long)b * Cin + c) * H + yy) * W + xx);
   }
-  for (int i = threadIdx.x; i < K * NACC; i += blockDim.x) {
-    const int k = i / NACC, j = i % NACC;
+  for (int i = threadIdx.x; i < K * SN; i += blockDim.x) {
+    const int k = i / SN, j = i % SN;
     ws[i] = (n0 + j < N) ? __ldg(w + (long long)k * N + n0 + j) : 0.f;
   }
   __syncthreads();
 
-  float acc[NACC];
+  float acc[4][SN];
 #pragma unroll
-  for (int j = 0; j < NACC; ++j) acc[j] = 0.f;
-  for (int ky = 0; ky < 7; ++ky)
-    for (int kx = 0; kx < 7; ++kx)
-      for (int c = 0; c < Cin; ++c) {
-        const float a = patch[(c * PT + ty + ky) * PT + tx + kx];
-        const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 7 + kx) * Cin + c) * NACC);
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int j = 0; j < NACC / 4; ++j) {
-          const float4 wv = wr[j];
-          acc[4 * j + 0] = fmaf(a, wv.x, acc[4 * j + 0]);
-          acc[4 * j + 1] = fmaf(a, wv.y, acc[4 * j + 1]);
-          acc[4 * j + 2] = fmaf(a, wv.z, acc[4 * j + 2]);
-          acc[4 * j + 3] = fmaf(a, wv.w, acc[4 * j + 3]);
+    for (int j = 0; j < SN; ++j) acc[r][j] = 0.f;
+
+  for (int ky = 0; ky < 7; ++ky) {
+    for (int c = 0; c < Cin; ++c) {
+      const float* prow = patch + (c * PH + wy + ky) * PW + tx;
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 7 + kx) * Cin + c) * SN);
+        const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+        const float wv[SN] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
+                              w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float a = prow[4 * r * PW + kx];
+#pragma unroll
+          for (int j = 0; j < SN; ++j) acc[r][j] = fmaf(a, wv[j], acc[r][j]);
         }
       }
-  const int y = y0 + ty, xo = x0 + tx;
-  if (y >= H || xo >= W) return;
-  const long long o = pix_off(out, b, y, xo);
-#pragma unroll
-  for (int j = 0; j < NACC / 4; ++j) {
-    const int n = n0 + 4 * j;
-    if (n >= N) break;
-    float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-    if (shift != nullptr) {
-      const float4 s = __ldg(reinterpret_cast<const float4*>(shift + n));
-      v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
     }
-    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-    store4(out, o + n, v);
+  }
+
+  const int xo = x0 + tx;
+  if (xo >= W) return;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int y = y0 + wy + 4 * r;
+    if (y >= H) continue;
+    const long long o = pix_off(out, b, y, xo);
+#pragma unroll
+    for (int q = 0; q < SN / 4; ++q) {
+      const int n = n0 + 4 * q;
+      if (n >= N) break;
+      float4 v = make_float4(acc[r][4 * q], acc[r][4 * q + 1], acc[r][4 * q + 2], acc[r][4 * q + 3]);
+      if (shift != nullptr) {
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + n));
+        v.x += sh.x; v.y += sh.y; v.z += sh.z; v.w += sh.w;
+      }
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      store4(out, o + n, v);
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------- head
-// One thread = one output pixel, all N<=4 outputs.  Channels are staged 16 at a time:
-// patch[22*22][PSTR] floats (PSTR = 20 keeps float4 reads conflict-free), w[N][49][16].
+// Register tile: 4 vertically adjacent pixels x (N <= 4) outputs per thread.  For one (kx, channel quad)
+// the 10 patch rows a thread needs are loaded once (float4, conflict-free: pixel pitch 20 floats) and
+// reused by the 4 pixels x 7 ky taps; weights are broadcast float4 reads.  Channels are staged 16 at a time:
+// patch[22][38][PSTR] floats, w[4][49][16].
 constexpr int HC = 16, PSTR = 20;
 
-__global__ void __launch_bounds__(TILE * TILE) head_conv7_kernel(View in, const float* __restrict__ w,
-                                                                 const float* __restrict__ bias, int N, int act,
-                                                                 float* __restrict__ y_out) {
+__global__ void __launch_bounds__(kShellThreads) head_conv7_kernel(View in, const float* __restrict__ w,
+                                                                   const float* __restrict__ bias, int N, int act,
+                                                                   float* __restrict__ y_out) {
   extern __shared__ __align__(16) float smem[];
-  float* patch = smem;                  // [PT*PT][PSTR]
-  float* ws = smem + PT * PT * PSTR;    // [4][49][HC]
-  const int tx = threadIdx.x % TILE, ty = threadIdx.x / TILE;
+  float* patch = smem;                  // [PH*PW][PSTR]
+  float* ws = smem + PH * PW * PSTR;    // [4][49][HC]
+  const int tx = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int H = in.H, W = in.W, C = in.C;
-  const int tiles_x = (W + TILE - 1) / TILE;
-  const int x0 = (blockIdx.x % tiles_x) * TILE, y0 = (blockIdx.x / tiles_x) * TILE;
+  const int tiles_x = (W + TX - 1) / TX;
+  const int x0 = (blockIdx.x % tiles_x) * TX, y0 = (blockIdx.x / tiles_x) * TY;
   const int b = blockIdx.y;
 
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) acc[r][n] = 0.f;
+
   for (int c0 = 0; c0 < C; c0 += HC) {
-    for (int i = threadIdx.x; i < PT * PT * (HC / 4); i += blockDim.x) {
+    for (int i = threadIdx.x; i < PH * PW * (HC / 4); i += blockDim.x) {
       const int pix = i / (HC / 4), q = i % (HC / 4);
-      const int yy = reflect_idx(y0 + pix / PT - HALO, H), xx = reflect_idx(x0 + pix % PT - HALO, W);
-      const int yc = min(max(yy, 0), H - 1), xc = min(max(xx, 0), W - 1);
+      const int yy = min(max(reflect_idx(y0 + pix / PW - HALO, H), 0), H - 1);
+      const int xx = min(max(reflect_idx(x0 + pix % PW - HALO, W), 0), W - 1);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c0 + 4 * q < C) v = load4(in, pix_off(in, b, yc, xc) + c0 + 4 * q);
+      if (c0 + 4 * q < C) v = load4(in, pix_off(in, b, yy, xx) + c0 + 4 * q);
       *reinterpret_cast<float4*>(patch + pix * PSTR + 4 * q) = v;
     }
     for (int i = threadIdx.x; i < 4 * 49 * HC; i += blockDim.x) {
@@ -110,27 +134,45 @@ __global__ void __launch_bounds__(TILE * TILE) head_conv7_kernel(View in, const 
       ws[i] = (n < N && c0 + c < C) ? __ldg(w + ((long long)n * 49 + t) * C + c0 + c) : 0.f;
     }
     __syncthreads();
-    for (int ky = 0; ky < 7; ++ky)
-      for (int kx = 0; kx < 7; ++kx) {
-        const float* pp = patch + ((ty + ky) * PT + tx + kx) * PSTR;
-        const float* wp = ws + (ky * 7 + kx) * HC;
+    for (int kx = 0; kx < 7; ++kx) {
 #pragma unroll
-        for (int q = 0; q < HC / 4; ++q) {
-          const float4 a = *reinterpret_cast<const float4*>(pp + 4 * q);
+      for (int q = 0; q < HC / 4; ++q) {
+        float4 a[10];
+        const float* pp = patch + ((4 * wy) * PW + tx + kx) * PSTR + 4 * q;
 #pragma unroll
-          for (int n = 0; n < 4; ++n) {
-            const float4 wv = *reinterpret_cast<const float4*>(wp + n * 49 * HC + 4 * q);
-            acc[n] = fmaf(a.x, wv.x, fmaf(a.y, wv.y, fmaf(a.z, wv.z, fmaf(a.w, wv.w, acc[n]))));
+        for (int j = 0; j < 10; ++j) a[j] = *reinterpret_cast<const float4*>(pp + j * PW * PSTR);
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+          for (int n = 0; n < 3; ++n) {
+            const float4 wv = *reinterpret_cast<const float4*>(ws + (n * 49 + ky * 7 + kx) * HC + 4 * q);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              acc[r][n] = fmaf(a[r + ky].x, wv.x,
+                               fmaf(a[r + ky].y, wv.y, fmaf(a[r + ky].z, wv.z, fmaf(a[r + ky].w, wv.w, acc[r][n]))));
+          }
+          if (N == 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(ws + (3 * 49 + ky * 7 + kx) * HC + 4 * q);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              acc[r][3] = fmaf(a[r + ky].x, wv.x,
+                               fmaf(a[r + ky].y, wv.y, fmaf(a[r + ky].z, wv.z, fmaf(a[r + ky].w, wv.w, acc[r][3]))));
           }
         }
       }
+    }
     __syncthreads();
   }
-  const int y = y0 + ty, xo = x0 + tx;
-  if (y >= H || xo >= W) return;
-  for (int n = 0; n < N; ++n) {
-    const float v = apply_act(acc[n] + (bias ? __ldg(bias + n) : 0.f), act);
-    y_out[(((long long)b * N + n) * H + y) * W + xo] = v;
+  const int xo = x0 + tx;
+  if (xo >= W) return;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int y = y0 + 4 * wy + r;
+    if (y >= H) continue;
+    for (int n = 0; n < N; ++n) {
+      const float v = apply_act(acc[r][n] + (bias ? __ldg(bias + n) : 0.f), act);
+      y_out[(((long long)b * N + n) * H + y) * W + xo] = v;
+    }
   }
 }
 
@@ -187,18 +229,6 @@ __global__ void reflect_ring_kernel(View t) {
   }
 }
 
-template <int NACC>
-int launch_stem(const float* x, int B, int Cin, int H, int W, const float* w, const float* shift, int N,
-                const View& out, cudaStream_t stream) {
-  const size_t smem = sizeof(float) * (((size_t)Cin * PT * PT + 3) / 4 * 4 + (size_t)49 * Cin * NACC);
-  if (smem > 48 * 1024)
-    FFCB_CUDA(cudaFuncSetAttribute(stem_conv7_kernel<NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE), B, (N + NACC - 1) / NACC);
-  stem_conv7_kernel<NACC><<<grid, TILE * TILE, smem, stream>>>(x, B, Cin, H, W, w, shift, N, out);
-  FFCB_LAUNCH_CHECK("stem_conv7_kernel");
-  return FFCB_OK;
-}
-
 }  // namespace
 
 int stem_conv7(const float* x, int B, int Cin, int H, int W, const float* w, const float* shift, int N,
@@ -210,12 +240,15 @@ int stem_conv7(const float* x, int B, int Cin, int H, int W, const float* w, con
   FFCB_REQUIRE(H >= 4 && W >= 4, "stem_conv7: reflect pad 3 needs H,W >= 4 (got %dx%d)", H, W);
   FFCB_REQUIRE(N % 4 == 0 && N >= 4, "stem_conv7: N=%d must be a positive multiple of 4", N);
   FFCB_REQUIRE(out->B == B && out->H == H && out->W == W && out->C == N, "stem_conv7: out view shape mismatch");
+  FFCB_REQUIRE(B <= 65535, "stem_conv7: batch exceeds grid.y");
   if (B == 0) return FFCB_OK;
-  const View vo = make_view(*out);
-  if (N >= 64) return launch_stem<64>(x, B, Cin, H, W, w, shift, N, vo, stream);
-  if (N >= 32) return launch_stem<32>(x, B, Cin, H, W, w, shift, N, vo, stream);
-  if (N >= 16) return launch_stem<16>(x, B, Cin, H, W, w, shift, N, vo, stream);
-  return launch_stem<8>(x, B, Cin, H, W, w, shift, N, vo, stream);
+  const size_t smem = sizeof(float) * (((size_t)Cin * PH * PW + 3) / 4 * 4 + (size_t)49 * Cin * SN);
+  if (smem > 48 * 1024)
+    FFCB_CUDA(cudaFuncSetAttribute(stem_conv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(((W + TX - 1) / TX) * ((H + TY - 1) / TY), B, (N + SN - 1) / SN);
+  stem_conv7_kernel<<<grid, kShellThreads, smem, stream>>>(x, B, Cin, H, W, w, shift, N, make_view(*out));
+  FFCB_LAUNCH_CHECK("stem_conv7_kernel");
+  return FFCB_OK;
 }
 
 int head_conv7(const ffcb_tensor* in, const float* w, const float* bias, int N, int act, float* y,
@@ -226,10 +259,11 @@ int head_conv7(const ffcb_tensor* in, const float* w, const float* bias, int N, 
   FFCB_REQUIRE(N >= 1 && N <= 4, "head_conv7: N=%d outside [1,4]", N);
   FFCB_REQUIRE(in->H >= 4 && in->W >= 4, "head_conv7: reflect pad 3 needs H,W >= 4");
   if (in->B == 0) return FFCB_OK;
-  dim3 grid(((in->W + TILE - 1) / TILE) * ((in->H + TILE - 1) / TILE), in->B);
-  constexpr size_t smem = sizeof(float) * (PT * PT * PSTR + 4 * 49 * HC);
+  FFCB_REQUIRE(in->B <= 65535, "head_conv7: batch exceeds grid.y");
+  dim3 grid(((in->W + TX - 1) / TX) * ((in->H + TY - 1) / TY), in->B);
+  constexpr size_t smem = sizeof(float) * (PH * PW * PSTR + 4 * 49 * HC);
   FFCB_CUDA(cudaFuncSetAttribute(head_conv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  head_conv7_kernel<<<grid, TILE * TILE, smem, stream>>>(make_view(*in), w, bias, N, act, y);
+  head_conv7_kernel<<<grid, kShellThreads, smem, stream>>>(make_view(*in), w, bias, N, act, y);
   FFCB_LAUNCH_CHECK("head_conv7_kernel");
   return FFCB_OK;
 }
