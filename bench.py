@@ -300,7 +300,7 @@ def main():
             gbs = fu_bytes / (ms_f * 1e-3) / 1e9
             roof["fourier_unit"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": gbs / peaks["hbm_gbs"], "ms": ms_f, "algorithmic_bytes": fu_bytes,
-                                    "shape": [B, c, h, h], "launches": 5,
+                                    "shape": [B, c, h, h], "launches": 3,
                                     "note": "warm L2 between repetitions of the same FU; intermediates (spectrum) not counted"}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample on all host cores

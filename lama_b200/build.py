@@ -15,7 +15,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(HERE, "libffc_b200.so")
 STAMP = LIB_PATH + ".stamp"
 
-SOURCES = ["api.cu", "fft.cu", "conv_simt.cu", "conv_tc.cu", "shell.cu"]
+SOURCES = ["api.cu", "fft.cu", "fft_plane.cu", "conv_simt.cu", "conv_tc.cu", "shell.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "--expt-relaxed-constexpr",

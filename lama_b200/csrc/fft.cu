@@ -14,6 +14,7 @@
 // every other length runs a direct DFT (same kernels, O(n^2)) so odd / non-power-of-two planes
 // (bin/predict.py pads images to multiples of 8 only -> e.g. 125x188 bottlenecks) stay native.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "fft_core.cuh"
@@ -311,6 +312,11 @@ int check_fft_shapes(const ffcb_tensor* real, const ffcb_tensor* spec, const cha
 
 }  // namespace
 
+// fused whole-plane path (fft_plane.cu)
+bool plane64_eligible(const ffcb_tensor* real);
+int rfft2_plane64(const ffcb_tensor* in, const ffcb_tensor* spec, cudaStream_t stream);
+int irfft2_plane64(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out, cudaStream_t stream);
+
 size_t fft2_workspace_bytes(int B, int H, int W, int C) {
   return sizeof(float2) * (size_t)B * H * (W / 2 + 1) * C;
 }
@@ -324,6 +330,7 @@ int rfft2(const ffcb_tensor* in, const ffcb_tensor* spec, void* ws, size_t ws_by
     return FFCB_ENOMEM;
   }
   if (in->B == 0 || in->C == 0) return FFCB_OK;
+  if (plane64_eligible(in) && !getenv("FFCB_FFT_TWO_PASS")) return rfft2_plane64(in, spec, stream);
   const View vin = make_view(*in), vspec = make_view(*spec);
   float2* w2 = reinterpret_cast<float2*>(ws);
   const int cblocks = (in->C + kLanes - 1) / kLanes;
@@ -368,6 +375,7 @@ int irfft2(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tens
     return FFCB_ENOMEM;
   }
   if (out->B == 0 || out->C == 0) return FFCB_OK;
+  if (plane64_eligible(out) && !getenv("FFCB_FFT_TWO_PASS")) return irfft2_plane64(spec, residual, out, stream);
   const View vspec = make_view(*spec), vout = make_view(*out);
   float2* w2 = reinterpret_cast<float2*>(ws);
   const int cblocks = (out->C + kLanes - 1) / kLanes;

@@ -151,5 +151,101 @@ FFCB_HD void c2r_pair_pre(float2* z, int W, int k, int lane, float2 x1, float2 x
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 64-point complex FFT held entirely in registers (fully unrolled 8 x 8 Cooley-Tukey, compile-time
+// twiddles): n = 8a + b, k = c + 8d;  step 1: FFT8 over a (stride 8), step 2: * w64^(b c), step 3: FFT8 over b.
+// In/out in place; OUTPUT ORDER IS TRANSPOSED: X[k] is left in v[8*(k%8) + k/8]  (see fft64_at()).
+FFCB_HD int fft64_at(int k) { return 8 * (k & 7) + (k >> 3); }
+
+// w64^t = exp(-2 pi i t / 64), t = 0..63
+FFCB_HD float2 tw64(int t) {
+  constexpr float c[17] = {1.0f, 0.99518472667219688624f, 0.98078528040323044913f, 0.95694033573220886494f,
+                           0.92387953251128675613f, 0.88192126434835502971f, 0.83146961230254523708f,
+                           0.77301045336273696081f, 0.70710678118654752440f, 0.63439328416364549822f,
+                           0.55557023301960222474f, 0.47139673682599764856f, 0.38268343236508977173f,
+                           0.29028467725446236764f, 0.19509032201612826785f, 0.09801714032956060199f, 0.0f};
+  // cos(2 pi t/64), sin(2 pi t/64) from the first-quadrant table
+  const int q = (t >> 4) & 3, r = t & 15;
+  const float cr = c[r], sr = c[16 - r];
+  float co, si;
+  if (q == 0) { co = cr; si = sr; }
+  else if (q == 1) { co = -sr; si = cr; }
+  else if (q == 2) { co = -cr; si = -sr; }
+  else { co = sr; si = -cr; }
+  return make_float2(co, -si);
+}
+
+template <bool INV>
+FFCB_HD void fft64_regs(float2* v) {
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    float2 t[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) t[a] = v[8 * a + b];
+    fft8<INV>(t);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float2 y = t[c];
+      if (b * c != 0) {
+        float2 w = tw64((b * c) & 63);
+        if (INV) w.y = -w.y;
+        y = cmul(y, w);
+      }
+      v[8 * c + b] = y;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) fft8<INV>(v + 8 * c);
+}
+
+
+// Per-thread steps of the fused 64x64 plane kernels (fft_plane.cu); functors keep them host-testable.
+//   rows forward : z[n] = (row_a[n], row_b[n]) -> half spectra A[k], B[k], k = 0..32 (two-for-one)
+//   columns      : 64-point complex transform of one (kx, channel) column, natural order in and out
+//   rows inverse : half spectra X1[k], X2[k] (C2R rule) -> (row_a[n], row_b[n])
+template <class Load, class Store>
+FFCB_HD void plane64_rows_fwd(Load&& ld, Store&& st) {
+  float2 v[64];
+#pragma unroll
+  for (int n = 0; n < 64; ++n) v[n] = ld(n);
+  fft64_regs<false>(v);
+#pragma unroll
+  for (int k = 0; k <= 32; ++k) {
+    const float2 zk = v[fft64_at(k)], zm = v[fft64_at((64 - k) & 63)];
+    st(k, make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y)),
+       make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x)));
+  }
+}
+
+template <bool INV, class Load, class Store>
+FFCB_HD void plane64_col(Load&& ld, Store&& st) {
+  float2 v[64];
+#pragma unroll
+  for (int n = 0; n < 64; ++n) v[n] = ld(n);
+  fft64_regs<INV>(v);
+#pragma unroll
+  for (int k = 0; k < 64; ++k) st(k, v[fft64_at(k)]);
+}
+
+template <class Load, class Store>
+FFCB_HD void plane64_rows_inv(Load&& ld, Store&& st) {
+  float2 v[64];
+#pragma unroll
+  for (int k = 0; k <= 32; ++k) {
+    float2 x1, x2;
+    ld(k, x1, x2);
+    if (k == 0 || k == 32) {
+      v[k] = make_float2(x1.x, x2.x);                      // Im of DC / Nyquist ignored (C2R rule)
+    } else {
+      v[k] = make_float2(x1.x - x2.y, x1.y + x2.x);        // X1 + i X2
+      v[64 - k] = make_float2(x1.x + x2.y, x2.x - x1.y);   // conj(X1) + i conj(X2)
+    }
+  }
+  fft64_regs<true>(v);
+#pragma unroll
+  for (int n = 0; n < 64; ++n) st(n, v[fft64_at(n)]);
+}
+
 }  // namespace fftc
 }  // namespace ffcb

@@ -1,0 +1,117 @@
+// Fused 2-D real FFT pair for 64x64 planes (the bottleneck of 512x512 images): one CTA transforms the
+// whole plane of 8 channels, so the half-spectrum intermediate lives in shared memory instead of a
+// global workspace (halves the HBM traffic of ffcb_rfft2 / ffcb_irfft2 and removes two launches).
+//
+// Every 64-point transform is held in the registers of ONE thread (fft64_regs: unrolled 8x8 Cooley-Tukey
+// with compile-time twiddles) — no shuffles, no shared-memory butterflies, one barrier per plane:
+//   forward : 256 threads = 8 channels x 32 row pairs (two-for-one real rows)  -> S[y][kx][c] -> barrier ->
+//             264 threads = 8 channels x 33 columns -> spectrum (Re/Im interleaved channels, scaled)
+//   inverse : columns first (all 33, complex), barrier, then C2R rows (+ residual).
+// smem: S[64][P] float2 with row pitch P = 33*8 + 4 (the +4 spreads the four row-pair groups of a warp
+// over both halves of the banks).  Lanes: 8 consecutive channels (32 B of a pixel) x 4 rows/columns.
+#include "common.cuh"
+#include "fft_core.cuh"
+
+namespace ffcb {
+namespace {
+
+using namespace fftc;
+constexpr int PN = 64, PWF = 33, PCH = 8, PPITCH = PWF * PCH + 4;
+constexpr int kPlaneThreads = 288;   // 9 warps: 264 column threads, 256 row threads
+constexpr size_t kPlaneSmem = sizeof(float2) * PN * PPITCH;
+
+__global__ void __launch_bounds__(kPlaneThreads, 1) rfft2_plane64_kernel(View in, View spec, float scale) {
+  extern __shared__ float2 S[];
+  const int tid = threadIdx.x, c = tid & 7, g = tid >> 3;
+  const int ch = blockIdx.x * PCH + c, b = blockIdx.y;
+  if (tid < 256) {   // g = row pair
+    const long long r0 = pix_off(in, b, 2 * g, 0) + ch, r1 = r0 + in.sy;
+    plane64_rows_fwd(
+        [&](int n) { return make_float2(load1(in, r0 + n * in.sx), load1(in, r1 + n * in.sx)); },
+        [&](int k, float2 a, float2 bb) {
+          S[(2 * g) * PPITCH + k * PCH + c] = a;
+          S[(2 * g + 1) * PPITCH + k * PCH + c] = bb;
+        });
+  }
+  __syncthreads();
+  if (tid < PWF * PCH) {   // g = kx
+    const long long o0 = pix_off(spec, b, 0, g) + 2 * ch;
+    plane64_col<false>(
+        [&](int y) { return S[y * PPITCH + g * PCH + c]; },
+        [&](int ky, float2 z) {
+          const long long o = o0 + ky * spec.sy;
+          z.x *= scale; z.y *= scale;
+          if (spec.fmt == FFCB_F32) {
+            *reinterpret_cast<float2*>(reinterpret_cast<float*>(spec.ptr) + o) = z;
+          } else {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(z.x, h0, l0);
+            split_bf16(z.y, h1, l1);
+            unsigned short* p = reinterpret_cast<unsigned short*>(spec.ptr);
+            *reinterpret_cast<unsigned*>(p + o) = pack_bf16(h0, h1);
+            *reinterpret_cast<unsigned*>(p + o + spec.lo_off) = pack_bf16(l0, l1);
+          }
+        });
+  }
+}
+
+__global__ void __launch_bounds__(kPlaneThreads, 1) irfft2_plane64_kernel(View spec, View res, View out, float scale) {
+  extern __shared__ float2 S[];
+  const int tid = threadIdx.x, c = tid & 7, g = tid >> 3;
+  const int ch = blockIdx.x * PCH + c, b = blockIdx.y;
+  if (tid < PWF * PCH) {   // g = kx: inverse along H for every column (complex)
+    const long long o0 = pix_off(spec, b, 0, g) + 2 * ch;
+    plane64_col<true>(
+        [&](int ky) {
+          const long long o = o0 + ky * spec.sy;
+          if (spec.fmt == FFCB_F32) return __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(spec.ptr) + o));
+          return make_float2(load1(spec, o), load1(spec, o + 1));
+        },
+        [&](int y, float2 z) { S[y * PPITCH + g * PCH + c] = z; });
+  }
+  __syncthreads();
+  if (tid < 256) {   // g = row pair: C2R along W
+    const long long r0 = pix_off(out, b, 2 * g, 0) + ch, r1 = r0 + out.sy;
+    const bool has_res = res.ptr != nullptr;
+    const long long q0 = has_res ? pix_off(res, b, 2 * g, 0) + ch : 0, q1 = q0 + res.sy;
+    plane64_rows_inv(
+        [&](int k, float2& x1, float2& x2) {
+          x1 = S[(2 * g) * PPITCH + k * PCH + c];
+          x2 = S[(2 * g + 1) * PPITCH + k * PCH + c];
+        },
+        [&](int n, float2 z) {
+          float a = z.x * scale, bb = z.y * scale;
+          if (has_res) {
+            a += load1(res, q0 + n * res.sx);
+            bb += load1(res, q1 + n * res.sx);
+          }
+          store1(out, r0 + n * out.sx, a);
+          store1(out, r1 + n * out.sx, bb);
+        });
+  }
+}
+
+}  // namespace
+
+bool plane64_eligible(const ffcb_tensor* real) {
+  return real->H == PN && real->W == PN && real->C % PCH == 0 && real->B <= 65535;
+}
+
+int rfft2_plane64(const ffcb_tensor* in, const ffcb_tensor* spec, cudaStream_t stream) {
+  FFCB_CUDA(cudaFuncSetAttribute(rfft2_plane64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlaneSmem));
+  dim3 grid(in->C / PCH, in->B);
+  rfft2_plane64_kernel<<<grid, kPlaneThreads, kPlaneSmem, stream>>>(make_view(*in), make_view(*spec), 1.0f / 64.0f);
+  FFCB_LAUNCH_CHECK("rfft2_plane64_kernel");
+  return FFCB_OK;
+}
+
+int irfft2_plane64(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out, cudaStream_t stream) {
+  FFCB_CUDA(cudaFuncSetAttribute(irfft2_plane64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlaneSmem));
+  dim3 grid(out->C / PCH, out->B);
+  const View vres = (residual && residual->ptr) ? make_view(*residual) : null_view();
+  irfft2_plane64_kernel<<<grid, kPlaneThreads, kPlaneSmem, stream>>>(make_view(*spec), vres, make_view(*out), 1.0f / 64.0f);
+  FFCB_LAUNCH_CHECK("irfft2_plane64_kernel");
+  return FFCB_OK;
+}
+
+}  // namespace ffcb

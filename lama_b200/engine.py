@@ -543,6 +543,7 @@ class CudaExecutor:
         self.ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=device)
         self.ws_bytes = ws_bytes
         self.outputs = {k: torch.empty(v, dtype=torch.float32, device=device) for k, v in prog.outputs.items()}
+        self._launches = None
         self._keep = []          # ctypes objects / tensors that must outlive the calls
         self.calls = []          # (fn, args) with a trailing stream argument appended at run time
         self.input_slots: Dict[str, List[Tuple[int, int]]] = {}   # input name -> [(call idx, arg idx)]
@@ -651,18 +652,22 @@ class CudaExecutor:
                 self.prog.inputs[name]), f"input {name}: expected contiguous float32 {self.prog.inputs[name]}"
             for ci, ai in slots:
                 self.calls[ci][2][ai] = t.data_ptr()
+        first = self._launches is None
+        if first:
+            self.lib.ffcb_reset_launch_count()
         for name, fn, args in self.calls:
             rc = fn(*args, stream)
             if rc != 0:
                 L.check(rc, name)
+        if first:
+            self._launches = int(self.lib.ffcb_launch_count())
         return self.outputs
 
     @property
     def launches_per_run(self) -> int:
-        n = 0
-        for name, _fn, _a in self.calls:
-            n += 2 if name in ("ffcb_rfft2", "ffcb_irfft2") else 1
-        return n
+        """Kernel launches of one replay, counted by the library itself during the first run."""
+        assert self._launches is not None, "run the executor once first"
+        return self._launches
 
 
 class GraphedProgram:

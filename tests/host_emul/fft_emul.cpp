@@ -133,6 +133,65 @@ static double check(int H, int W, bool verbose) {
   return rel;
 }
 
+// Fused 64x64 plane kernels (fft_plane.cu): same per-thread functors, one channel, S[y][kx].
+static double check_plane64(bool verbose) {
+  const int N = 64, WF = 33;
+  std::vector<float> x(N * N);
+  for (auto& v : x) v = (float)(rand() / (double)RAND_MAX * 2.0 - 1.0);
+  std::vector<float2> S(N * WF), spec(N * WF);
+  const float scale = 1.0f / 64.0f;
+  for (int g = 0; g < 32; ++g)
+    plane64_rows_fwd([&](int n) { return make_float2(x[(2 * g) * N + n], x[(2 * g + 1) * N + n]); },
+                     [&](int k, float2 a, float2 b) { S[(2 * g) * WF + k] = a; S[(2 * g + 1) * WF + k] = b; });
+  for (int kx = 0; kx < WF; ++kx)
+    plane64_col<false>([&](int y) { return S[y * WF + kx]; },
+                       [&](int ky, float2 z) { spec[ky * WF + kx] = make_float2(z.x * scale, z.y * scale); });
+  double err_f = 0, mag = 0;
+  for (int ky = 0; ky < N; ++ky)
+    for (int kx = 0; kx < WF; ++kx) {
+      cd acc = 0;
+      for (int y = 0; y < N; ++y)
+        for (int xx = 0; xx < N; ++xx)
+          acc += (double)x[y * N + xx] * std::polar(1.0, -2 * M_PI * ((double)ky * y / N + (double)kx * xx / N));
+      acc /= 64.0;
+      err_f = std::max(err_f, std::abs(acc - cd(spec[ky * WF + kx].x, spec[ky * WF + kx].y)));
+      mag = std::max(mag, std::abs(acc));
+    }
+  // inverse of a non-Hermitian spectrum with residual
+  std::vector<float2> z(N * WF);
+  for (auto& v : z) v = make_float2(std::max(0.f, (float)(rand() / (double)RAND_MAX * 2 - 1)),
+                                    std::max(0.f, (float)(rand() / (double)RAND_MAX * 2 - 1)));
+  std::vector<float> out(N * N), res(N * N);
+  for (auto& v : res) v = (float)(rand() / (double)RAND_MAX);
+  for (int kx = 0; kx < WF; ++kx)
+    plane64_col<true>([&](int ky) { return z[ky * WF + kx]; }, [&](int y, float2 v) { S[y * WF + kx] = v; });
+  for (int g = 0; g < 32; ++g)
+    plane64_rows_inv([&](int k, float2& x1, float2& x2) { x1 = S[(2 * g) * WF + k]; x2 = S[(2 * g + 1) * WF + k]; },
+                     [&](int n, float2 v) {
+                       out[(2 * g) * N + n] = v.x * scale + res[(2 * g) * N + n];
+                       out[(2 * g + 1) * N + n] = v.y * scale + res[(2 * g + 1) * N + n];
+                     });
+  double err_i = 0, mag_i = 0;
+  std::vector<cd> t(N * WF);
+  for (int k = 0; k < WF; ++k)
+    for (int y = 0; y < N; ++y) {
+      cd acc = 0;
+      for (int q = 0; q < N; ++q) acc += cd(z[q * WF + k].x, z[q * WF + k].y) * std::polar(1.0, 2 * M_PI * (double)q * y / N);
+      t[y * WF + k] = acc / 8.0;
+    }
+  for (int y = 0; y < N; ++y)
+    for (int n = 0; n < N; ++n) {
+      double acc = t[y * WF].real();
+      for (int k = 1; k < 32; ++k) acc += 2.0 * (t[y * WF + k] * std::polar(1.0, 2 * M_PI * (double)k * n / N)).real();
+      acc += t[y * WF + 32].real() * ((n % 2) ? -1.0 : 1.0);
+      acc = acc / 8.0 + res[y * N + n];
+      err_i = std::max(err_i, std::abs(acc - (double)out[y * N + n]));
+      mag_i = std::max(mag_i, std::abs(acc));
+    }
+  if (verbose) printf("plane64   fwd %.2e / %.2e   inv %.2e / %.2e\n", err_f, mag, err_i, mag_i);
+  return std::max(err_f / mag, err_i / mag_i);
+}
+
 int main(int argc, char** argv) {
   const bool verbose = argc > 1;
   const int sizes[][2] = {{4, 4}, {8, 8}, {16, 16}, {32, 32}, {64, 64}, {128, 128}, {256, 256}, {8, 32}, {64, 16},
@@ -140,6 +199,7 @@ int main(int argc, char** argv) {
                           {64, 33}, {9, 64}};
   double worst = 0;
   for (auto& s : sizes) worst = std::max(worst, check(s[0], s[1], verbose));
+  worst = std::max(worst, check_plane64(verbose));
   printf("worst relative error %.3e\n", worst);
   return worst < 2e-6 ? 0 : 1;
 }

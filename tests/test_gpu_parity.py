@@ -78,6 +78,18 @@ def _run_program(prog, feed):
                                      (1, 4, 20, 24), (1, 8, 125, 188), (1, 4, 5, 2), (1, 40, 64, 4)])
 def test_rfft2_irfft2_against_numpy(b, c, h, w, math_mode):
     _fp32_only(math_mode)
+    _check_fft_pair(b, c, h, w)
+
+
+def test_two_pass_fft_kernels_at_64x64(math_mode, monkeypatch):
+    """64x64 planes normally take the fused whole-plane kernels (fft_plane.cu); keep the general
+    row/column kernels covered at that size too."""
+    _fp32_only(math_mode)
+    monkeypatch.setenv("FFCB_FFT_TWO_PASS", "1")
+    _check_fft_pair(2, 40, 64, 64)
+
+
+def _check_fft_pair(b, c, h, w):
     """ffcb_rfft2 / ffcb_irfft2 vs numpy (float64): forward spectrum, and the inverse of a NON-Hermitian
     (ReLU'd) spectrum with the residual add — pow2 Stockham and direct-DFT sizes."""
     rng = np.random.default_rng(h * 1000 + w)
