@@ -243,8 +243,15 @@ FFCB_HD void plane64_rows_inv(Load&& ld, Store&& st) {
     }
   }
   fft64_regs<true>(v);
+  // hand the results over 16 pixels at a time so that the caller can put its 32 residual loads in
+  // flight before the dependent adds / stores (registers are full of v[]: no room to hoist all 128)
 #pragma unroll
-  for (int n = 0; n < 64; ++n) st(n, v[fft64_at(n)]);
+  for (int n0 = 0; n0 < 64; n0 += 16) {
+    float2 zb[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) zb[j] = v[fft64_at(n0 + j)];
+    st(n0, zb);
+  }
 }
 
 }  // namespace fftc

@@ -20,7 +20,7 @@ constexpr int PN = 64, PWF = 33, PCH = 8, PPITCH = PWF * PCH + 4;
 constexpr int kPlaneThreads = 288;   // 9 warps: 264 column threads, 256 row threads
 constexpr size_t kPlaneSmem = sizeof(float2) * PN * PPITCH;
 
-__global__ void __launch_bounds__(kPlaneThreads, 1) rfft2_plane64_kernel(View in, View spec, float scale) {
+__global__ void __maxnreg__(224) rfft2_plane64_kernel(View in, View spec, float scale) {
   extern __shared__ float2 S[];
   const int tid = threadIdx.x, c = tid & 7, g = tid >> 3;
   const int ch = blockIdx.x * PCH + c, b = blockIdx.y;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) rfft2_plane64_kernel(View in
   }
 }
 
-__global__ void __launch_bounds__(kPlaneThreads, 1) irfft2_plane64_kernel(View spec, View res, View out, float scale) {
+__global__ void __maxnreg__(224) irfft2_plane64_kernel(View spec, View res, View out, float scale) {
   extern __shared__ float2 S[];
   const int tid = threadIdx.x, c = tid & 7, g = tid >> 3;
   const int ch = blockIdx.x * PCH + c, b = blockIdx.y;
@@ -79,14 +79,18 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) irfft2_plane64_kernel(View s
           x1 = S[(2 * g) * PPITCH + k * PCH + c];
           x2 = S[(2 * g + 1) * PPITCH + k * PCH + c];
         },
-        [&](int n, float2 z) {
-          float a = z.x * scale, bb = z.y * scale;
-          if (has_res) {
-            a += load1(res, q0 + n * res.sx);
-            bb += load1(res, q1 + n * res.sx);
+        [&](int n0, const float2* zb) {
+          float ra[16], rb[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            ra[j] = has_res ? load1(res, q0 + (n0 + j) * res.sx) : 0.f;
+            rb[j] = has_res ? load1(res, q1 + (n0 + j) * res.sx) : 0.f;
           }
-          store1(out, r0 + n * out.sx, a);
-          store1(out, r1 + n * out.sx, bb);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            store1(out, r0 + (n0 + j) * out.sx, fmaf(zb[j].x, scale, ra[j]));
+            store1(out, r1 + (n0 + j) * out.sx, fmaf(zb[j].y, scale, rb[j]));
+          }
         });
   }
 }

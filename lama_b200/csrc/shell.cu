@@ -48,11 +48,13 @@ __global__ void __launch_bounds__(kShellThreads) stem_conv7_kernel(const float* 
   }
   __syncthreads();
 
-  float acc[4][SN];
+  // accumulators as channel pairs: Blackwell issues scalar FFMA at half rate; the packed
+  // fma.rn.f32x2 (FFMA2) does two per lane per issue slot
+  float2 acc[4][SN / 2];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int j = 0; j < SN; ++j) acc[r][j] = 0.f;
+    for (int j = 0; j < SN / 2; ++j) acc[r][j] = make_float2(0.f, 0.f);
 
   for (int ky = 0; ky < 7; ++ky) {
     for (int c = 0; c < Cin; ++c) {
@@ -61,13 +63,15 @@ __global__ void __launch_bounds__(kShellThreads) stem_conv7_kernel(const float* 
       for (int kx = 0; kx < 7; ++kx) {
         const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 7 + kx) * Cin + c) * SN);
         const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
-        const float wv[SN] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
-                              w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+        const float2 wv[SN / 2] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
+                                   make_float2(w1.z, w1.w), make_float2(w2.x, w2.y), make_float2(w2.z, w2.w),
+                                   make_float2(w3.x, w3.y), make_float2(w3.z, w3.w)};
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const float a = prow[4 * r * PW + kx];
+          const float2 aa = make_float2(a, a);
 #pragma unroll
-          for (int j = 0; j < SN; ++j) acc[r][j] = fmaf(a, wv[j], acc[r][j]);
+          for (int j = 0; j < SN / 2; ++j) acc[r][j] = __ffma2_rn(aa, wv[j], acc[r][j]);
         }
       }
     }
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(kShellThreads) stem_conv7_kernel(const float* 
     for (int q = 0; q < SN / 4; ++q) {
       const int n = n0 + 4 * q;
       if (n >= N) break;
-      float4 v = make_float4(acc[r][4 * q], acc[r][4 * q + 1], acc[r][4 * q + 2], acc[r][4 * q + 3]);
+      float4 v = make_float4(acc[r][2 * q].x, acc[r][2 * q].y, acc[r][2 * q + 1].x, acc[r][2 * q + 1].y);
       if (shift != nullptr) {
         const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + n));
         v.x += sh.x; v.y += sh.y; v.z += sh.z; v.w += sh.w;
@@ -114,11 +118,12 @@ __global__ void __launch_bounds__(kShellThreads) head_conv7_kernel(View in, cons
   const int x0 = (blockIdx.x % tiles_x) * TX, y0 = (blockIdx.x / tiles_x) * TY;
   const int b = blockIdx.y;
 
-  float acc[4][4];
+  // two partial sums per output (even / odd channels) so that every step is one packed FFMA2
+  float2 acc[4][4];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int n = 0; n < 4; ++n) acc[r][n] = 0.f;
+    for (int n = 0; n < 4; ++n) acc[r][n] = make_float2(0.f, 0.f);
 
   for (int c0 = 0; c0 < C; c0 += HC) {
     for (int i = threadIdx.x; i < PH * PW * (HC / 4); i += blockDim.x) {
@@ -146,17 +151,21 @@ __global__ void __launch_bounds__(kShellThreads) head_conv7_kernel(View in, cons
 #pragma unroll
           for (int n = 0; n < 3; ++n) {
             const float4 wv = *reinterpret_cast<const float4*>(ws + (n * 49 + ky * 7 + kx) * HC + 4 * q);
+            const float2 wlo = make_float2(wv.x, wv.y), whi = make_float2(wv.z, wv.w);
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-              acc[r][n] = fmaf(a[r + ky].x, wv.x,
-                               fmaf(a[r + ky].y, wv.y, fmaf(a[r + ky].z, wv.z, fmaf(a[r + ky].w, wv.w, acc[r][n]))));
+            for (int r = 0; r < 4; ++r) {
+              acc[r][n] = __ffma2_rn(make_float2(a[r + ky].x, a[r + ky].y), wlo, acc[r][n]);
+              acc[r][n] = __ffma2_rn(make_float2(a[r + ky].z, a[r + ky].w), whi, acc[r][n]);
+            }
           }
           if (N == 4) {
             const float4 wv = *reinterpret_cast<const float4*>(ws + (3 * 49 + ky * 7 + kx) * HC + 4 * q);
+            const float2 wlo = make_float2(wv.x, wv.y), whi = make_float2(wv.z, wv.w);
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-              acc[r][3] = fmaf(a[r + ky].x, wv.x,
-                               fmaf(a[r + ky].y, wv.y, fmaf(a[r + ky].z, wv.z, fmaf(a[r + ky].w, wv.w, acc[r][3]))));
+            for (int r = 0; r < 4; ++r) {
+              acc[r][3] = __ffma2_rn(make_float2(a[r + ky].x, a[r + ky].y), wlo, acc[r][3]);
+              acc[r][3] = __ffma2_rn(make_float2(a[r + ky].z, a[r + ky].w), whi, acc[r][3]);
+            }
           }
         }
       }
@@ -169,9 +178,12 @@ __global__ void __launch_bounds__(kShellThreads) head_conv7_kernel(View in, cons
   for (int r = 0; r < 4; ++r) {
     const int y = y0 + 4 * wy + r;
     if (y >= H) continue;
-    for (int n = 0; n < N; ++n) {
-      const float v = apply_act(acc[r][n] + (bias ? __ldg(bias + n) : 0.f), act);
-      y_out[(((long long)b * N + n) * H + y) * W + xo] = v;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {       // static indices keep acc[][] in registers
+      if (n < N) {
+        const float v = apply_act(acc[r][n].x + acc[r][n].y + (bias ? __ldg(bias + n) : 0.f), act);
+        y_out[(((long long)b * N + n) * H + y) * W + xo] = v;
+      }
     }
   }
 }

@@ -167,9 +167,12 @@ static double check_plane64(bool verbose) {
     plane64_col<true>([&](int ky) { return z[ky * WF + kx]; }, [&](int y, float2 v) { S[y * WF + kx] = v; });
   for (int g = 0; g < 32; ++g)
     plane64_rows_inv([&](int k, float2& x1, float2& x2) { x1 = S[(2 * g) * WF + k]; x2 = S[(2 * g + 1) * WF + k]; },
-                     [&](int n, float2 v) {
-                       out[(2 * g) * N + n] = v.x * scale + res[(2 * g) * N + n];
-                       out[(2 * g + 1) * N + n] = v.y * scale + res[(2 * g + 1) * N + n];
+                     [&](int n0, const float2* zb) {
+                       for (int j = 0; j < 16; ++j) {
+                         const int n = n0 + j;
+                         out[(2 * g) * N + n] = zb[j].x * scale + res[(2 * g) * N + n];
+                         out[(2 * g + 1) * N + n] = zb[j].y * scale + res[(2 * g + 1) * N + n];
+                       }
                      });
   double err_i = 0, mag_i = 0;
   std::vector<cd> t(N * WF);
