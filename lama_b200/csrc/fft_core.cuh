@@ -228,6 +228,47 @@ FFCB_HD void plane64_col(Load&& ld, Store&& st) {
   for (int k = 0; k < 64; ++k) st(k, v[fft64_at(k)]);
 }
 
+// The DC (kx = 0) and Nyquist (kx = 32) columns are special: after the real row transforms they are REAL
+// (forward), and the C2R rule only uses the REAL part of their H-inverse (inverse).  Both therefore go
+// through one complex 64-point transform (two-for-one again), which makes the column phase exactly
+// 31 + 1 = 32 transforms per channel — the same 256 threads as the 32 row pairs.
+template <class Load, class Store>
+FFCB_HD void plane64_col_fwd_packed(Load&& ld, Store&& st) {   // ld(y) -> (a0[y], a32[y]);  st(ky, X0, X32)
+  float2 v[64];
+#pragma unroll
+  for (int n = 0; n < 64; ++n) v[n] = ld(n);
+  fft64_regs<false>(v);
+#pragma unroll
+  for (int k = 0; k < 64; ++k) {
+    const float2 wk = v[fft64_at(k)], wm = v[fft64_at((64 - k) & 63)];
+    st(k, make_float2(0.5f * (wk.x + wm.x), 0.5f * (wk.y - wm.y)),
+       make_float2(0.5f * (wk.y + wm.y), -0.5f * (wk.x - wm.x)));
+  }
+}
+
+template <class Load, class Store>
+FFCB_HD void plane64_col_inv_packed(Load&& ld, Store&& st) {   // ld(ky, Z0&, Z32&);  st(y, Re T0[y], Re T32[y])
+  float2 v[64];
+#pragma unroll
+  for (int k = 0; k <= 32; ++k) {
+    const int m = (64 - k) & 63;
+    float2 a0, a32, b0, b32;
+    ld(k, a0, a32);
+    if (m != k) ld(m, b0, b32); else { b0 = a0; b32 = a32; }
+    // Hermitian parts H[k] = (Z[k] + conj(Z[-k])) / 2 : their inverse transforms are Re(ifft(Z))
+    const float2 h0 = make_float2(0.5f * (a0.x + b0.x), 0.5f * (a0.y - b0.y));
+    const float2 h32 = make_float2(0.5f * (a32.x + b32.x), 0.5f * (a32.y - b32.y));
+    v[k] = make_float2(h0.x - h32.y, h0.y + h32.x);            // H0[k] + i H32[k]
+    if (m != k) v[m] = make_float2(h0.x + h32.y, h32.x - h0.y);   // conj(H0[k]) + i conj(H32[k])
+  }
+  fft64_regs<true>(v);
+#pragma unroll
+  for (int n = 0; n < 64; ++n) {
+    const float2 z = v[fft64_at(n)];
+    st(n, z.x, z.y);
+  }
+}
+
 template <class Load, class Store>
 FFCB_HD void plane64_rows_inv(Load&& ld, Store&& st) {
   float2 v[64];

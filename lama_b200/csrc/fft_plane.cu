@@ -5,7 +5,7 @@
 // Every 64-point transform is held in the registers of ONE thread (fft64_regs: unrolled 8x8 Cooley-Tukey
 // with compile-time twiddles) — no shuffles, no shared-memory butterflies, one barrier per plane:
 //   forward : 256 threads = 8 channels x 32 row pairs (two-for-one real rows)  -> S[y][kx][c] -> barrier ->
-//             264 threads = 8 channels x 33 columns -> spectrum (Re/Im interleaved channels, scaled)
+//             8 channels x (31 complex columns + 1 packed DC/Nyquist pair) -> spectrum (Re/Im interleaved, scaled)
 //   inverse : columns first (all 33, complex), barrier, then C2R rows (+ residual).
 // smem: S[64][P] float2 with row pitch P = 33*8 + 4 (the +4 spreads the four row-pair groups of a warp
 // over both halves of the banks).  Lanes: 8 consecutive channels (32 B of a pixel) x 4 rows/columns.
@@ -17,14 +17,14 @@ namespace {
 
 using namespace fftc;
 constexpr int PN = 64, PWF = 33, PCH = 8, PPITCH = PWF * PCH + 4;
-constexpr int kPlaneThreads = 288;   // 9 warps: 264 column threads, 256 row threads
+constexpr int kPlaneThreads = 256;   // 8 channels x 32 row pairs == 8 channels x (31 columns + the packed DC/Nyquist pair)
 constexpr size_t kPlaneSmem = sizeof(float2) * PN * PPITCH;
 
-__global__ void __maxnreg__(224) rfft2_plane64_kernel(View in, View spec, float scale) {
+__global__ void __launch_bounds__(kPlaneThreads, 1) rfft2_plane64_kernel(View in, View spec, float scale) {
   extern __shared__ float2 S[];
   const int tid = threadIdx.x, c = tid & 7, g = tid >> 3;
   const int ch = blockIdx.x * PCH + c, b = blockIdx.y;
-  if (tid < 256) {   // g = row pair
+  {   // g = row pair
     const long long r0 = pix_off(in, b, 2 * g, 0) + ch, r1 = r0 + in.sy;
     plane64_rows_fwd(
         [&](int n) { return make_float2(load1(in, r0 + n * in.sx), load1(in, r1 + n * in.sx)); },
@@ -34,43 +34,58 @@ __global__ void __maxnreg__(224) rfft2_plane64_kernel(View in, View spec, float 
         });
   }
   __syncthreads();
-  if (tid < PWF * PCH) {   // g = kx
-    const long long o0 = pix_off(spec, b, 0, g) + 2 * ch;
-    plane64_col<false>(
-        [&](int y) { return S[y * PPITCH + g * PCH + c]; },
-        [&](int ky, float2 z) {
-          const long long o = o0 + ky * spec.sy;
-          z.x *= scale; z.y *= scale;
-          if (spec.fmt == FFCB_F32) {
-            *reinterpret_cast<float2*>(reinterpret_cast<float*>(spec.ptr) + o) = z;
-          } else {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(z.x, h0, l0);
-            split_bf16(z.y, h1, l1);
-            unsigned short* p = reinterpret_cast<unsigned short*>(spec.ptr);
-            *reinterpret_cast<unsigned*>(p + o) = pack_bf16(h0, h1);
-            *reinterpret_cast<unsigned*>(p + o + spec.lo_off) = pack_bf16(l0, l1);
-          }
+  auto put = [&](long long o, float2 z) {   // one spectrum bin: channels 2c (Re), 2c+1 (Im)
+    z.x *= scale; z.y *= scale;
+    if (spec.fmt == FFCB_F32) {
+      *reinterpret_cast<float2*>(reinterpret_cast<float*>(spec.ptr) + o) = z;
+    } else {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(z.x, h0, l0);
+      split_bf16(z.y, h1, l1);
+      unsigned short* p = reinterpret_cast<unsigned short*>(spec.ptr);
+      *reinterpret_cast<unsigned*>(p + o) = pack_bf16(h0, h1);
+      *reinterpret_cast<unsigned*>(p + o + spec.lo_off) = pack_bf16(l0, l1);
+    }
+  };
+  const long long o0 = pix_off(spec, b, 0, 0) + 2 * ch;
+  if (g == 0) {        // DC + Nyquist columns (real after the row pass) share one transform
+    plane64_col_fwd_packed(
+        [&](int y) { return make_float2(S[y * PPITCH + c].x, S[y * PPITCH + 32 * PCH + c].x); },
+        [&](int ky, float2 x0, float2 x32) {
+          put(o0 + ky * spec.sy, x0);
+          put(o0 + ky * spec.sy + 32 * spec.sx, x32);
         });
+  } else {             // g = kx in 1..31
+    plane64_col<false>([&](int y) { return S[y * PPITCH + g * PCH + c]; },
+                       [&](int ky, float2 z) { put(o0 + ky * spec.sy + g * spec.sx, z); });
   }
 }
 
-__global__ void __maxnreg__(224) irfft2_plane64_kernel(View spec, View res, View out, float scale) {
+__global__ void __launch_bounds__(kPlaneThreads, 1) irfft2_plane64_kernel(View spec, View res, View out, float scale) {
   extern __shared__ float2 S[];
   const int tid = threadIdx.x, c = tid & 7, g = tid >> 3;
   const int ch = blockIdx.x * PCH + c, b = blockIdx.y;
-  if (tid < PWF * PCH) {   // g = kx: inverse along H for every column (complex)
-    const long long o0 = pix_off(spec, b, 0, g) + 2 * ch;
-    plane64_col<true>(
-        [&](int ky) {
-          const long long o = o0 + ky * spec.sy;
-          if (spec.fmt == FFCB_F32) return __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(spec.ptr) + o));
-          return make_float2(load1(spec, o), load1(spec, o + 1));
+  auto get = [&](long long o) {
+    if (spec.fmt == FFCB_F32) return __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(spec.ptr) + o));
+    return make_float2(load1(spec, o), load1(spec, o + 1));
+  };
+  const long long o0 = pix_off(spec, b, 0, 0) + 2 * ch;
+  if (g == 0) {        // only Re of the H-inverse of the DC / Nyquist columns is used: one packed transform
+    plane64_col_inv_packed(
+        [&](int ky, float2& z0, float2& z32) {
+          z0 = get(o0 + ky * spec.sy);
+          z32 = get(o0 + ky * spec.sy + 32 * spec.sx);
         },
-        [&](int y, float2 z) { S[y * PPITCH + g * PCH + c] = z; });
+        [&](int y, float t0, float t32) {
+          S[y * PPITCH + c] = make_float2(t0, 0.f);
+          S[y * PPITCH + 32 * PCH + c] = make_float2(t32, 0.f);
+        });
+  } else {             // g = kx in 1..31: inverse along H (complex)
+    plane64_col<true>([&](int ky) { return get(o0 + ky * spec.sy + g * spec.sx); },
+                      [&](int y, float2 z) { S[y * PPITCH + g * PCH + c] = z; });
   }
   __syncthreads();
-  if (tid < 256) {   // g = row pair: C2R along W
+  {   // g = row pair: C2R along W
     const long long r0 = pix_off(out, b, 2 * g, 0) + ch, r1 = r0 + out.sy;
     const bool has_res = res.ptr != nullptr;
     const long long q0 = has_res ? pix_off(res, b, 2 * g, 0) + ch : 0, q1 = q0 + res.sy;

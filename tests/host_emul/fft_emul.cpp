@@ -143,7 +143,12 @@ static double check_plane64(bool verbose) {
   for (int g = 0; g < 32; ++g)
     plane64_rows_fwd([&](int n) { return make_float2(x[(2 * g) * N + n], x[(2 * g + 1) * N + n]); },
                      [&](int k, float2 a, float2 b) { S[(2 * g) * WF + k] = a; S[(2 * g + 1) * WF + k] = b; });
-  for (int kx = 0; kx < WF; ++kx)
+  plane64_col_fwd_packed([&](int y) { return make_float2(S[y * WF].x, S[y * WF + 32].x); },
+                         [&](int ky, float2 x0, float2 x32) {
+                           spec[ky * WF] = make_float2(x0.x * scale, x0.y * scale);
+                           spec[ky * WF + 32] = make_float2(x32.x * scale, x32.y * scale);
+                         });
+  for (int kx = 1; kx < 32; ++kx)
     plane64_col<false>([&](int y) { return S[y * WF + kx]; },
                        [&](int ky, float2 z) { spec[ky * WF + kx] = make_float2(z.x * scale, z.y * scale); });
   double err_f = 0, mag = 0;
@@ -163,7 +168,12 @@ static double check_plane64(bool verbose) {
                                     std::max(0.f, (float)(rand() / (double)RAND_MAX * 2 - 1)));
   std::vector<float> out(N * N), res(N * N);
   for (auto& v : res) v = (float)(rand() / (double)RAND_MAX);
-  for (int kx = 0; kx < WF; ++kx)
+  plane64_col_inv_packed([&](int ky, float2& z0, float2& z32) { z0 = z[ky * WF]; z32 = z[ky * WF + 32]; },
+                         [&](int y, float t0, float t32) {
+                           S[y * WF] = make_float2(t0, 123.f);       // imaginary parts must be ignored downstream
+                           S[y * WF + 32] = make_float2(t32, -7.f);
+                         });
+  for (int kx = 1; kx < 32; ++kx)
     plane64_col<true>([&](int ky) { return z[ky * WF + kx]; }, [&](int y, float2 v) { S[y * WF + kx] = v; });
   for (int g = 0; g < 32; ++g)
     plane64_rows_inv([&](int k, float2& x1, float2& x2) { x1 = S[(2 * g) * WF + k]; x2 = S[(2 * g + 1) * WF + k]; },
