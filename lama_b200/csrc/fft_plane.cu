@@ -48,17 +48,11 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) rfft2_plane64_kernel(View in
     }
   };
   const long long o0 = pix_off(spec, b, 0, 0) + 2 * ch;
-  if (g == 0) {        // DC + Nyquist columns (real after the row pass) share one transform
-    plane64_col_fwd_packed(
-        [&](int y) { return make_float2(S[y * PPITCH + c].x, S[y * PPITCH + 32 * PCH + c].x); },
-        [&](int ky, float2 x0, float2 x32) {
-          put(o0 + ky * spec.sy, x0);
-          put(o0 + ky * spec.sy + 32 * spec.sx, x32);
-        });
-  } else {             // g = kx in 1..31
-    plane64_col<false>([&](int y) { return S[y * PPITCH + g * PCH + c]; },
-                       [&](int ky, float2 z) { put(o0 + ky * spec.sy + g * spec.sx, z); });
-  }
+  const bool packed = g == 0;            // g = kx; task 0 carries the DC and Nyquist columns together
+  plane64_col_fwd_any(
+      packed, [&](int y) { return S[y * PPITCH + g * PCH + c]; }, [&](int y) { return S[y * PPITCH + 32 * PCH + c]; },
+      [&](int ky, float2 z) { put(o0 + ky * spec.sy + g * spec.sx, z); },
+      [&](int ky, float2 z) { put(o0 + ky * spec.sy + 32 * spec.sx, z); });
 }
 
 __global__ void __launch_bounds__(kPlaneThreads, 1) irfft2_plane64_kernel(View spec, View res, View out, float scale) {
@@ -70,20 +64,12 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) irfft2_plane64_kernel(View s
     return make_float2(load1(spec, o), load1(spec, o + 1));
   };
   const long long o0 = pix_off(spec, b, 0, 0) + 2 * ch;
-  if (g == 0) {        // only Re of the H-inverse of the DC / Nyquist columns is used: one packed transform
-    plane64_col_inv_packed(
-        [&](int ky, float2& z0, float2& z32) {
-          z0 = get(o0 + ky * spec.sy);
-          z32 = get(o0 + ky * spec.sy + 32 * spec.sx);
-        },
-        [&](int y, float t0, float t32) {
-          S[y * PPITCH + c] = make_float2(t0, 0.f);
-          S[y * PPITCH + 32 * PCH + c] = make_float2(t32, 0.f);
-        });
-  } else {             // g = kx in 1..31: inverse along H (complex)
-    plane64_col<true>([&](int ky) { return get(o0 + ky * spec.sy + g * spec.sx); },
-                      [&](int y, float2 z) { S[y * PPITCH + g * PCH + c] = z; });
-  }
+  const bool packed = g == 0;
+  plane64_col_inv_any(
+      packed, [&](int ky) { return get(o0 + ky * spec.sy + g * spec.sx); },
+      [&](int ky) { return get(o0 + ky * spec.sy + 32 * spec.sx); },
+      [&](int y, float2 z) { S[y * PPITCH + g * PCH + c] = z; },
+      [&](int y, float2 z) { S[y * PPITCH + 32 * PCH + c] = z; });
   __syncthreads();
   {   // g = row pair: C2R along W
     const long long r0 = pix_off(out, b, 2 * g, 0) + ch, r1 = r0 + out.sy;

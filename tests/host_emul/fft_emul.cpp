@@ -143,14 +143,10 @@ static double check_plane64(bool verbose) {
   for (int g = 0; g < 32; ++g)
     plane64_rows_fwd([&](int n) { return make_float2(x[(2 * g) * N + n], x[(2 * g + 1) * N + n]); },
                      [&](int k, float2 a, float2 b) { S[(2 * g) * WF + k] = a; S[(2 * g + 1) * WF + k] = b; });
-  plane64_col_fwd_packed([&](int y) { return make_float2(S[y * WF].x, S[y * WF + 32].x); },
-                         [&](int ky, float2 x0, float2 x32) {
-                           spec[ky * WF] = make_float2(x0.x * scale, x0.y * scale);
-                           spec[ky * WF + 32] = make_float2(x32.x * scale, x32.y * scale);
-                         });
-  for (int kx = 1; kx < 32; ++kx)
-    plane64_col<false>([&](int y) { return S[y * WF + kx]; },
-                       [&](int ky, float2 z) { spec[ky * WF + kx] = make_float2(z.x * scale, z.y * scale); });
+  for (int kx = 0; kx < 32; ++kx)
+    plane64_col_fwd_any(kx == 0, [&](int y) { return S[y * WF + kx]; }, [&](int y) { return S[y * WF + 32]; },
+                        [&](int ky, float2 z) { spec[ky * WF + kx] = make_float2(z.x * scale, z.y * scale); },
+                        [&](int ky, float2 z) { spec[ky * WF + 32] = make_float2(z.x * scale, z.y * scale); });
   double err_f = 0, mag = 0;
   for (int ky = 0; ky < N; ++ky)
     for (int kx = 0; kx < WF; ++kx) {
@@ -168,13 +164,9 @@ static double check_plane64(bool verbose) {
                                     std::max(0.f, (float)(rand() / (double)RAND_MAX * 2 - 1)));
   std::vector<float> out(N * N), res(N * N);
   for (auto& v : res) v = (float)(rand() / (double)RAND_MAX);
-  plane64_col_inv_packed([&](int ky, float2& z0, float2& z32) { z0 = z[ky * WF]; z32 = z[ky * WF + 32]; },
-                         [&](int y, float t0, float t32) {
-                           S[y * WF] = make_float2(t0, 123.f);       // imaginary parts must be ignored downstream
-                           S[y * WF + 32] = make_float2(t32, -7.f);
-                         });
-  for (int kx = 1; kx < 32; ++kx)
-    plane64_col<true>([&](int ky) { return z[ky * WF + kx]; }, [&](int y, float2 v) { S[y * WF + kx] = v; });
+  for (int kx = 0; kx < 32; ++kx)
+    plane64_col_inv_any(kx == 0, [&](int ky) { return z[ky * WF + kx]; }, [&](int ky) { return z[ky * WF + 32]; },
+                        [&](int y, float2 v) { S[y * WF + kx] = v; }, [&](int y, float2 v) { S[y * WF + 32] = v; });
   for (int g = 0; g < 32; ++g)
     plane64_rows_inv([&](int k, float2& x1, float2& x2) { x1 = S[(2 * g) * WF + k]; x2 = S[(2 * g + 1) * WF + k]; },
                      [&](int n0, const float2* zb) {
