@@ -236,15 +236,37 @@ __global__ void __launch_bounds__(1024) irfft_rows_kernel(const float2* __restri
   const float2* fin = fft_dispatch<N, true>(data, tmp, tw, W, lane, worker, nworkers);
 
   if (cok) {
-    for (int x = worker; x < W; x += nworkers) {
-      const float2 z = fin[x * kLanes + lane];
-      float r0 = z.x * scale, r1 = z.y * scale;
-      if (res.ptr != nullptr) {
-        r0 += load1(res, pix_off(res, b, y0, x) + c);
-        if (row1) r1 += load1(res, pix_off(res, b, y0 + 1, x) + c);
+    if (N > 0) {
+      // power-of-two lengths: every worker owns exactly 8 pixels.  Put all residual loads in flight first —
+      // the compiler cannot hoist them above the stores itself (res / out may alias as far as it knows).
+      float ra[8], rb[8];
+      const long long q0 = res.ptr ? pix_off(res, b, y0, 0) + c : 0, o0 = pix_off(out, b, y0, 0) + c;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int x = worker + i * nworkers;
+        ra[i] = (res.ptr != nullptr && x < W) ? load1(res, q0 + x * res.sx) : 0.f;
+        rb[i] = (res.ptr != nullptr && x < W && row1) ? load1(res, q0 + res.sy + x * res.sx) : 0.f;
       }
-      store1(out, pix_off(out, b, y0, x) + c, r0);
-      if (row1) store1(out, pix_off(out, b, y0 + 1, x) + c, r1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int x = worker + i * nworkers;
+        if (x < W) {
+          const float2 z = fin[x * kLanes + lane];
+          store1(out, o0 + x * out.sx, fmaf(z.x, scale, ra[i]));
+          if (row1) store1(out, o0 + out.sy + x * out.sx, fmaf(z.y, scale, rb[i]));
+        }
+      }
+    } else {
+      for (int x = worker; x < W; x += nworkers) {
+        const float2 z = fin[x * kLanes + lane];
+        float r0 = z.x * scale, r1 = z.y * scale;
+        if (res.ptr != nullptr) {
+          r0 += load1(res, pix_off(res, b, y0, x) + c);
+          if (row1) r1 += load1(res, pix_off(res, b, y0 + 1, x) + c);
+        }
+        store1(out, pix_off(out, b, y0, x) + c, r0);
+        if (row1) store1(out, pix_off(out, b, y0 + 1, x) + c, r1);
+      }
     }
   }
 }
@@ -375,7 +397,9 @@ int irfft2(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tens
     return FFCB_ENOMEM;
   }
   if (out->B == 0 || out->C == 0) return FFCB_OK;
-  if (plane64_eligible(out) && !getenv("FFCB_FFT_TWO_PASS")) return irfft2_plane64(spec, residual, out, stream);
+  // the fused inverse plane kernel is correct but (round 1) slower than the two-pass kernels: opt-in only
+  if (plane64_eligible(out) && getenv("FFCB_FFT_INV_PLANE") && !getenv("FFCB_FFT_TWO_PASS"))
+    return irfft2_plane64(spec, residual, out, stream);
   const View vspec = make_view(*spec), vout = make_view(*out);
   float2* w2 = reinterpret_cast<float2*>(ws);
   const int cblocks = (out->C + kLanes - 1) / kLanes;

@@ -89,6 +89,13 @@ def test_two_pass_fft_kernels_at_64x64(math_mode, monkeypatch):
     _check_fft_pair(2, 40, 64, 64)
 
 
+def test_inverse_plane_kernel_opt_in(math_mode, monkeypatch):
+    """The fused inverse plane kernel (fft_plane.cu) is opt-in in round 1 (slower than two-pass); keep it correct."""
+    _fp32_only(math_mode)
+    monkeypatch.setenv("FFCB_FFT_INV_PLANE", "1")
+    _check_fft_pair(2, 24, 64, 64)
+
+
 def _check_fft_pair(b, c, h, w):
     """ffcb_rfft2 / ffcb_irfft2 vs numpy (float64): forward spectrum, and the inverse of a NON-Hermitian
     (ReLU'd) spectrum with the residual add — pow2 Stockham and direct-DFT sizes."""

@@ -53,4 +53,12 @@ for w in want:
         os.environ["FFCB_TC_DEBUG"] = str(dbg)
         row.append(time_call(idx[w]))
     os.environ["FFCB_TC_DEBUG"] = "0"
+    if w == "ffcb_irfft2":
+        os.environ["FFCB_FFT_INV_PLANE"] = "1"
+        row.append(time_call(idx[w]))
+        del os.environ["FFCB_FFT_INV_PLANE"]
+    if w in ("ffcb_rfft2", "ffcb_irfft2"):
+        os.environ["FFCB_FFT_TWO_PASS"] = "1"
+        row.append(time_call(idx[w]))
+        del os.environ["FFCB_FFT_TWO_PASS"]
     print(f"{w:45s} " + " ".join(f"{v:10.1f}" for v in row))
