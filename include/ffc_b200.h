@@ -69,7 +69,9 @@ typedef struct {
                       reflect_border!=0: producers also write the reflected border ring so
                       that TMA tiles of 3x3 taps need no index math. */
   int32_t reflect_border;
-  int32_t _reserved;
+  int32_t window;  /* != 0: "sliding window" view — consecutive pixels overlap (sx < C): pixel x exposes the C
+                      contiguous elements starting at x*sx.  Used to feed the 7x7 stem to ffcb_conv as 7 K-segments
+                      of (8 taps x 8 channels) read straight out of a packed NHWC8 image (see ffcb_stem_pack). */
 } ffcb_tensor;
 
 /* One K-segment of an implicit-GEMM convolution: `nch` input channels starting at channel
@@ -133,6 +135,16 @@ int ffcb_conv(const ffcb_conv_desc* desc, ffcb_stream_t stream);
  */
 int ffcb_stem_conv7(const float* x_nchw, int B, int Cin, int H, int W, const float* w, const float* shift,
                     int N, const ffcb_tensor* out, ffcb_stream_t stream);
+
+/*
+ * Stem, tensor-core form.  ffcb_stem_pack writes the generator input as a reflect-padded (3 pixels) channels-last
+ * image with 8 channels per pixel (Cin real + zeros), rows of W+8 pixels (the tail is zero), in split bf16:
+ *     packed[b][yp][xp][c],  yp in [0,H+6), xp in [0,W+8),  = x[b][c][reflect(yp-3)][reflect(xp-3)]
+ * A window view of it (C = 64, sx = 8, window = 1) exposes, at pixel x, the 8 taps x 8 channels of one kernel
+ * row as ONE contiguous 128-byte K block, so ReflectionPad2d(3) + Conv2d(k7) (ffc.py:315-317) becomes an
+ * ffcb_conv with seven K-segments (dy = 0..6, dx = 0) and zero-padded weights [N][7][8 taps][8 channels].
+ */
+int ffcb_stem_pack(const float* x_nchw, int B, int Cin, int H, int W, const ffcb_tensor* packed, ffcb_stream_t stream);
 
 /*
  * Head: ReflectionPad2d(3) + Conv2d(C -> N<=4, k7, bias) + activation, NCHW float output.

@@ -24,7 +24,7 @@ class Tensor(C.Structure):
     """``ffcb_tensor``"""
     _fields_ = [("ptr", C.c_void_p), ("sb", C.c_int64), ("sy", C.c_int64), ("sx", C.c_int64),
                 ("lo_off", C.c_int64), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
-                ("fmt", C.c_int32), ("pad", C.c_int32), ("reflect_border", C.c_int32), ("_reserved", C.c_int32)]
+                ("fmt", C.c_int32), ("pad", C.c_int32), ("reflect_border", C.c_int32), ("window", C.c_int32)]
 
 
 class KSeg(C.Structure):
@@ -50,6 +50,7 @@ SIGNATURES = {
     "ffcb_conv": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "ffcb_stem_conv7": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                   _PT, C.c_void_p]),
+    "ffcb_stem_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _PT, C.c_void_p]),
     "ffcb_head_conv7": (C.c_int, [_PT, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ffcb_fft2_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ffcb_rfft2": (C.c_int, [_PT, _PT, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -37,7 +37,8 @@ int check_tensor(const ffcb_tensor* t, const char* name) {
   FFCB_REQUIRE(((uintptr_t)t->ptr % align) == 0, "%s: pointer %p not %zu-byte aligned", name, t->ptr, (size_t)align);
   FFCB_REQUIRE(t->sx % 4 == 0 && t->sy % 4 == 0 && t->sb % 4 == 0, "%s: strides must be multiples of 4 elements",
                name);
-  FFCB_REQUIRE(t->sx >= t->C, "%s: pixel stride %lld < C=%d", name, (long long)t->sx, t->C);
+  FFCB_REQUIRE(t->sx >= t->C || t->window, "%s: pixel stride %lld < C=%d (only window views may overlap)", name,
+               (long long)t->sx, t->C);
   if (t->fmt == FFCB_BF16X2)
     FFCB_REQUIRE(t->lo_off % 4 == 0 && t->lo_off != 0, "%s: lo_off must be a non-zero multiple of 4", name);
   FFCB_REQUIRE(t->pad == 0 || t->pad == 1, "%s: pad must be 0 or 1", name);
@@ -56,6 +57,7 @@ int irfft2(const ffcb_tensor*, const ffcb_tensor*, const ffcb_tensor*, void*, si
 int nchw_to_nhwc(const float*, int, int, int, int, const ffcb_tensor*, cudaStream_t);
 int nhwc_to_nchw(const ffcb_tensor*, float*, cudaStream_t);
 int fill_reflect_border(const ffcb_tensor*, cudaStream_t);
+int stem_pack(const float*, int, int, int, int, const ffcb_tensor*, cudaStream_t);
 
 static int check_conv(const ffcb_conv_desc* d) {
   FFCB_REQUIRE(d != nullptr, "conv: null descriptor");
@@ -131,6 +133,10 @@ int ffcb_conv(const ffcb_conv_desc* d, ffcb_stream_t stream) {
 int ffcb_stem_conv7(const float* x, int B, int Cin, int H, int W, const float* w, const float* shift, int N,
                     const ffcb_tensor* out, ffcb_stream_t stream) {
   return stem_conv7(x, B, Cin, H, W, w, shift, N, out, (cudaStream_t)stream);
+}
+
+int ffcb_stem_pack(const float* x, int B, int Cin, int H, int W, const ffcb_tensor* packed, ffcb_stream_t stream) {
+  return stem_pack(x, B, Cin, H, W, packed, (cudaStream_t)stream);
 }
 
 int ffcb_head_conv7(const ffcb_tensor* in, const float* w, const float* bias, int N, int act, float* y,

@@ -117,7 +117,7 @@ int irfft2_plane64(const ffcb_tensor* spec, const ffcb_tensor* residual, const f
   FFCB_CUDA(cudaFuncSetAttribute(irfft2_plane64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlaneSmem));
   dim3 grid(out->C / PCH, out->B);
   const View vres = (residual && residual->ptr) ? make_view(*residual) : null_view();
-  irfft2_plane64_kernel<<<grid, kFwdThreads, kPlaneSmem, stream>>>(make_view(*spec), vres, make_view(*out), 1.0f / 64.0f);
+  irfft2_plane64_kernel<<<grid, kPlaneThreads, kPlaneSmem, stream>>>(make_view(*spec), vres, make_view(*out), 1.0f / 64.0f);
   FFCB_LAUNCH_CHECK("irfft2_plane64_kernel");
   return FFCB_OK;
 }

@@ -99,6 +99,32 @@ __global__ void __launch_bounds__(kShellThreads) stem_conv7_kernel(const float* 
   }
 }
 
+// ---------------------------------------------------------------------------------------- stem pack
+// NCHW float -> reflect-padded NHWC8 (split bf16 or fp32): one thread per padded pixel, 8 channels = one
+// 16-byte (bf16) store per plane.  Feeds the tensor-core stem through a sliding-window view.
+__global__ void stem_pack_kernel(const float* __restrict__ x, int Cin, int H, int W, View out) {
+  const int Wp = out.W, Hp = out.H;           // W + 8, H + 6
+  const long long total = (long long)out.B * Hp * Wp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int xp = (int)(i % Wp);
+    const int yp = (int)((i / Wp) % Hp);
+    const int b = (int)(i / ((long long)Wp * Hp));
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+    if (xp < W + 6) {
+      const int yy = reflect_idx(yp - HALO, H), xx = reflect_idx(xp - HALO, W);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < Cin) v[c] = __ldg(x + (((long long)b * Cin + c) * H + yy) * W + xx);
+    }
+    const long long o = pix_off(out, b, yp, xp);
+    store4(out, o, make_float4(v[0], v[1], v[2], v[3]));
+    store4(out, o + 4, make_float4(v[4], v[5], v[6], v[7]));
+  }
+}
+
 // ---------------------------------------------------------------------------------------- head
 // Register tile: 4 vertically adjacent pixels x (N <= 4) outputs per thread.  For one (kx, channel quad)
 // the 10 patch rows a thread needs are loaded once (float4, conflict-free: pixel pitch 20 floats) and
@@ -260,6 +286,22 @@ int stem_conv7(const float* x, int B, int Cin, int H, int W, const float* w, con
   dim3 grid(((W + TX - 1) / TX) * ((H + TY - 1) / TY), B, (N + SN - 1) / SN);
   stem_conv7_kernel<<<grid, kShellThreads, smem, stream>>>(x, B, Cin, H, W, w, shift, N, make_view(*out));
   FFCB_LAUNCH_CHECK("stem_conv7_kernel");
+  return FFCB_OK;
+}
+
+int stem_pack(const float* x, int B, int Cin, int H, int W, const ffcb_tensor* packed, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_tensor(packed, "stem_pack.packed"))) return rc;
+  FFCB_REQUIRE(x != nullptr, "stem_pack: null input");
+  FFCB_REQUIRE(Cin >= 1 && Cin <= 8, "stem_pack: Cin=%d outside [1,8]", Cin);
+  FFCB_REQUIRE(H >= 4 && W >= 4, "stem_pack: reflect pad 3 needs H,W >= 4");
+  FFCB_REQUIRE(packed->B == B && packed->H == H + 6 && packed->W == W + 8 && packed->C == 8 && !packed->window,
+               "stem_pack: packed view must be (B, H+6, W+8, 8)");
+  const long long total = (long long)B * (H + 6) * (W + 8);
+  if (total == 0) return FFCB_OK;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  stem_pack_kernel<<<blocks, 256, 0, stream>>>(x, Cin, H, W, make_view(*packed));
+  FFCB_LAUNCH_CHECK("stem_pack_kernel");
   return FFCB_OK;
 }
 

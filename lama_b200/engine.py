@@ -55,13 +55,18 @@ class TV:
     c0: int = 0
     C: Optional[int] = None
     phase: Optional[Tuple[int, int]] = None   # (a, b): pixels (2i+a, 2j+b) of the buffer
+    window: int = 0                           # sliding-window view: pixel x exposes pixels x..x+window-1 (C*window channels)
 
     @property
     def channels(self) -> int:
+        if self.window:
+            return self.buf.C * self.window
         return self.buf.C - self.c0 if self.C is None else self.C
 
     @property
     def hw(self) -> Tuple[int, int]:
+        if self.window:
+            return (self.buf.H, self.buf.W - self.window)
         return (self.buf.H // 2, self.buf.W // 2) if self.phase else (self.buf.H, self.buf.W)
 
 
@@ -84,6 +89,14 @@ class StemOp:
     w: torch.Tensor   # [(ky*7+kx)*Cin + c][N]
     shift: torch.Tensor
     out: TV
+
+
+@dataclass
+class StemPackOp:
+    """NCHW float input -> reflect-padded NHWC8 image for the tensor-core stem (ffcb_stem_pack)."""
+    src: str
+    cin: int
+    out: TV           # Buf (B, H+6, W+8, 8)
 
 
 @dataclass
@@ -465,7 +478,14 @@ def build_generator_program(prog: Program, gen, shape):
     s0, b0 = P.bn_scale_shift(stem.bn_l)
     wst, shst = P.pack_stem(conv.weight, s0, b0, device=dev)
     X = prog.buf("stem", b, h, w, n0, gemm=True, halo=True)
-    prog.ops.append(StemOp("x0", cin, wst, shst, TV(X)))
+    if prog.math == L.MATH_BF16X3 and cin <= 8 and n0 % 8 == 0 and os.environ.get("LAMA_B200_STEM", "tc") == "tc":
+        # tensor-core stem: the 7x7 window of the packed image is 7 contiguous 128-byte K blocks per pixel
+        Pk = prog.buf("stem.packed", b, h + 6, w + 8, 8, gemm=True)
+        prog.ops.append(StemPackOp("x0", cin, TV(Pk)))
+        pk = P.pack_stem_windowed(conv.weight, s0, b0, device=dev)
+        prog.ops.append(ConvOp(pk, [TV(Pk, window=8), None], TV(X), tag="stem 7x7 (windowed)+bn+relu"))
+    else:
+        prog.ops.append(StemOp("x0", cin, wst, shst, TV(X)))
     cl, cg = n0, 0
     for d in downs:
         X, cl, cg = emit_ffc_bn_act(prog, d, X, cl, cg)
@@ -513,7 +533,7 @@ def insert_border_ops(prog: Program):
                     del dirty[id(tv.buf)]
         out.append(op)
         wrote = None
-        if isinstance(op, (ToNHWC, StemOp, IrfftOp, ConvOp)):
+        if isinstance(op, (ToNHWC, StemOp, StemPackOp, IrfftOp, ConvOp)):
             wrote = op.out
         elif isinstance(op, RfftOp):
             wrote = op.spec
@@ -571,6 +591,8 @@ class CudaExecutor:
         t.fmt, t.pad, t.reflect_border = b.fmt, b.pad, b.reflect_border
         if tv.phase is not None:     # a sub-pixel phase is not a contiguous image: no ring semantics
             t.pad, t.reflect_border = 0, 0
+        if tv.window:                # pixel x exposes the buf.C * window contiguous elements starting at x * sx
+            t.W, t.C, t.window = b.W - tv.window, b.C * tv.window, 1
         return t
 
     def _ref(self, obj):
@@ -601,6 +623,11 @@ class CudaExecutor:
             self.input_slots.setdefault(op.src, []).append((len(self.calls), 0))
             self.calls.append(("ffcb_stem_conv7", lib.ffcb_stem_conv7,
                                [None, bb, c, h, w, wd.data_ptr(), sd.data_ptr(), wd.shape[1], C.byref(t)]))
+        elif isinstance(op, StemPackOp):
+            bb, c, h, w = self.prog.inputs[op.src]
+            t = self._ref(self.tensor(op.out))
+            self.input_slots.setdefault(op.src, []).append((len(self.calls), 0))
+            self.calls.append(("ffcb_stem_pack", lib.ffcb_stem_pack, [None, bb, c, h, w, C.byref(t)]))
         elif isinstance(op, HeadOp):
             t = self._ref(self.tensor(op.inp))
             wd, bd = self._dev(op.w), self._dev(op.bias)

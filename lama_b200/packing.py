@@ -159,6 +159,23 @@ def pack_stem(weight: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, de
     return w, sh
 
 
+def pack_stem_windowed(weight: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, device=None) -> PackedConv:
+    """7x7 stem (ffc.py:316) for the tensor-core arm: seven K-segments (one per kernel row, dy = 0..6 into the
+    reflect-padded packed image) of 64 = 8 taps x 8 channels; tap 7 and channels >= Cin carry zero weights.
+    K index inside a segment = kx*8 + c, matching the sliding-window view of ffcb_stem_pack's output."""
+    w = weight.detach().double() * scale.double()[:, None, None, None]           # [N, Cin, 7, 7]
+    n, cin = w.shape[0], w.shape[1]
+    assert cin <= 8 and w.shape[2] == 7 and w.shape[3] == 7
+    full = torch.zeros(n, 7, 8, 8, dtype=torch.float64, device=w.device)         # [N, ky, kx, c]
+    full[:, :, :7, :cin] = w.permute(0, 2, 3, 1)
+    w_kn = full.reshape(n, 7 * 64).t().contiguous().float()
+    sh = shift.float().contiguous()
+    if device is not None:
+        w_kn, sh = w_kn.to(device), sh.to(device)
+    segs = [Seg(0, ky, 0, 0, 64) for ky in range(7)]
+    return PackedConv(segs=segs, n_out=n, w_kn=w_kn, shift=sh, stride=1, border=L.BORDER_ZERO, act=L.ACT_RELU)
+
+
 def pack_head(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None):
     """7x7 head (ffc.py:361): [N, C, 7, 7] -> float [N][49][C]; bias [N]."""
     w = weight.detach().float().permute(0, 2, 3, 1).reshape(weight.shape[0], 49, weight.shape[1]).contiguous()

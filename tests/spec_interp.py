@@ -18,6 +18,9 @@ class SpecInterpreter:
 
     def read(self, tv: E.TV) -> torch.Tensor:
         t = self.mem[tv.buf.name]
+        if tv.window:      # sliding-window view: pixel x exposes pixels x .. x+window-1, channel index = j*C + c
+            w_out = tv.buf.W - tv.window
+            return torch.cat([t[:, :, j:j + w_out] for j in range(tv.window)], dim=-1)
         if tv.phase is not None:
             a, b = tv.phase
             t = t[:, a::2, b::2]
@@ -38,6 +41,10 @@ class SpecInterpreter:
                 self.write(op.out, inputs[op.src].double().permute(0, 2, 3, 1))
             elif isinstance(op, E.ToNCHW):
                 out[op.dst] = self.read(op.inp).permute(0, 3, 1, 2).contiguous()
+            elif isinstance(op, E.StemPackOp):
+                x = torch.nn.functional.pad(inputs[op.src].double(), (3, 3, 3, 3), mode="reflect")
+                x = torch.nn.functional.pad(x, (0, 2, 0, 0, 0, 8 - op.cin))          # W+6 -> W+8, Cin -> 8 (zeros)
+                self.write(op.out, x.permute(0, 2, 3, 1))
             elif isinstance(op, E.StemOp):
                 x = torch.nn.functional.pad(inputs[op.src].double(), (3, 3, 3, 3), mode="reflect")
                 cin = op.cin

@@ -124,7 +124,8 @@ def test_bf16x3_program_layout_and_semantics():
     assert by["st.t"].fmt == L.F32 and by["spectrum_out"].fmt == L.F32
     assert prog.bufs[-1].name.startswith("up") and prog.bufs[-1].fmt == L.F32      # head input
     ops = prog.ops
-    assert isinstance(ops[0], E.StemOp) and isinstance(ops[1], E.BorderOp)
+    assert isinstance(ops[0], E.StemPackOp) and isinstance(ops[1], E.ConvOp) and isinstance(ops[2], E.BorderOp)
+    assert ops[1].ins[0].window == 8 and len(ops[1].packed.segs) == 7
     # ring discipline: whenever a contraction reads a ring buffer, the last op that touched that buffer
     # before it is a BorderOp (no producer writes rings), and no BorderOp is redundant.
     last = {}
