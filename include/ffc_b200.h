@@ -65,9 +65,9 @@ typedef struct {
   int64_t lo_off;  /* FFCB_BF16X2: offset (elements) from the hi to the lo plane */
   int32_t B, H, W, C;
   int32_t fmt;     /* FFCB_F32 | FFCB_BF16X2 */
-  int32_t pad;     /* physical border pixels around the interior (0 or 1).  pad==1 and
-                      reflect_border!=0: producers also write the reflected border ring so
-                      that TMA tiles of 3x3 taps need no index math. */
+  int32_t pad;     /* physical border pixels around the interior (0..3).  With reflect_border != 0 the ring holds
+                      the reflected image (ffcb_fill_reflect_border), so that the TMA tile of tap (dy,dx),
+                      |dy|,|dx| <= pad, is the output tile shifted by (dx,dy) — no index math. */
   int32_t reflect_border;
   int32_t window;  /* != 0: "sliding window" view — consecutive pixels overlap (sx < C): pixel x exposes the C
                       contiguous elements starting at x*sx.  Used to feed the 7x7 stem to ffcb_conv as 7 K-segments
@@ -173,6 +173,15 @@ size_t ffcb_fft2_workspace_bytes(int B, int H, int W, int C);
 int ffcb_rfft2(const ffcb_tensor* in, const ffcb_tensor* spec, void* ws, size_t ws_bytes, ffcb_stream_t stream);
 int ffcb_irfft2(const ffcb_tensor* spec, const ffcb_tensor* residual /* nullable */, const ffcb_tensor* out,
                 void* ws, size_t ws_bytes, ffcb_stream_t stream);
+
+/*
+ * Head, tensor-core form (ffc.py:360-363).  The 7x7 convolution to N <= 3 outputs is split into
+ *   (1) an ffcb_conv over the kernel ROWS only — seven K-segments (dy = -3..3, dx = 0) producing, for every input
+ *       column, the 7*N partial sums q[b,y,x',n*7+kx] = sum_ky sum_c in[b,y+ky-3,x',c] * w[n,c,ky,kx], and
+ *   (2) this gather: y[b,n,y,x] = act(bias[n] + sum_kx q[b,y,reflect(x+kx-3),n*7+kx])   (NCHW float output).
+ * q: float view (B,H,W,>=7N).
+ */
+int ffcb_head_gather7(const ffcb_tensor* q, const float* bias, int N, int act, float* y_nchw, ffcb_stream_t stream);
 
 /* Layout/format conversion at the module boundary (the reference's tensors are NCHW float):
  * ffc.py has no counterpart — these replace nothing, they adapt torch's layout to the path's. */

@@ -41,7 +41,7 @@ int check_tensor(const ffcb_tensor* t, const char* name) {
                (long long)t->sx, t->C);
   if (t->fmt == FFCB_BF16X2)
     FFCB_REQUIRE(t->lo_off % 4 == 0 && t->lo_off != 0, "%s: lo_off must be a non-zero multiple of 4", name);
-  FFCB_REQUIRE(t->pad == 0 || t->pad == 1, "%s: pad must be 0 or 1", name);
+  FFCB_REQUIRE(t->pad >= 0 && t->pad <= 3, "%s: pad must be in [0,3]", name);
   (void)esz;
   return FFCB_OK;
 }
@@ -58,6 +58,7 @@ int nchw_to_nhwc(const float*, int, int, int, int, const ffcb_tensor*, cudaStrea
 int nhwc_to_nchw(const ffcb_tensor*, float*, cudaStream_t);
 int fill_reflect_border(const ffcb_tensor*, cudaStream_t);
 int stem_pack(const float*, int, int, int, int, const ffcb_tensor*, cudaStream_t);
+int head_gather7(const ffcb_tensor*, const float*, int, int, float*, cudaStream_t);
 
 static int check_conv(const ffcb_conv_desc* d) {
   FFCB_REQUIRE(d != nullptr, "conv: null descriptor");
@@ -137,6 +138,10 @@ int ffcb_stem_conv7(const float* x, int B, int Cin, int H, int W, const float* w
 
 int ffcb_stem_pack(const float* x, int B, int Cin, int H, int W, const ffcb_tensor* packed, ffcb_stream_t stream) {
   return stem_pack(x, B, Cin, H, W, packed, (cudaStream_t)stream);
+}
+
+int ffcb_head_gather7(const ffcb_tensor* q, const float* bias, int N, int act, float* y, ffcb_stream_t stream) {
+  return head_gather7(q, bias, N, act, y, (cudaStream_t)stream);
 }
 
 int ffcb_head_conv7(const ffcb_tensor* in, const float* w, const float* bias, int N, int act, float* y,

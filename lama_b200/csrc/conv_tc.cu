@@ -495,9 +495,13 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   FFCB_REQUIRE(d->out.B > 0, "conv(tc): empty batch");
   FFCB_REQUIRE((long long)d->out.B * d->out.H * d->out.W < (1ll << 31), "conv(tc): more than 2^31 output pixels");
   bool used[2] = {false, false}, taps[2] = {false, false};
+  int reach[2] = {0, 0};       // furthest tap offset per source: the ring must be at least that wide
   for (int i = 0; i < d->nseg; ++i) {
     used[d->seg[i].src] = true;
     if (d->seg[i].dx != 0 || d->seg[i].dy != 0) taps[d->seg[i].src] = true;
+    const int ax = d->seg[i].dx < 0 ? -d->seg[i].dx : d->seg[i].dx, ay = d->seg[i].dy < 0 ? -d->seg[i].dy : d->seg[i].dy;
+    if (ax > reach[d->seg[i].src]) reach[d->seg[i].src] = ax;
+    if (ay > reach[d->seg[i].src]) reach[d->seg[i].src] = ay;
     FFCB_REQUIRE(d->seg[i].c0 % 8 == 0, "conv(tc): segment %d starts at channel %d (must be a multiple of 8)", i,
                  d->seg[i].c0);
   }
@@ -508,7 +512,8 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     FFCB_REQUIRE(t.sx % 8 == 0 && t.sy % 8 == 0 && t.sb % 8 == 0 && t.lo_off % 8 == 0 && ((uintptr_t)t.ptr % 16) == 0,
                  "conv(tc): in[%d] strides / pointer not 16-byte aligned", s);
     if (taps[s] && d->border == FFCB_BORDER_REFLECT)
-      FFCB_REQUIRE(t.pad == 1 && t.reflect_border, "conv(tc): in[%d] needs a reflected border ring (pad=1)", s);
+      FFCB_REQUIRE(t.pad >= reach[s] && t.reflect_border, "conv(tc): in[%d] needs a reflected border ring of %d pixels",
+                   s, reach[s]);
   }
 
   TcParams p;
@@ -572,8 +577,8 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
       if ((rc = encode(&maps[s], t.ptr, 3, dims, str, box, es, "flat activations"))) return rc;
     } else {
       const bool ring = taps[s] && d->border == FFCB_BORDER_REFLECT;
-      const int off = ring ? 1 : 0;
-      char* base = (char*)t.ptr - (ring ? ((int64_t)t.sy + t.sx) * (int64_t)esz : 0);
+      const int off = ring ? t.pad : 0;
+      char* base = (char*)t.ptr - (int64_t)off * ((int64_t)t.sy + t.sx) * (int64_t)esz;
       cuuint64_t dims[5] = {(cuuint64_t)t.C, (cuuint64_t)(t.W + 2 * off), (cuuint64_t)(t.H + 2 * off),
                             (cuuint64_t)t.B, 2};
       cuuint64_t str[4] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.sy * esz, (cuuint64_t)t.sb * esz,

@@ -247,23 +247,47 @@ __global__ void nhwc_to_nchw_kernel(View in, float* __restrict__ yo) {
   }
 }
 
-// Reflected ring of a pad==1 view: ring pixel (y, x) with y in {-1, H} or x in {-1, W}
-// copies interior pixel (reflect(y), reflect(x)).
+// Reflected ring of a padded view (pad = 1..3): every pixel of the padded plane outside the interior copies
+// interior pixel (reflect(y), reflect(x)).
 __global__ void reflect_ring_kernel(View t) {
-  const int ring = 2 * (t.W + 2) + 2 * t.H;  // ring pixels per image
+  const int p = t.pad, Hp = t.H + 2 * p, Wp = t.W + 2 * p;
   const int c4 = t.C / 4;
-  const long long total = (long long)t.B * ring * c4;
+  const long long total = (long long)t.B * Hp * Wp * c4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(i % c4);
     const long long pi = i / c4;
-    const int r = (int)(pi % ring), b = (int)(pi / ring);
-    int y, x;
-    if (r < t.W + 2) { y = -1; x = r - 1; }
-    else if (r < 2 * (t.W + 2)) { y = t.H; x = r - (t.W + 2) - 1; }
-    else { const int s = r - 2 * (t.W + 2); y = s >> 1; x = (s & 1) ? t.W : -1; }
+    const int x = (int)(pi % Wp) - p;
+    const int y = (int)((pi / Wp) % Hp) - p;
+    const int b = (int)(pi / ((long long)Wp * Hp));
+    if (y >= 0 && y < t.H && x >= 0 && x < t.W) continue;
     const float4 v = load4(t, pix_off(t, b, reflect_idx(y, t.H), reflect_idx(x, t.W)) + 4 * q);
     store4(t, pix_off(t, b, y, x) + 4 * q, v);
+  }
+}
+
+// Head gather: y[b,n,y,x] = act(bias[n] + sum_kx q[b,y,reflect(x+kx-3),n*7+kx]).  One CTA = 128 consecutive
+// pixels of a row; the (128+6) x 7N partial sums are staged through shared memory (row pitch 7N+1: conflict-free).
+constexpr int GT = 128;
+__global__ void __launch_bounds__(GT) head_gather7_kernel(View q, const float* __restrict__ bias, int N, int act,
+                                                          float* __restrict__ y_out) {
+  extern __shared__ float tile[];
+  const int nq = 7 * N, pitch = nq + 1;
+  const int tiles_x = (q.W + GT - 1) / GT;
+  const int x0 = (blockIdx.x % tiles_x) * GT, y = blockIdx.x / tiles_x, b = blockIdx.y;
+  for (int i = threadIdx.x; i < (GT + 6) * nq; i += GT) {
+    const int px = i / nq, j = i % nq;
+    const int xx = min(max(reflect_idx(x0 + px - 3, q.W), 0), q.W - 1);
+    tile[px * pitch + j] = load1(q, pix_off(q, b, y, xx) + j);
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x;
+  if (x >= q.W) return;
+  for (int n = 0; n < N; ++n) {
+    float acc = bias ? __ldg(bias + n) : 0.f;
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) acc += tile[(threadIdx.x + kx) * pitch + n * 7 + kx];
+    y_out[(((long long)b * N + n) * q.H + y) * q.W + x] = apply_act(acc, act);
   }
 }
 
@@ -302,6 +326,20 @@ int stem_pack(const float* x, int B, int Cin, int H, int W, const ffcb_tensor* p
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   stem_pack_kernel<<<blocks, 256, 0, stream>>>(x, Cin, H, W, make_view(*packed));
   FFCB_LAUNCH_CHECK("stem_pack_kernel");
+  return FFCB_OK;
+}
+
+int head_gather7(const ffcb_tensor* q, const float* bias, int N, int act, float* y, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_tensor(q, "head_gather7.q"))) return rc;
+  FFCB_REQUIRE(y != nullptr, "head_gather7: null output");
+  FFCB_REQUIRE(N >= 1 && N <= 4 && q->C >= 7 * N, "head_gather7: need 1 <= N <= 4 and q.C >= 7N (N=%d, C=%d)", N, q->C);
+  FFCB_REQUIRE(q->W >= 4 && q->B <= 65535, "head_gather7: W >= 4 and B <= 65535 required");
+  if (q->B == 0) return FFCB_OK;
+  dim3 grid(((q->W + GT - 1) / GT) * q->H, q->B);
+  const size_t smem = sizeof(float) * (GT + 6) * (7 * N + 1);
+  head_gather7_kernel<<<grid, GT, smem, stream>>>(make_view(*q), bias, N, act, y);
+  FFCB_LAUNCH_CHECK("head_gather7_kernel");
   return FFCB_OK;
 }
 
@@ -348,9 +386,9 @@ int nhwc_to_nchw(const ffcb_tensor* in, float* y, cudaStream_t stream) {
 int fill_reflect_border(const ffcb_tensor* t, cudaStream_t stream) {
   int rc;
   if ((rc = check_tensor(t, "fill_reflect_border"))) return rc;
-  FFCB_REQUIRE(t->pad == 1, "fill_reflect_border: view has no border ring (pad=%d)", t->pad);
-  FFCB_REQUIRE(t->H >= 2 && t->W >= 2, "fill_reflect_border: reflect needs H,W >= 2");
-  const long long total = (long long)t->B * (2 * (t->W + 2) + 2 * t->H) * (t->C / 4);
+  FFCB_REQUIRE(t->pad >= 1, "fill_reflect_border: view has no border ring (pad=%d)", t->pad);
+  FFCB_REQUIRE(t->H > t->pad && t->W > t->pad, "fill_reflect_border: reflect needs H,W > pad");
+  const long long total = (long long)t->B * (t->H + 2 * t->pad) * (t->W + 2 * t->pad) * (t->C / 4);
   if (total == 0) return FFCB_OK;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   reflect_ring_kernel<<<blocks, 256, 0, stream>>>(make_view(*t));

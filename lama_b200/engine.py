@@ -110,6 +110,16 @@ class HeadOp:
 
 
 @dataclass
+class HeadGatherOp:
+    """y = act(bias + sum_kx q[.., reflect(x+kx-3), n*7+kx]) -> external NCHW output (ffcb_head_gather7)."""
+    q: TV
+    bias: torch.Tensor
+    n_out: int
+    act: int
+    dst: str
+
+
+@dataclass
 class ConvOp:
     packed: P.PackedConv
     ins: List[Optional[TV]]
@@ -147,14 +157,15 @@ class Program:
     inputs: Dict[str, Tuple[int, ...]] = field(default_factory=dict)    # name -> NCHW shape
     outputs: Dict[str, Tuple[int, ...]] = field(default_factory=dict)
 
-    def buf(self, name, B, H, W, C, gemm=False, halo=False) -> Buf:
+    def buf(self, name, B, H, W, C, gemm=False, halo=False, halo_px=1) -> Buf:
         """``gemm``: the buffer is an operand of a contraction; ``halo``: that contraction has spatial taps.
         FFCB_MATH_BF16X3 stores gemm operands as split bf16, and gives halo buffers a reflected border
         ring so that the TMA box of tap (dy,dx) is the tile shifted by (dx,dy); everything else (FFT
         inputs, spectra leaving the GEMM, the head's input) stays float32 without padding."""
         tc = self.math == L.MATH_BF16X3 and gemm
-        ring = 1 if (tc and halo) else 0
-        b = Buf(f"{name}#{len(self.bufs)}", B, H, W, C, pad=ring, fmt=L.BF16X2 if tc else L.F32, reflect_border=ring)
+        ring = halo_px if (tc and halo) else 0
+        b = Buf(f"{name}#{len(self.bufs)}", B, H, W, C, pad=ring, fmt=L.BF16X2 if tc else L.F32,
+                reflect_border=1 if ring else 0)
         self.bufs.append(b)
         return b
 
@@ -492,15 +503,26 @@ def build_generator_program(prog: Program, gen, shape):
     for blk in blocks:
         X = emit_resnet_block(prog, blk, X, cl, cg, in_place=True)
     # ConcatTupleLayer (ffc.py:295-302) is free: x_l | x_g already share X.
+    tc_head = (prog.math == L.MATH_BF16X3 and head.in_channels % 8 == 0 and head.out_channels <= 3
+               and min(h, w) > 3 and os.environ.get("LAMA_B200_HEAD", "tc") == "tc")
     for iu, (ct, bn) in enumerate(ups):
         sc, sh = P.bn_scale_shift(bn)
-        last = iu == len(ups) - 1          # the head is a CUDA-core kernel: keep its input float32
-        Yb = prog.buf("up", b, X.H * 2, X.W * 2, ct.out_channels, gemm=not last, halo=not last)
+        last = iu == len(ups) - 1
+        # tensor-core head: its row contraction reads 3 pixels up and down -> ring of 3; CUDA-core head: float32
+        Yb = prog.buf("up", b, X.H * 2, X.W * 2, ct.out_channels, gemm=(not last) or tc_head,
+                      halo=(not last) or tc_head, halo_px=3 if last else 1)
         for a, bb, pk in P.pack_conv_transpose_phases(ct.weight, ct.bias, sc, sh, act=L.ACT_RELU, device=dev):
             prog.ops.append(ConvOp(pk, [TV(X), None], TV(Yb, phase=(a, bb)), tag=f"convT phase {a}{bb}+bn+relu"))
         X = Yb
-    wh, bh = P.pack_head(head.weight, head.bias, device=dev)
-    prog.ops.append(HeadOp(TV(X), wh, bh, head.out_channels, out_act, "y0"))
+    if tc_head and ups:
+        pkh = P.pack_head_rows(head.weight, device=dev)
+        Q = prog.buf("head.q", b, h, w, pkh.n_out)
+        prog.ops.append(ConvOp(pkh, [TV(X), None], TV(Q), tag="head 7x7 rows"))
+        bias = head.bias.detach().float().contiguous() if head.bias is not None else torch.zeros(head.out_channels)
+        prog.ops.append(HeadGatherOp(TV(Q), bias.to(dev), head.out_channels, out_act, "y0"))
+    else:
+        wh, bh = P.pack_head(head.weight, head.bias, device=dev)
+        prog.ops.append(HeadOp(TV(X), wh, bh, head.out_channels, out_act, "y0"))
     prog.outputs["y0"] = (b, head.out_channels, h, w)
 
 
@@ -634,6 +656,11 @@ class CudaExecutor:
             self.calls.append(("ffcb_head_conv7", lib.ffcb_head_conv7,
                                [C.byref(t), wd.data_ptr(), bd.data_ptr(), op.n_out, op.act,
                                 self.outputs[op.dst].data_ptr()]))
+        elif isinstance(op, HeadGatherOp):
+            t = self._ref(self.tensor(op.q))
+            bd = self._dev(op.bias)
+            self.calls.append(("ffcb_head_gather7", lib.ffcb_head_gather7,
+                               [C.byref(t), bd.data_ptr(), op.n_out, op.act, self.outputs[op.dst].data_ptr()]))
         elif isinstance(op, ConvOp):
             d = self._ref(L.ConvDesc())
             pk = op.packed

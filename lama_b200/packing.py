@@ -176,6 +176,22 @@ def pack_stem_windowed(weight: torch.Tensor, scale: torch.Tensor, shift: torch.T
     return PackedConv(segs=segs, n_out=n, w_kn=w_kn, shift=sh, stride=1, border=L.BORDER_ZERO, act=L.ACT_RELU)
 
 
+def pack_head_rows(weight: torch.Tensor, device=None) -> PackedConv:
+    """7x7 head (ffc.py:361) for the tensor-core arm, kernel-ROW part: output channel n*7+kx of the contraction is
+    sum_ky sum_c in[y+ky-3, x', c] * w[n, c, ky, kx]; seven K-segments (dy = ky-3, dx = 0).  N*7 is padded to a
+    multiple of 8 with zero rows.  Bias and activation are applied by ffcb_head_gather7."""
+    w = weight.detach().double()                                   # [N, C, 7, 7]
+    n, c = w.shape[0], w.shape[1]
+    nq = (7 * n + 7) // 8 * 8
+    rows = torch.zeros(nq, 7, c, dtype=torch.float64, device=w.device)          # [(n,kx), ky, c]
+    rows[: 7 * n] = w.permute(0, 3, 2, 1).reshape(7 * n, 7, c)
+    w_kn = rows.reshape(nq, 7 * c).t().contiguous().float()
+    if device is not None:
+        w_kn = w_kn.to(device)
+    segs = [Seg(0, ky - 3, 0, 0, c) for ky in range(7)]
+    return PackedConv(segs=segs, n_out=nq, w_kn=w_kn, shift=None, stride=1, border=L.BORDER_REFLECT, act=L.ACT_NONE)
+
+
 def pack_head(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None):
     """7x7 head (ffc.py:361): [N, C, 7, 7] -> float [N][49][C]; bias [N]."""
     w = weight.detach().float().permute(0, 2, 3, 1).reshape(weight.shape[0], 49, weight.shape[1]).contiguous()

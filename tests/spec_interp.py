@@ -59,6 +59,18 @@ class SpecInterpreter:
                 y = {L.ACT_NONE: y, L.ACT_RELU: y.clamp_min(0), L.ACT_SIGMOID: torch.sigmoid(y),
                      L.ACT_TANH: torch.tanh(y)}[op.act]
                 out[op.dst] = y
+            elif isinstance(op, E.HeadGatherOp):
+                q = self.read(op.q)                                   # [B,H,W,>=7N]
+                w = q.shape[2]
+                xi = torch.arange(w)[:, None] + torch.arange(7)[None, :] - 3           # [W,7]
+                xi = xi.abs(); xi = torch.where(xi >= w, 2 * w - 2 - xi, xi)
+                ys = []
+                for n in range(op.n_out):
+                    g = q[:, :, :, n * 7:n * 7 + 7]                  # [B,H,W,7]
+                    ys.append(sum(g[:, :, xi[:, kx], kx] for kx in range(7)) + float(op.bias[n]))
+                y = torch.stack(ys, dim=1)
+                out[op.dst] = {L.ACT_NONE: y, L.ACT_RELU: y.clamp_min(0), L.ACT_SIGMOID: torch.sigmoid(y),
+                               L.ACT_TANH: torch.tanh(y)}[op.act]
             elif isinstance(op, E.ConvOp):
                 ins = [self.read(tv) if tv is not None else None for tv in op.ins]
                 assert all(not torch.isnan(t).any() for t in ins if t is not None), f"{op.tag}: reads unwritten data"

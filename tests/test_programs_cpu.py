@@ -122,7 +122,9 @@ def test_bf16x3_program_layout_and_semantics():
     assert by["spectrum"].fmt == L.BF16X2 and by["spectrum"].pad == 0
     assert by["st.u"].fmt == L.BF16X2 and by["st.u"].pad == 0
     assert by["st.t"].fmt == L.F32 and by["spectrum_out"].fmt == L.F32
-    assert prog.bufs[-1].name.startswith("up") and prog.bufs[-1].fmt == L.F32      # head input
+    up_last = [b for b in prog.bufs if b.name.startswith("up")][-1]
+    assert up_last.fmt == L.BF16X2 and up_last.pad == 3       # tensor-core head: 3-pixel reflected ring
+    assert isinstance(prog.ops[-1], E.HeadGatherOp) and prog.ops[-2].tag == "head 7x7 rows"
     ops = prog.ops
     assert isinstance(ops[0], E.StemPackOp) and isinstance(ops[1], E.ConvOp) and isinstance(ops[2], E.BorderOp)
     assert ops[1].ins[0].window == 8 and len(ops[1].packed.segs) == 7
@@ -142,7 +144,7 @@ def test_bf16x3_program_layout_and_semantics():
             if isinstance(w, E.TV) and w.buf.reflect_border:
                 last[w.buf.name] = "write"
     n_border = sum(isinstance(o, E.BorderOp) for o in ops)
-    assert n_border == 4 + 2 * 2 + 2      # stem + 3 stride-2 outputs | 2 blocks x (Y, X) | 2 split up-sampled outputs
+    assert n_border == 4 + 2 * 2 + 3      # stem + 3 stride-2 outputs | 2 blocks x (Y, X) | 3 split up-sampled outputs
     out = SpecInterpreter(prog).run({"x0": x})
     assert float(np.abs(out["y0"].numpy() - a["y"]).max()) < 2e-6
     # weights of the tcgen05 arm: [2][N][Kpad], K padded per segment to 64
