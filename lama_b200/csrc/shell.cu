@@ -250,17 +250,21 @@ __global__ void nhwc_to_nchw_kernel(View in, float* __restrict__ yo) {
 // Reflected ring of a padded view (pad = 1..3): every pixel of the padded plane outside the interior copies
 // interior pixel (reflect(y), reflect(x)).
 __global__ void reflect_ring_kernel(View t) {
-  const int p = t.pad, Hp = t.H + 2 * p, Wp = t.W + 2 * p;
+  const int p = t.pad, Wp = t.W + 2 * p;
+  const int band = p * Wp;                       // pixels of the top (and of the bottom) band
+  const int ring = 2 * band + 2 * p * t.H;       // ring pixels per image
   const int c4 = t.C / 4;
-  const long long total = (long long)t.B * Hp * Wp * c4;
+  const long long total = (long long)t.B * ring * c4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(i % c4);
     const long long pi = i / c4;
-    const int x = (int)(pi % Wp) - p;
-    const int y = (int)((pi / Wp) % Hp) - p;
-    const int b = (int)(pi / ((long long)Wp * Hp));
-    if (y >= 0 && y < t.H && x >= 0 && x < t.W) continue;
+    int r = (int)(pi % ring);
+    const int b = (int)(pi / ring);
+    int y, x;
+    if (r < band) { y = r / Wp - p; x = r % Wp - p; }
+    else if (r < 2 * band) { r -= band; y = t.H + r / Wp; x = r % Wp - p; }
+    else { r -= 2 * band; y = r / (2 * p); const int j = r % (2 * p); x = j < p ? j - p : t.W + (j - p); }
     const float4 v = load4(t, pix_off(t, b, reflect_idx(y, t.H), reflect_idx(x, t.W)) + 4 * q);
     store4(t, pix_off(t, b, y, x) + 4 * q, v);
   }
@@ -388,7 +392,7 @@ int fill_reflect_border(const ffcb_tensor* t, cudaStream_t stream) {
   if ((rc = check_tensor(t, "fill_reflect_border"))) return rc;
   FFCB_REQUIRE(t->pad >= 1, "fill_reflect_border: view has no border ring (pad=%d)", t->pad);
   FFCB_REQUIRE(t->H > t->pad && t->W > t->pad, "fill_reflect_border: reflect needs H,W > pad");
-  const long long total = (long long)t->B * (t->H + 2 * t->pad) * (t->W + 2 * t->pad) * (t->C / 4);
+  const long long total = (long long)t->B * (2 * t->pad * (t->W + 2 * t->pad) + 2 * t->pad * t->H) * (t->C / 4);
   if (total == 0) return FFCB_OK;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   reflect_ring_kernel<<<blocks, 256, 0, stream>>>(make_view(*t));
