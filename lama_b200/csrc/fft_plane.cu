@@ -9,6 +9,8 @@
 //   inverse : columns first (all 33, complex), barrier, then C2R rows (+ residual).
 // smem: S[64][P] float2 with row pitch P = 33*8 + 4 (the +4 spreads the four row-pair groups of a warp
 // over both halves of the banks).  Lanes: 8 consecutive channels (32 B of a pixel) x 4 rows/columns.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "fft_core.cuh"
 
@@ -99,6 +101,47 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) irfft2_plane64_kernel(View s
   }
 }
 
+// Inverse, 9-warp variant (FFCB_FFT_INV_PLANE=2): 264 independent column tasks (no packing), then 256 row tasks.
+__global__ void __launch_bounds__(kFwdThreads, 1) irfft2_plane64_9w_kernel(View spec, View res, View out, float scale) {
+  extern __shared__ float2 S[];
+  const int tid = threadIdx.x, c = tid & 7, g = tid >> 3;
+  const int ch = blockIdx.x * PCH + c, b = blockIdx.y;
+  if (tid < PWF * PCH) {   // g = kx
+    const long long o0 = pix_off(spec, b, 0, g) + 2 * ch;
+    plane64_col<true>(
+        [&](int ky) {
+          const long long o = o0 + ky * spec.sy;
+          if (spec.fmt == FFCB_F32) return __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(spec.ptr) + o));
+          return make_float2(load1(spec, o), load1(spec, o + 1));
+        },
+        [&](int y, float2 z) { S[y * PPITCH + g * PCH + c] = z; });
+  }
+  __syncthreads();
+  if (tid < 256) {   // g = row pair
+    const long long r0 = pix_off(out, b, 2 * g, 0) + ch, r1 = r0 + out.sy;
+    const bool has_res = res.ptr != nullptr;
+    const long long q0 = has_res ? pix_off(res, b, 2 * g, 0) + ch : 0, q1 = q0 + res.sy;
+    plane64_rows_inv(
+        [&](int k, float2& x1, float2& x2) {
+          x1 = S[(2 * g) * PPITCH + k * PCH + c];
+          x2 = S[(2 * g + 1) * PPITCH + k * PCH + c];
+        },
+        [&](int n0, const float2* zb) {
+          float ra[16], rb[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            ra[j] = has_res ? load1(res, q0 + (n0 + j) * res.sx) : 0.f;
+            rb[j] = has_res ? load1(res, q1 + (n0 + j) * res.sx) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            store1(out, r0 + (n0 + j) * out.sx, fmaf(zb[j].x, scale, ra[j]));
+            store1(out, r1 + (n0 + j) * out.sx, fmaf(zb[j].y, scale, rb[j]));
+          }
+        });
+  }
+}
+
 }  // namespace
 
 bool plane64_eligible(const ffcb_tensor* real) {
@@ -114,9 +157,16 @@ int rfft2_plane64(const ffcb_tensor* in, const ffcb_tensor* spec, cudaStream_t s
 }
 
 int irfft2_plane64(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out, cudaStream_t stream) {
-  FFCB_CUDA(cudaFuncSetAttribute(irfft2_plane64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlaneSmem));
   dim3 grid(out->C / PCH, out->B);
   const View vres = (residual && residual->ptr) ? make_view(*residual) : null_view();
+  const char* variant = getenv("FFCB_FFT_INV_PLANE");
+  if (variant && variant[0] == '2') {
+    FFCB_CUDA(cudaFuncSetAttribute(irfft2_plane64_9w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlaneSmem));
+    irfft2_plane64_9w_kernel<<<grid, kFwdThreads, kPlaneSmem, stream>>>(make_view(*spec), vres, make_view(*out), 1.0f / 64.0f);
+    FFCB_LAUNCH_CHECK("irfft2_plane64_9w_kernel");
+    return FFCB_OK;
+  }
+  FFCB_CUDA(cudaFuncSetAttribute(irfft2_plane64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlaneSmem));
   irfft2_plane64_kernel<<<grid, kPlaneThreads, kPlaneSmem, stream>>>(make_view(*spec), vres, make_view(*out), 1.0f / 64.0f);
   FFCB_LAUNCH_CHECK("irfft2_plane64_kernel");
   return FFCB_OK;

@@ -89,10 +89,12 @@ def test_two_pass_fft_kernels_at_64x64(math_mode, monkeypatch):
     _check_fft_pair(2, 40, 64, 64)
 
 
-def test_inverse_plane_kernel_opt_in(math_mode, monkeypatch):
-    """The fused inverse plane kernel (fft_plane.cu) is opt-in in round 1 (slower than two-pass); keep it correct."""
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_inverse_plane_kernel_opt_in(math_mode, monkeypatch, variant):
+    """The fused inverse plane kernels (fft_plane.cu; 1 = packed 8-warp, 2 = 9-warp) are opt-in in round 1
+    (not faster than two-pass yet); keep them correct."""
     _fp32_only(math_mode)
-    monkeypatch.setenv("FFCB_FFT_INV_PLANE", "1")
+    monkeypatch.setenv("FFCB_FFT_INV_PLANE", variant)
     _check_fft_pair(2, 24, 64, 64)
 
 

@@ -54,8 +54,9 @@ for w in want:
         row.append(time_call(idx[w]))
     os.environ["FFCB_TC_DEBUG"] = "0"
     if w == "ffcb_irfft2":
-        os.environ["FFCB_FFT_INV_PLANE"] = "1"
-        row.append(time_call(idx[w]))
+        for variant in ("1", "2"):
+            os.environ["FFCB_FFT_INV_PLANE"] = variant
+            row.append(time_call(idx[w]))
         del os.environ["FFCB_FFT_INV_PLANE"]
     if w in ("ffcb_rfft2", "ffcb_irfft2"):
         os.environ["FFCB_FFT_TWO_PASS"] = "1"
