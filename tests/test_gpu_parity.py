@@ -383,3 +383,24 @@ def test_errors_are_loud(math_mode):
         d.out = L.Tensor(t.data_ptr(), 128, 32, 8, 0, 1, 4, 4, 6, 0, 0, 0, 0)
         d.n_out, d.nseg, d.stride, d.weight = 6, 1, 1, t.data_ptr()
         L.check(lib.ffcb_conv(d, None), "ffcb_conv")
+
+
+def test_serving_pipeline_matches_module_call(math_mode):
+    """lama_b200.serving.GeneratorPipeline (overlapped H2D / graph replay / D2H) returns exactly what the
+    module call returns, for several in-flight batches and slot reuse."""
+    from lama_b200.serving import GeneratorPipeline
+    a, sd = load_golden("generator_ngf8_b2_64x64")
+    g = _load(M.FFCResNetGenerator(**small_lama_kwargs(ngf=8, n_blocks=2)), sd)
+    pipe = GeneratorPipeline(g, 2, 64, 64, depth=2)
+    xs = [torch.from_numpy(a["x"]).roll(i, dims=0).contiguous().pin_memory() for i in range(5)]
+    with torch.no_grad():
+        want = [g(x.to(DEV)).cpu() for x in xs]
+    tickets = []
+    got = []
+    for i, x in enumerate(xs):
+        tickets.append(pipe.submit(x))
+        if i >= 1:
+            got.append(pipe.result(tickets[i - 1]).clone())
+    got.append(pipe.result(tickets[-1]).clone())
+    for w, y in zip(want, got):
+        assert torch.equal(w, y)

@@ -25,13 +25,21 @@ print("by kernel:")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"  {t / 1e3:9.3f} ms {100 * t / tot:5.1f}%  n={n:4d}  avg {t / n:9.1f} us  {k}")
 if len(sys.argv) > 2:
-    names = []
-    for c in (l.strip() for l in open(sys.argv[2])):
-        names += [c + "#rows", c + "#cols"] if c == "ffcb_rfft2" else ([c + "#cols", c + "#rows"] if c == "ffcb_irfft2" else [c])
-    if len(names) == len(rows):
-        agg = collections.OrderedDict()
-        for n, r in zip(names, rows):
-            a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += us(r)
+    # map launches to program ops: an FFT op is one launch (fused plane kernel) or two (row + column pass)
+    calls = [l.strip() for l in open(sys.argv[2])]
+    agg = collections.OrderedDict()
+    i, ok = 0, True
+    for c in calls:
+        if i >= len(rows):
+            ok = False
+            break
+        n = 1
+        if c in ("ffcb_rfft2", "ffcb_irfft2") and "plane" not in rows[i]["Kernel Name"]:
+            n = 2
+        t = sum(us(r) for r in rows[i:i + n])
+        i += n
+        a = agg.setdefault(c, [0, 0.0]); a[0] += 1; a[1] += t
+    if ok and i == len(rows):
         print("\nby op (program order):")
         for k, (n, t) in agg.items():
             print(f"  {t / 1e3:9.3f} ms {100 * t / tot:5.1f}%  n={n:4d}  avg {t / n:9.1f} us  {k}")
