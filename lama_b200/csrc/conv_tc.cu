@@ -159,6 +159,50 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Residual (addend) row of one pixel: 32 consecutive channels as eight 16-byte loads.
+// split bf16: raw[0..3] = hi plane (64 B), raw[4..7] = lo plane; fp32: raw[0..7] = 128 B.  `left` = channels that
+// exist from this offset on (tail of N): quads beyond it are not loaded and decode to zero.
+__device__ __forceinline__ void fetch_addend(const View& a, bool on, long long off, int left, uint4* raw) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) raw[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (!on) return;
+  if (a.fmt == FFCB_F32) {
+    const float* p = reinterpret_cast<const float*>(a.ptr) + off;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (4 * i < left) raw[i] = __ldg(reinterpret_cast<const uint4*>(p + 4 * i));
+  } else {
+    const unsigned short* p = reinterpret_cast<const unsigned short*>(a.ptr) + off;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (8 * i < left) {
+        raw[i] = __ldg(reinterpret_cast<const uint4*>(p + 8 * i));
+        raw[4 + i] = __ldg(reinterpret_cast<const uint4*>(p + a.lo_off + 8 * i));
+      }
+  }
+}
+
+__device__ __forceinline__ void decode_addend(const View& a, const uint4* raw, float* ad) {
+  if (a.fmt == FFCB_F32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ad[4 * i] = __uint_as_float(raw[i].x); ad[4 * i + 1] = __uint_as_float(raw[i].y);
+      ad[4 * i + 2] = __uint_as_float(raw[i].z); ad[4 * i + 3] = __uint_as_float(raw[i].w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned h[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+      const unsigned l[4] = {raw[4 + i].x, raw[4 + i].y, raw[4 + i].z, raw[4 + i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ad[8 * i + 2 * k] = __uint_as_float(h[k] << 16) + __uint_as_float(l[k] << 16);
+        ad[8 * i + 2 * k + 1] = __uint_as_float(h[k] & 0xffff0000u) + __uint_as_float(l[k] & 0xffff0000u);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ kernel
 struct TileCoord {
   int b, y0, x0;       // spatial: first output pixel of the tile
@@ -341,26 +385,22 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       const int box_x = tc.x0 + (wq * 32) % p.TW, box_y = tc.y0 + (wq * 32) / p.TW;
       const int c_end = (p.debug & 2) ? 0 : p.BN;
 
+      // residual rows do not depend on the accumulator: request the first chunk's before waiting for the MMAs,
+      // and each following chunk's while the current one is converted and stored (eight 16-byte loads per lane)
+      uint4 raw[8];
+      fetch_addend(p.addend, has_add && valid && half * 32 < c_end, o_add + n_tile * p.BN + half * 32,
+                   p.N - (n_tile * p.BN + half * 32), raw);
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kAccStride);
       for (int c0 = half * 32; c0 < c_end; c0 += 64) {
         const int n0 = n_tile * p.BN + c0;
-        // residual / addend row of this pixel: 32 channels, independent 16-byte loads
+        // residual / addend row of this pixel (32 channels) was requested one chunk ahead: raw[] holds it
         float ad[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) ad[j] = 0.f;
-        if (has_add && valid) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (n0 + 4 * q < p.N) {
-              const float4 a = load4(p.addend, o_add + n0 + 4 * q);
-              ad[4 * q] = a.x; ad[4 * q + 1] = a.y; ad[4 * q + 2] = a.z; ad[4 * q + 3] = a.w;
-            }
-          }
-        }
+        decode_addend(p.addend, raw, ad);
         uint32_t r[32];
         tmem_ld32(t_row + (uint32_t)c0, r);
+        fetch_addend(p.addend, has_add && valid && c0 + 64 < c_end, o_add + n0 + 64, p.N - (n0 + 64), raw);
         float v[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
