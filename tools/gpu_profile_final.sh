@@ -1,0 +1,11 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+OUT=gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv python tools/profile_step.py bf16x3 32 > $OUT/prof1.log 2>&1
+echo "launch list rc=$?"
+timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 8 -c 4 -o $OUT/conv_tc_final -f python tools/profile_step.py bf16x3 32 > $OUT/prof2.log 2>&1
+echo "conv_tc full rc=$?"
+timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"rfft2_plane64|irfft_rows|fft_cols_inv" -s 3 -c 3 -o $OUT/fft_final -f python tools/profile_step.py bf16x3 32 > $OUT/prof3.log 2>&1
+echo "fft full rc=$?"
