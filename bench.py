@@ -45,6 +45,19 @@ def _peaks():
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def _ncu_traffic(prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    (profiles/r01_traffic.json, bs32 512x512); None if the capture is not there."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.isfile(p):
+        return None
+    with open(p) as fh:
+        for k, v in json.load(fh).items():
+            if k.startswith(prefix):
+                return v
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -309,7 +322,8 @@ def main():
         roof = {"kernel": "conv_simt_kernel" if math == L.MATH_FP32 else "conv_tc_kernel",
                 "op": "resblock local 3x3 contraction (convl2l+convg2l+bn_l+relu): M=B*64*64, N=128, K=9*512",
                 "bound": "tensor", "achieved": ach, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_burst"], "traffic": None, "ms_per_launch": ms_c,
+                "frac": ach / peaks["bf16_burst"], "traffic": _ncu_traffic("L:") if (B, S) == (32, 512) else None,
+                "ms_per_launch": ms_c,
                 "algorithmic_flops_per_launch": flops, "peak_source": peaks["source"] + ", bf16 burst",
                 "note": "fp32 CUDA-core arm (FFCB_MATH_FP32)" if math == L.MATH_FP32 else
                         "bf16x3 tcgen05 arm: 3 bf16 products per algorithmic MAC"}
