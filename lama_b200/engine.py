@@ -56,12 +56,21 @@ class TV:
     C: Optional[int] = None
     phase: Optional[Tuple[int, int]] = None   # (a, b): pixels (2i+a, 2j+b) of the buffer
     window: int = 0                           # sliding-window view: pixel x exposes pixels x..x+window-1 (C*window channels)
+    b0: int = 0                               # batch slice [b0, b0+nb)
+    nb: Optional[int] = None
 
     @property
     def channels(self) -> int:
         if self.window:
             return self.buf.C * self.window
         return self.buf.C - self.c0 if self.C is None else self.C
+
+    @property
+    def batch(self) -> int:
+        return self.buf.B - self.b0 if self.nb is None else self.nb
+
+    def bslice(self, b0: int, nb: int) -> "TV":
+        return TV(self.buf, self.c0, self.C, self.phase, self.window, self.b0 + b0, nb)
 
     @property
     def hw(self) -> Tuple[int, int]:
@@ -173,9 +182,9 @@ class Program:
         need = 0
         for op in self.ops:
             if isinstance(op, RfftOp):
-                b, (h, w), c = op.inp.buf.B, op.inp.hw, op.inp.channels
+                b, (h, w), c = op.inp.batch, op.inp.hw, op.inp.channels
             elif isinstance(op, IrfftOp):
-                b, (h, w), c = op.out.buf.B, op.out.hw, op.out.channels
+                b, (h, w), c = op.out.batch, op.out.hw, op.out.channels
             else:
                 continue
             need = max(need, 8 * b * h * (w // 2 + 1) * c)
@@ -330,21 +339,39 @@ def _fold(bn, n, device):
     return torch.ones(n, dtype=torch.float64, device=device), torch.zeros(n, dtype=torch.float64, device=device)
 
 
+def fu_batch_chunk(batch: int, h: int, w: int, c: int) -> int:
+    """Images per pass of the rfft2 -> GEMM -> irfft2 chain.  The chain's intermediates (spectrum in, spectrum
+    out, row-pass workspace: ~3 x 8 bytes x c x h x (w/2+1) per image) are written and read back to back; running
+    it over slices of the batch keeps them inside the 126 MB L2 instead of round-tripping through HBM.
+    LAMA_B200_FU_CHUNK overrides (0 = whole batch)."""
+    env = os.environ.get("LAMA_B200_FU_CHUNK")
+    if env is not None:
+        n = int(env)
+        return batch if n <= 0 else min(batch, n)
+    per_image = 3 * 8 * c * h * (w // 2 + 1)
+    n = max(1, (48 << 20) // max(per_image, 1))       # ~48 MB of intermediates in flight
+    return batch if n >= batch else n
+
+
 def emit_fourier_unit(prog: Program, fu, t: TV, out: TV, residual: Optional[TV]):
     """FourierUnit (ffc.py:76-113): rfft2 -> [1x1 conv + BN + ReLU] on the interleaved spectrum -> irfft2,
     optionally with the SpectralTransform residual fused into the inverse (out = residual + fu(t))."""
-    b = t.buf.B
+    b = t.batch
     h, w = t.hw
     wf = w // 2 + 1
     cin2, cout2 = fu.conv_layer.in_channels, fu.conv_layer.out_channels
     S = prog.buf("spectrum", b, h, wf, cin2, gemm=True)
     Z = prog.buf("spectrum_out", b, h, wf, cout2)
-    prog.ops.append(RfftOp(t, TV(S)))
     scale, shift = P.bn_scale_shift(fu.bn)
     pk = P.pack_conv([(fu.conv_layer.weight, 0, 0, 0)], scale, shift, act=L.ACT_RELU,
                      device=fu.conv_layer.weight.device)
-    prog.ops.append(ConvOp(pk, [TV(S), None], TV(Z), tag="fu.conv_layer+bn+relu"))
-    prog.ops.append(IrfftOp(TV(Z), residual, out))
+    chunk = fu_batch_chunk(b, h, w, cin2 // 2) if prog.math == L.MATH_BF16X3 else b
+    for b0 in range(0, b, chunk):
+        nb = min(chunk, b - b0)
+        prog.ops.append(RfftOp(t.bslice(b0, nb), TV(S).bslice(b0, nb)))
+        prog.ops.append(ConvOp(pk, [TV(S).bslice(b0, nb), None], TV(Z).bslice(b0, nb), tag="fu.conv_layer+bn+relu"))
+        prog.ops.append(IrfftOp(TV(Z).bslice(b0, nb), residual.bslice(b0, nb) if residual is not None else None,
+                                out.bslice(b0, nb)))
 
 
 def emit_spectral_transform(prog: Program, st, x: TV, u_consumer=None) -> Tuple[TV, P.PackedConv]:
@@ -606,10 +633,12 @@ class CudaExecutor:
             off += a * sy + bb * sx
             sy, sx, h, w = 2 * sy, 2 * sx, b.H // 2, b.W // 2
         t = L.Tensor()
-        t.ptr = st.data_ptr() + off * es
+        t.ptr = 0  # set below (after the batch-slice offset)
         t.sb, t.sy, t.sx = sb, sy, sx
         t.lo_off = b.B * hp * wp * b.C if b.fmt == L.BF16X2 else 0
-        t.B, t.H, t.W, t.C = b.B, h, w, tv.channels
+        off += tv.b0 * sb
+        t.ptr = st.data_ptr() + off * es
+        t.B, t.H, t.W, t.C = tv.batch, h, w, tv.channels
         t.fmt, t.pad, t.reflect_border = b.fmt, b.pad, b.reflect_border
         if tv.phase is not None:     # a sub-pixel phase is not a contiguous image: no ring semantics
             t.pad, t.reflect_border = 0, 0

@@ -17,7 +17,7 @@ class SpecInterpreter:
         self.mem = {b.name: torch.full((b.B, b.H, b.W, b.C), float("nan"), dtype=torch.float64) for b in prog.bufs}
 
     def read(self, tv: E.TV) -> torch.Tensor:
-        t = self.mem[tv.buf.name]
+        t = self.mem[tv.buf.name][tv.b0:tv.b0 + tv.batch]
         if tv.window:      # sliding-window view: pixel x exposes pixels x .. x+window-1, channel index = j*C + c
             w_out = tv.buf.W - tv.window
             return torch.cat([t[:, :, j:j + w_out] for j in range(tv.window)], dim=-1)
@@ -27,7 +27,7 @@ class SpecInterpreter:
         return t[..., tv.c0:tv.c0 + tv.channels]
 
     def write(self, tv: E.TV, val: torch.Tensor):
-        t = self.mem[tv.buf.name]
+        t = self.mem[tv.buf.name][tv.b0:tv.b0 + tv.batch]
         if tv.phase is not None:
             a, b = tv.phase
             t[:, a::2, b::2, tv.c0:tv.c0 + tv.channels] = val
