@@ -340,17 +340,13 @@ def _fold(bn, n, device):
 
 
 def fu_batch_chunk(batch: int, h: int, w: int, c: int) -> int:
-    """Images per pass of the rfft2 -> GEMM -> irfft2 chain.  The chain's intermediates (spectrum in, spectrum
-    out, row-pass workspace: ~3 x 8 bytes x c x h x (w/2+1) per image) are written and read back to back; running
-    it over slices of the batch keeps them inside the 126 MB L2 instead of round-tripping through HBM.
-    LAMA_B200_FU_CHUNK overrides (0 = whole batch)."""
-    env = os.environ.get("LAMA_B200_FU_CHUNK")
-    if env is not None:
-        n = int(env)
-        return batch if n <= 0 else min(batch, n)
-    per_image = 3 * 8 * c * h * (w // 2 + 1)
-    n = max(1, (48 << 20) // max(per_image, 1))       # ~48 MB of intermediates in flight
-    return batch if n >= batch else n
+    """Images per pass of the rfft2 -> GEMM -> irfft2 chain.  Running the chain over slices of the batch keeps
+    its intermediates inside the 126 MB L2, but measured on B200 (bs32, 512x512: 624 img/s unsliced vs 600-620
+    with 6..16-image slices, profiles/r01_fu_chunk_sweep.txt) the extra launches and partial waves cost more than
+    the L2 hits save — the kernels are latency- not bandwidth-bound.  Default: whole batch;
+    LAMA_B200_FU_CHUNK=n slices."""
+    n = int(os.environ.get("LAMA_B200_FU_CHUNK", "0"))
+    return batch if n <= 0 else min(batch, n)
 
 
 def emit_fourier_unit(prog: Program, fu, t: TV, out: TV, residual: Optional[TV]):
