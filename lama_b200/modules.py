@@ -25,7 +25,7 @@ import torch.nn.functional as F
 from . import engine as _engine
 
 __all__ = ["FFCSE_block", "FourierUnit", "SpectralTransform", "FFC", "FFC_BN_ACT", "FFCResnetBlock",
-           "ConcatTupleLayer", "FFCResNetGenerator", "get_activation"]
+           "ConcatTupleLayer", "FFCResNetGenerator", "FFCNLayerDiscriminator", "get_activation"]
 
 
 def get_activation(kind="tanh"):
@@ -370,3 +370,48 @@ class FFCResNetGenerator(nn.Module):
             return _engine.run_module(self, "generator", (input,))[0]
         _fallback("FFCResNetGenerator topology / mode")
         return self.model(input)
+
+
+class FFCNLayerDiscriminator(nn.Module):
+    """ffc.py:370-433 — training-only FFC discriminator (no shipped config uses it).  Kept so that the module
+    surface is complete; it is a composition of the drop-in FFC_BN_ACT blocks (LeakyReLU activations keep them
+    on the torch path) with the reference's attribute names (model0..modelN) and forward contract
+    (final scores, list of intermediate activations)."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=nn.BatchNorm2d, max_features=512,
+                 init_conv_kwargs={}, conv_kwargs={}):
+        super().__init__()
+        self.n_layers = n_layers
+
+        def act(inplace=True):
+            return nn.LeakyReLU(negative_slope=0.2, inplace=inplace)
+
+        kw, padw = 3, 1
+        stages = [[FFC_BN_ACT(input_nc, ndf, kernel_size=kw, padding=padw, norm_layer=norm_layer,
+                              activation_layer=act, **init_conv_kwargs)]]
+        nf = ndf
+        for _ in range(1, n_layers):
+            nf_prev, nf = nf, min(nf * 2, max_features)
+            stages.append([FFC_BN_ACT(nf_prev, nf, kernel_size=kw, stride=2, padding=padw, norm_layer=norm_layer,
+                                      activation_layer=act, **conv_kwargs)])
+        nf_prev, nf = nf, min(nf * 2, 512)
+        stages.append([FFC_BN_ACT(nf_prev, nf, kernel_size=kw, stride=1, padding=padw, norm_layer=norm_layer,
+                                  activation_layer=act, **conv_kwargs), ConcatTupleLayer()])
+        stages.append([nn.Conv2d(nf, 1, kernel_size=kw, stride=1, padding=padw)])
+        for i, st in enumerate(stages):
+            setattr(self, f"model{i}", nn.Sequential(*st))
+
+    def get_all_activations(self, x):
+        res = [x]
+        for i in range(self.n_layers + 2):
+            res.append(getattr(self, f"model{i}")(res[-1]))
+        return res[1:]
+
+    def forward(self, x):
+        acts = self.get_all_activations(x)
+        feats = []
+        for out in acts[:-1]:
+            if isinstance(out, tuple):
+                out = torch.cat(out, dim=1) if torch.is_tensor(out[1]) else out[0]
+            feats.append(out)
+        return acts[-1], feats

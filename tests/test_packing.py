@@ -90,3 +90,22 @@ def test_module_torch_composition_matches_reference_on_cpu():
     with torch.no_grad():
         a, b = ref((xl, xg)); c, d = ours((xl, xg))
     assert torch.allclose(a, c, atol=1e-6) and torch.allclose(b, d, atol=1e-6)
+
+
+def test_discriminator_surface_matches_reference():
+    """FFCNLayerDiscriminator (ffc.py:370-433, training only) keeps the reference's state_dict and outputs."""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    ffc = ref_import.load_reference_ffc()
+    kw = dict(input_nc=3, ndf=16, n_layers=3, init_conv_kwargs=dict(ratio_gin=0, ratio_gout=0.5, enable_lfu=False),
+              conv_kwargs=dict(ratio_gin=0.5, ratio_gout=0.5, enable_lfu=False))
+    ref = seeded_parameters_(ffc.FFCNLayerDiscriminator(**kw).eval(), 9)
+    ours = M.FFCNLayerDiscriminator(**kw).eval()
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    x = torch.randn(1, 3, 32, 32, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        a, fa = ref(x)
+        b, fb = ours(x)
+    assert torch.allclose(a, b, atol=1e-6) and len(fa) == len(fb)
+    assert all(torch.allclose(p, q, atol=1e-6) for p, q in zip(fa, fb))
