@@ -523,6 +523,10 @@ int encode(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const
 }
 
 int pick_bn(int n) {
+  if (const char* e = getenv("FFCB_TC_BN")) {          // tuning knob: force the N tile (multiple of 32, <= 128)
+    const int v = atoi(e);
+    if (v >= 32 && v <= 128 && v % 32 == 0) return v < n ? v : (n + 31) / 32 * 32;
+  }
   if (n <= 128) return (n + 31) / 32 * 32;
   if (n == 192) return 96;
   return 128;

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(1024) fft_cols_fwd_kernel(const float2* __rest
 
 // Column pass, inverse: spec (B,H,Wf,2C) -> ws[b][y][k][c] complex (unscaled inverse along H).
 template <int N>
-__global__ void __launch_bounds__(1024) fft_cols_inv_kernel(View spec, float2* __restrict__ ws, int n, int C) {
+__global__ void __launch_bounds__(N > 0 && N <= 64 ? 256 : 1024, N > 0 && N <= 64 ? 6 : 1) fft_cols_inv_kernel(View spec, float2* __restrict__ ws, int n, int C) {
   extern __shared__ float2 smem_f2[];
   const int H = (N > 0) ? N : n;
   const int lane = threadIdx.x, worker = threadIdx.y, nworkers = blockDim.y, group = threadIdx.z;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(1024) fft_cols_inv_kernel(View spec, float2* _
 // Row pass, inverse (C2R, two rows at a time): ws[b][y][k][c] -> out (B,H,W,C) real,
 // out = residual + scale * c2r(ws).  Im of bins 0 and (even W) W/2 is ignored.
 template <int N>
-__global__ void __launch_bounds__(1024) irfft_rows_kernel(const float2* __restrict__ ws, View res, View out, int n,
+__global__ void __launch_bounds__(N > 0 && N <= 64 ? 256 : 1024, N > 0 && N <= 64 ? 6 : 1) irfft_rows_kernel(const float2* __restrict__ ws, View res, View out, int n,
                                                           float scale) {
   extern __shared__ float2 smem_f2[];
   const int W = (N > 0) ? N : n;

@@ -46,6 +46,17 @@ def time_call(i, reps=20):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
+if os.environ.get("SWEEP_BN"):
+    print("N-tile sweep (FFCB_TC_BN), us per launch")
+    for w in want[:4]:
+        row = []
+        for bn in ("32", "64", "96", "128"):
+            os.environ["FFCB_TC_BN"] = bn
+            row.append(time_call(idx[w]))
+        del os.environ["FFCB_TC_BN"]
+        row.append(time_call(idx[w]))
+        print(f"{w:45s} " + " ".join(f"{v:10.1f}" for v in row) + "   (32 64 96 128 default)")
+    sys.exit(0)
 print(f"{'op':45s} " + " ".join(f"{k:>10s}" for k in ["full", "noGlobal", "noEpi", "noMMA", "noA", "noMMA+Epi", "noA+noEpi"]))
 for w in want:
     row = []
