@@ -148,7 +148,7 @@ def _cpu_setup():
     return best
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """Reference arm: the reference's CPU path (oracle torch-CPU port; the reference tree itself cannot
     travel to the GPU box) on all host threads.  Rank 0 only."""
     if rank != 0:
@@ -172,10 +172,22 @@ def run_reference(args, rank, world):
                          "sample": f"{per_step} images/step x {args.steps} steps, torch-CPU port of ffc.py (oracle/ffc_torch_cpu.py)"},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), file=out)
+    out.flush()
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    init), so keep a private handle to the real stdout and point fd 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w")
+    return real
 
 
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -191,7 +203,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch
@@ -371,7 +383,8 @@ def main():
             "gpu_launches": ex.launches_per_run * args.steps,
             "launches_per_step": ex.launches_per_run,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-        }))
+        }), file=out)
+        out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
