@@ -322,13 +322,14 @@ def _big_lama(seed=0):
     return g.to(DEV), sd_cpu
 
 
-@pytest.mark.parametrize("size,batch,seed", [(256, 2, 0), (512, 1, 1), ((384, 640), 1, 2), (1024, 1, 3)])
+@pytest.mark.parametrize("size,batch,seed", [(256, 2, 0), (512, 1, 1), ((384, 640), 1, 2), (1024, 1, 3), (2048, 1, 4)])
 def test_big_lama_generator_vs_oracle(size, batch, seed, math_mode):
     """The shipped architecture (configs/training/big-lama.yaml:26-45), seeded weights, vs the torch-CPU
     oracle port (fp32) on identical (image, mask): north_star tolerance 1e-3 max-abs."""
     g, sd = _big_lama(seed)
     # (384, 640): 48 x 80 bottleneck planes -> direct-DFT kernels and partially filled / clipped TMA tiles;
-    # 1024: 128 x 128 planes, 128-pixel-wide tiles, stride-2 boxes at the 256-element TMA limit
+    # 1024: 128 x 128 planes, 128-pixel-wide tiles, stride-2 boxes at the 256-element TMA limit;
+    # 2048 (BASELINE config 5 resolution, plain inference): 256 x 256 planes -> 1024-thread FFT CTAs, 128 KB smem
     h, w = (size, size) if isinstance(size, int) else size
     if math_mode == "fp32" and h * w > 512 * 512:
         pytest.skip("large sizes are covered in the tensor-core mode only (CUDA-core arm is ~7x slower)")
