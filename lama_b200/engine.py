@@ -27,6 +27,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import packing as P
 
+PROGRAM_CACHE_SIZE = 3          # executors (programs + their buffers) kept per module, LRU
 MATH_ENV = "LAMA_B200_MATH"     # "bf16x3" (default: tcgen05 arm) | "fp32" (CUDA-core arm)
 
 
@@ -786,12 +787,16 @@ def get_executor(module, kind: str, tensors, math: Optional[int] = None) -> Cuda
     sig = _weights_signature(module)
     hit = cache.get(key)
     if hit is not None and hit[0] == sig:
+        cache[key] = cache.pop(key)          # LRU: most recently used last
         return hit[1]
     with torch.no_grad():
         prog = build_module_program(module, kind, shapes, math)
     ex = CudaExecutor(prog, dev)
-    if len(cache) > 8:
-        cache.clear()
+    cache.pop(key, None)                      # stale weights
+    # every executor owns its activation buffers (~0.3 GB per 512x512 image for big-lama): keep only the few most
+    # recently used shapes per module so that a stream of differently sized images cannot exhaust HBM
+    while len(cache) >= PROGRAM_CACHE_SIZE:
+        cache.pop(next(iter(cache)))
     cache[key] = (sig, ex)
     return ex
 
