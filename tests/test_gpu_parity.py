@@ -410,3 +410,31 @@ def test_serving_pipeline_matches_module_call(math_mode):
     got.append(pipe.result(tickets[-1]).clone())
     for w, y in zip(want, got):
         assert torch.equal(w, y)
+
+
+def test_baseline_config0_single_fourier_unit(math_mode):
+    """BASELINE.json configs[0]: single FourierUnit(64, 64) forward on 1x64x256x256 fp32, seeded weights,
+    vs the float64 numpy oracle (256x256 planes: 1024-thread two-pass FFT kernels, 128-channel spectral GEMM)."""
+    m = seeded_parameters_(M.FourierUnit(64, 64).eval(), 11, gain=1.0)
+    sd = {k: v.numpy().astype(np.float64) for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
+    x = torch.randn(1, 64, 256, 256, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        y = m.to(DEV)(x.to(DEV)).cpu().numpy()
+    want = onp.fourier_unit(x.numpy().astype(np.float64), sd)
+    assert _rel_err(y, want) < TOL[math_mode]
+
+
+def test_baseline_config1_resnet_block_bs8(math_mode):
+    """BASELINE.json configs[1]: FFCResnetBlock(512, ratio 0.75/0.75) forward, bs8 at the 512x512 image resolution
+    (x_l 8x128x64x64, x_g 8x384x64x64), vs the torch-CPU oracle port."""
+    blk = seeded_parameters_(M.FFCResnetBlock(512, padding_type="reflect", norm_layer=torch.nn.BatchNorm2d,
+                                              activation_layer=torch.nn.ReLU, ratio_gin=0.75, ratio_gout=0.75,
+                                              enable_lfu=False).eval(), 12)
+    sd = {k: v.clone() for k, v in blk.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    xl, xg = torch.randn(8, 128, 64, 64, generator=g), torch.randn(8, 384, 64, 64, generator=g)
+    with torch.no_grad():
+        yl, yg = blk.to(DEV)((xl.to(DEV), xg.to(DEV)))
+        rl, rg = otc.ffc_resnet_block(xl, xg, sd, "")
+    assert _rel_err(yl.cpu().numpy(), rl.numpy()) < TOL[math_mode]
+    assert _rel_err(yg.cpu().numpy(), rg.numpy()) < TOL[math_mode]
