@@ -109,3 +109,60 @@ def test_discriminator_surface_matches_reference():
         b, fb = ours(x)
     assert torch.allclose(a, b, atol=1e-6) and len(fa) == len(fb)
     assert all(torch.allclose(p, q, atol=1e-6) for p, q in zip(fa, fb))
+
+
+# ------------------------------------------------------------------ property tests of the ffcb_conv contract
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None)
+@given(k=st.sampled_from([1, 3]), stride=st.sampled_from([1, 2]), cin=st.sampled_from([4, 8, 12]),
+       cout=st.sampled_from([4, 8]), h=st.integers(4, 11), w=st.integers(4, 11), seed=st.integers(0, 10 ** 6),
+       reflect=st.booleans(), act=st.sampled_from([L.ACT_NONE, L.ACT_RELU, L.ACT_SIGMOID]))
+def test_packed_conv_equals_torch_conv(k, stride, cin, cout, h, w, seed, reflect, act):
+    """pack_conv + apply_packed_reference (the executable spec of ffcb_conv) == nn.Conv2d semantics for every
+    kernel size / stride / border mode / ragged size the path uses."""
+    g = torch.Generator().manual_seed(seed)
+    pad = k // 2
+    x = torch.randn(2, cin, h, w, generator=g, dtype=torch.float64)
+    wt = torch.randn(cout, cin, k, k, generator=g, dtype=torch.float64)
+    scale = torch.rand(cout, generator=g, dtype=torch.float64) + 0.5
+    shift = torch.randn(cout, generator=g, dtype=torch.float64)
+    xp = F.pad(x, (pad,) * 4, mode="reflect") if (reflect and pad) else F.pad(x, (pad,) * 4)
+    want = F.conv2d(xp, wt, stride=stride) * scale[None, :, None, None] + shift[None, :, None, None]
+    want = {L.ACT_NONE: want, L.ACT_RELU: want.clamp_min(0), L.ACT_SIGMOID: torch.sigmoid(want)}[act]
+    pk = P.pack_conv([(wt, 0, 0, pad)], scale, shift, stride=stride,
+                     border=L.BORDER_REFLECT if reflect else L.BORDER_ZERO, act=act)
+    got = P.apply_packed_reference(pk, [x.permute(0, 2, 3, 1), None], tuple(want.shape[2:]))
+    np.testing.assert_allclose(got.permute(0, 3, 1, 2).numpy(), want.numpy(), atol=2e-6)
+
+
+def test_windowed_stem_packing_equals_reflect_conv7():
+    """pack_stem_windowed over the packed NHWC8 image (ffcb_stem_pack layout) == ReflectionPad2d(3)+Conv2d(k7)+BN+ReLU."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 4, 9, 13, generator=g, dtype=torch.float64)
+    conv = torch.nn.Conv2d(4, 8, 7, bias=False).double()
+    bn = seeded_parameters_(torch.nn.BatchNorm2d(8).double(), 4).eval()
+    want = torch.relu(bn(conv(F.pad(x, (3, 3, 3, 3), mode="reflect"))))
+    sc, sh = P.bn_scale_shift(bn)
+    pk = P.pack_stem_windowed(conv.weight, sc, sh)
+    packed = F.pad(F.pad(x, (3, 3, 3, 3), mode="reflect"), (0, 2, 0, 0, 0, 4)).permute(0, 2, 3, 1)   # [B,H+6,W+8,8]
+    wout = x.shape[3]
+    window = torch.cat([packed[:, :, j:j + wout] for j in range(8)], dim=-1)                        # [B,H+6,W,64]
+    got = P.apply_packed_reference(pk, [window, None], (x.shape[2], wout))
+    np.testing.assert_allclose(got.permute(0, 3, 1, 2).detach().numpy(), want.detach().numpy(), atol=2e-6)
+
+
+def test_head_rows_plus_gather_equals_reflect_conv7():
+    """pack_head_rows (kernel-row contraction) + the gather of ffcb_head_gather7 == ReflectionPad2d(3)+Conv2d(k7,bias)."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 8, 10, 12, generator=g, dtype=torch.float64)
+    conv = torch.nn.Conv2d(8, 3, 7, bias=True).double()
+    want = conv(F.pad(x, (3, 3, 3, 3), mode="reflect"))
+    pk = P.pack_head_rows(conv.weight)
+    q = P.apply_packed_reference(pk, [x.permute(0, 2, 3, 1), None], (10, 12))              # [B,H,W,24]
+    w = 12
+    xi = torch.arange(w)[:, None] + torch.arange(7)[None, :] - 3
+    xi = xi.abs(); xi = torch.where(xi >= w, 2 * w - 2 - xi, xi)
+    got = torch.stack([sum(q[:, :, xi[:, kx], n * 7 + kx] for kx in range(7)) + conv.bias[n] for n in range(3)], dim=1)
+    np.testing.assert_allclose(got.detach().numpy(), want.detach().numpy(), atol=2e-6)
