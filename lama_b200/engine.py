@@ -774,8 +774,19 @@ class GraphedProgram:
 
 
 # ---------------------------------------------------------------------------- module entry point
+_REWALK_EVERY = 32
+
+
 def _weights_signature(module) -> Tuple:
-    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+    """(data_ptr, version) of every parameter / buffer: changes on load_state_dict, .to(), in-place edits.
+    Walking the module tree costs ~1.5 ms for big-lama (989 tensors) — as much as a bs1 forward — so the flat
+    tensor list is cached on the module and re-walked only every few calls (catches replaced Parameter objects)."""
+    st = module.__dict__.get("_ffcb_tensors")
+    if st is None or st[1] >= _REWALK_EVERY:
+        st = [list(module.parameters()) + list(module.buffers()), 0]
+        module.__dict__["_ffcb_tensors"] = st
+    st[1] += 1
+    return tuple((t.data_ptr(), t._version) for t in st[0])
 
 
 def get_executor(module, kind: str, tensors, math: Optional[int] = None) -> CudaExecutor:

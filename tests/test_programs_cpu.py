@@ -162,3 +162,21 @@ def test_tc_incompatible_program_downgrades_to_fp32():
     with torch.no_grad():
         prog = E.build_module_program(m, "ffc_bn_act", ((1, 4, 22, 22), None), L.MATH_BF16X3)
     assert prog.math == L.MATH_FP32
+
+
+def test_weights_signature_tracks_changes_cheaply():
+    """Programs are rebuilt when weights change (load_state_dict / in-place edits / replaced parameters); the
+    per-call check uses a cached flat tensor list (the module walk alone costs as much as a bs1 forward)."""
+    m = M.FFC_BN_ACT(16, 16, 3, 0.5, 0.5, padding=1, enable_lfu=False).eval()
+    s0 = E._weights_signature(m)
+    assert E._weights_signature(m) == s0
+    with torch.no_grad():
+        m.bn_l.running_mean.add_(1.0)                       # in-place edit bumps the version counter
+    s1 = E._weights_signature(m)
+    assert s1 != s0
+    m.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})
+    s2 = E._weights_signature(m)
+    assert s2 != s1
+    m.ffc.convl2l.weight = torch.nn.Parameter(m.ffc.convl2l.weight.detach().clone())   # replaced object
+    sigs = [E._weights_signature(m) for _ in range(E._REWALK_EVERY + 1)]
+    assert sigs[-1] != s2                                   # noticed at the latest after the periodic re-walk
