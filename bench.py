@@ -197,6 +197,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--io", default=os.environ.get("LAMA_B200_BENCH_IO", "f32"), choices=["f32", "both"],
+                    help="both: also time the uint8 predict path (lama_b200.predict, SURVEY.md row f1) end to end")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -365,6 +367,40 @@ def main():
                "sample": f"{n_img} images of 512x512 one at a time (bin/predict.py:74 batch size), torch-CPU port of "
                          f"the reference ops (oracle/ffc_torch_cpu.py), {cores} threads (calibrated)"}
 
+    # ---- the same step through the uint8 predict path (row f1): decoded bytes in, inpainted bytes out; /255, mask
+    # multiply / concat, blend and x255 run inside the first / last kernels, PCIe carries 1 byte per sample.
+    # Measured last and fenced: it is an extra reading, a failure here must not take the headline numbers down.
+    u8_io = None
+    if args.io == "both" and math == L.MATH_BF16X3:
+        try:
+            img_h = (x_host[:, :3].permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().pin_memory()
+            msk_h = (x_host[:, 3] * 255).to(torch.uint8).contiguous().pin_memory()
+            pipe8 = GeneratorPipeline(gen, B, S, S, device=dev, depth=2, math=math, u8=True)
+            for _ in range(3):
+                pipe8.result(pipe8.submit(img_h, msk_h))
+            pipe8.drain()
+            barrier()
+            t0 = _time.perf_counter()
+            tickets = []
+            for _ in range(args.steps):
+                tickets.append(pipe8.submit(img_h, msk_h))
+                if len(tickets) > 1:
+                    pipe8.result(tickets[-2])
+            y8 = pipe8.result(tickets[-1])
+            pipe8.drain()
+            barrier()
+            ms8 = (_time.perf_counter() - t0) * 1e3
+            if world > 1:
+                t = torch.tensor([ms8], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms8 = float(t.item())
+            u8_io = {"value": world * B * args.steps / (ms8 / 1e3), "unit": "images/s",
+                     "ms_per_step": ms8 / args.steps, "h2d_bytes_per_step": img_h.numel() + msk_h.numel(),
+                     "d2h_bytes_per_step": y8.numel(), "launches_per_step": pipe8.launches_per_batch,
+                     "api": "lama_b200.serving.GeneratorPipeline(u8=True) — the engine of lama_b200.predict"}
+        except Exception as ex_u8:  # noqa: BLE001
+            u8_io = {"error": f"{type(ex_u8).__name__}: {ex_u8}"[:300]}
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -379,7 +415,8 @@ def main():
                     "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": ms_e2e / args.steps,
                     "api": "lama_b200.serving.GeneratorPipeline (depth 2: copies overlap the neighbouring steps)",
                     "timer": "host wall clock around submit/result of all steps (copies are on side streams)",
-                    "module_call_serial_copies": world * B * args.steps / (ms_serial / 1e3)},
+                    "module_call_serial_copies": world * B * args.steps / (ms_serial / 1e3),
+                    "u8_io": u8_io},
             "gpu_launches": ex.launches_per_run * args.steps,
             "launches_per_step": ex.launches_per_run,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,

@@ -183,6 +183,30 @@ int ffcb_irfft2(const ffcb_tensor* spec, const ffcb_tensor* residual /* nullable
  */
 int ffcb_head_gather7(const ffcb_tensor* q, const float* bias, int N, int act, float* y_nchw, ffcb_stream_t stream);
 
+/*
+ * uint8 image I/O of the predict path — the elementwise work the reference does around the
+ * generator, fused into the two kernels that touch the full-resolution image anyway.
+ *
+ * ffcb_stem_pack_u8 replaces, for a batch of decoded RGB images [B][H0][W0][3] and masks [B][H0][W0]:
+ *     load_image: u8 -> float32 / 255                         saicinpainting/evaluation/data.py:11-19
+ *     pad_img_to_modulo(mode='symmetric') to (H, W)           evaluation/data.py:32-36 (bottom / right only)
+ *     mask = (mask > 0) * 1                                   bin/predict.py:83
+ *     masked_img = img * (1 - mask); cat([masked_img, mask])  training/trainers/default.py:59, 68
+ *     ReflectionPad2d(3) of the stem                          ffc.py:315
+ * and writes the packed stem image of ffcb_stem_pack (view (B, H+6, W+8, 8); H, W = padded size, H-H0 <= H0).
+ *
+ * ffcb_head_gather7_blend_u8 is ffcb_head_gather7 (N = 3) followed by
+ *     inpainted = mask * predicted + (1 - mask) * image       training/trainers/default.py:71
+ *     crop to unpad_to_size (H0, W0)                          bin/predict.py:86-91
+ *     np.clip(res * 255, 0, 255).astype('uint8')              bin/predict.py:93   (truncation)
+ * writing RGB bytes [B][H0][W0][3].  Pixels outside the hole reproduce the reference's u8 -> /255 -> *255 -> u8
+ * round trip bit for bit (IEEE float32 division and product).
+ */
+int ffcb_stem_pack_u8(const uint8_t* image_hwc, const uint8_t* mask_hw, int B, int H0, int W0,
+                      const ffcb_tensor* packed, ffcb_stream_t stream);
+int ffcb_head_gather7_blend_u8(const ffcb_tensor* q, const float* bias, int act, const uint8_t* image_hwc,
+                               const uint8_t* mask_hw, int H0, int W0, uint8_t* out_hwc, ffcb_stream_t stream);
+
 /* Layout/format conversion at the module boundary (the reference's tensors are NCHW float):
  * ffc.py has no counterpart — these replace nothing, they adapt torch's layout to the path's. */
 int ffcb_nchw_to_nhwc(const float* x_nchw, int B, int C, int H, int W, const ffcb_tensor* out, ffcb_stream_t stream);

@@ -52,6 +52,9 @@ SIGNATURES = {
                                   _PT, C.c_void_p]),
     "ffcb_stem_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _PT, C.c_void_p]),
     "ffcb_head_gather7": (C.c_int, [_PT, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ffcb_stem_pack_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, _PT, C.c_void_p]),
+    "ffcb_head_gather7_blend_u8": (C.c_int, [_PT, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p]),
     "ffcb_head_conv7": (C.c_int, [_PT, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ffcb_fft2_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ffcb_rfft2": (C.c_int, [_PT, _PT, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -59,6 +59,9 @@ int nhwc_to_nchw(const ffcb_tensor*, float*, cudaStream_t);
 int fill_reflect_border(const ffcb_tensor*, cudaStream_t);
 int stem_pack(const float*, int, int, int, int, const ffcb_tensor*, cudaStream_t);
 int head_gather7(const ffcb_tensor*, const float*, int, int, float*, cudaStream_t);
+int stem_pack_u8(const uint8_t*, const uint8_t*, int, int, int, const ffcb_tensor*, cudaStream_t);
+int head_gather7_blend_u8(const ffcb_tensor*, const float*, int, const uint8_t*, const uint8_t*, int, int, uint8_t*,
+                          cudaStream_t);
 
 static int check_conv(const ffcb_conv_desc* d) {
   FFCB_REQUIRE(d != nullptr, "conv: null descriptor");
@@ -138,6 +141,16 @@ int ffcb_stem_conv7(const float* x, int B, int Cin, int H, int W, const float* w
 
 int ffcb_stem_pack(const float* x, int B, int Cin, int H, int W, const ffcb_tensor* packed, ffcb_stream_t stream) {
   return stem_pack(x, B, Cin, H, W, packed, (cudaStream_t)stream);
+}
+
+int ffcb_stem_pack_u8(const uint8_t* image_hwc, const uint8_t* mask_hw, int B, int H0, int W0,
+                      const ffcb_tensor* packed, ffcb_stream_t stream) {
+  return stem_pack_u8(image_hwc, mask_hw, B, H0, W0, packed, (cudaStream_t)stream);
+}
+
+int ffcb_head_gather7_blend_u8(const ffcb_tensor* q, const float* bias, int act, const uint8_t* image_hwc,
+                               const uint8_t* mask_hw, int H0, int W0, uint8_t* out_hwc, ffcb_stream_t stream) {
+  return head_gather7_blend_u8(q, bias, act, image_hwc, mask_hw, H0, W0, out_hwc, (cudaStream_t)stream);
 }
 
 int ffcb_head_gather7(const ffcb_tensor* q, const float* bias, int N, int act, float* y, ffcb_stream_t stream) {

@@ -125,6 +125,40 @@ __global__ void stem_pack_kernel(const float* __restrict__ x, int Cin, int H, in
   }
 }
 
+// uint8 front end of the predict path: decode + pad_img_to_modulo('symmetric') + mask
+// binarisation + mask multiply + channel concat + ReflectionPad2d(3), written straight into the packed stem image.
+//   reference: evaluation/data.py:11-19 (u8 / 255, float32), :32-36 (np.pad symmetric to a multiple of 8),
+//              bin/predict.py:83 (mask > 0), trainers/default.py:59 (img * (1 - mask)), :68 (cat mask)
+// image: [B][H0][W0][3] (decoded RGB), mask: [B][H0][W0]; the padded size (H, W) comes from the packed view.
+__device__ __forceinline__ int symmetric_idx(int i, int n0) { return i < n0 ? i : 2 * n0 - 1 - i; }
+
+__global__ void stem_pack_u8_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, int H0, int W0,
+                                    View out) {
+  const int Wp = out.W, Hp = out.H, H = Hp - 2 * HALO, W = Wp - 8;
+  const long long total = (long long)out.B * Hp * Wp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int xp = (int)(i % Wp);
+    const int yp = (int)((i / Wp) % Hp);
+    const int b = (int)(i / ((long long)Wp * Hp));
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (xp < W + 2 * HALO) {
+      const int ys = symmetric_idx(reflect_idx(yp - HALO, H), H0), xs = symmetric_idx(reflect_idx(xp - HALO, W), W0);
+      const long long p = ((long long)b * H0 + ys) * W0 + xs;
+      if (__ldg(mask + p) > 0) {
+        lo.w = 1.f;                                  // img * (1 - 1) = +0, mask channel = 1
+      } else {                                       // img * (1 - 0) = img exactly
+        lo.x = __fdiv_rn((float)__ldg(img + 3 * p + 0), 255.f);
+        lo.y = __fdiv_rn((float)__ldg(img + 3 * p + 1), 255.f);
+        lo.z = __fdiv_rn((float)__ldg(img + 3 * p + 2), 255.f);
+      }
+    }
+    const long long o = pix_off(out, b, yp, xp);
+    store4(out, o, lo);
+    store4(out, o + 4, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+
 // ---------------------------------------------------------------------------------------- head
 // Register tile: 4 vertically adjacent pixels x (N <= 4) outputs per thread.  For one (kx, channel quad)
 // the 10 patch rows a thread needs are loaded once (float4, conflict-free: pixel pitch 20 floats) and
@@ -295,6 +329,45 @@ __global__ void __launch_bounds__(GT) head_gather7_kernel(View q, const float* _
   }
 }
 
+// uint8 back end of the predict path (row f1): head gather + output activation + blend with the input image +
+// crop to the unpadded size + x255 / clip / truncate, RGB bytes out.
+//   reference: trainers/default.py:71 (mask * predicted + (1 - mask) * image — an exact select for mask in {0,1}),
+//              bin/predict.py:86-91 (unpad_to_size crop), :93 (np.clip(res * 255, 0, 255).astype('uint8'))
+// q is over the padded image (reflection about the padded width); out: [B][H0][W0][3].
+__global__ void __launch_bounds__(GT) head_gather7_blend_u8_kernel(View q, const float* __restrict__ bias, int act,
+                                                                   const uint8_t* __restrict__ img,
+                                                                   const uint8_t* __restrict__ mask, int H0, int W0,
+                                                                   uint8_t* __restrict__ out) {
+  extern __shared__ float tile[];
+  constexpr int nq = 21, pitch = nq + 1;
+  const int tiles_x = (W0 + GT - 1) / GT;
+  const int x0 = (blockIdx.x % tiles_x) * GT, y = blockIdx.x / tiles_x, b = blockIdx.y;
+  for (int i = threadIdx.x; i < (GT + 6) * nq; i += GT) {
+    const int px = i / nq, j = i % nq;
+    const int xx = min(max(reflect_idx(x0 + px - 3, q.W), 0), q.W - 1);
+    tile[px * pitch + j] = load1(q, pix_off(q, b, y, xx) + j);
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x;
+  if (x >= W0) return;
+  const long long p = ((long long)b * H0 + y) * W0 + x;
+  const bool hole = __ldg(mask + p) > 0;
+#pragma unroll
+  for (int n = 0; n < 3; ++n) {
+    float v;
+    if (hole) {
+      float acc = bias ? __ldg(bias + n) : 0.f;
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) acc += tile[(threadIdx.x + kx) * pitch + n * 7 + kx];
+      v = apply_act(acc, act);
+    } else {
+      v = __fdiv_rn((float)__ldg(img + 3 * p + n), 255.f);
+    }
+    v = fminf(fmaxf(__fmul_rn(v, 255.f), 0.f), 255.f);
+    out[3 * p + n] = (uint8_t)(int)v;            // float -> int truncates toward zero like astype('uint8')
+  }
+}
+
 }  // namespace
 
 int stem_conv7(const float* x, int B, int Cin, int H, int W, const float* w, const float* shift, int N,
@@ -330,6 +403,41 @@ int stem_pack(const float* x, int B, int Cin, int H, int W, const ffcb_tensor* p
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   stem_pack_kernel<<<blocks, 256, 0, stream>>>(x, Cin, H, W, make_view(*packed));
   FFCB_LAUNCH_CHECK("stem_pack_kernel");
+  return FFCB_OK;
+}
+
+int stem_pack_u8(const uint8_t* img, const uint8_t* mask, int B, int H0, int W0, const ffcb_tensor* packed,
+                 cudaStream_t stream) {
+  int rc;
+  if ((rc = check_tensor(packed, "stem_pack_u8.packed"))) return rc;
+  FFCB_REQUIRE(img != nullptr && mask != nullptr, "stem_pack_u8: null input");
+  const int H = packed->H - 6, W = packed->W - 8;
+  FFCB_REQUIRE(packed->B == B && packed->C == 8 && !packed->window && H >= 4 && W >= 4,
+               "stem_pack_u8: packed view must be (B, H+6, W+8, 8) with H, W >= 4");
+  FFCB_REQUIRE(H0 >= 1 && W0 >= 1 && H0 <= H && W0 <= W && H - H0 <= H0 && W - W0 <= W0,
+               "stem_pack_u8: %dx%d cannot be symmetric-padded to %dx%d", H0, W0, H, W);
+  const long long total = (long long)B * (H + 6) * (W + 8);
+  if (total == 0) return FFCB_OK;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  stem_pack_u8_kernel<<<blocks, 256, 0, stream>>>(img, mask, H0, W0, make_view(*packed));
+  FFCB_LAUNCH_CHECK("stem_pack_u8_kernel");
+  return FFCB_OK;
+}
+
+int head_gather7_blend_u8(const ffcb_tensor* q, const float* bias, int act, const uint8_t* img, const uint8_t* mask,
+                          int H0, int W0, uint8_t* out, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_tensor(q, "head_gather7_blend_u8.q"))) return rc;
+  FFCB_REQUIRE(img && mask && out, "head_gather7_blend_u8: null pointer");
+  FFCB_REQUIRE(q->C >= 21, "head_gather7_blend_u8: q.C=%d < 21 (three outputs x seven taps)", q->C);
+  FFCB_REQUIRE(q->W >= 4 && q->B <= 65535, "head_gather7_blend_u8: W >= 4 and B <= 65535 required");
+  FFCB_REQUIRE(H0 >= 1 && W0 >= 1 && H0 <= q->H && W0 <= q->W, "head_gather7_blend_u8: crop %dx%d outside %dx%d", H0,
+               W0, q->H, q->W);
+  if (q->B == 0) return FFCB_OK;
+  dim3 grid(((W0 + GT - 1) / GT) * H0, q->B);
+  const size_t smem = sizeof(float) * (GT + 6) * 22;
+  head_gather7_blend_u8_kernel<<<grid, GT, smem, stream>>>(make_view(*q), bias, act, img, mask, H0, W0, out);
+  FFCB_LAUNCH_CHECK("head_gather7_blend_u8_kernel");
   return FFCB_OK;
 }
 

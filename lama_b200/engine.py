@@ -130,6 +130,30 @@ class HeadGatherOp:
 
 
 @dataclass
+class StemPackU8Op:
+    """Decoded RGB bytes + mask bytes -> packed stem image (ffcb_stem_pack_u8): /255, symmetric pad to the
+    modulo size, mask > 0, img * (1 - mask), cat(mask), ReflectionPad2d(3)."""
+    img: str          # external uint8 (B, H0, W0, 3)
+    mask: str         # external uint8 (B, H0, W0)
+    h0: int
+    w0: int
+    out: TV           # Buf (B, H+6, W+8, 8)
+
+
+@dataclass
+class HeadGatherU8Op:
+    """ffcb_head_gather7_blend_u8: head gather + activation + blend with the input + crop + x255/clip/truncate."""
+    q: TV
+    bias: torch.Tensor
+    act: int
+    img: str
+    mask: str
+    h0: int
+    w0: int
+    dst: str          # external uint8 (B, H0, W0, 3)
+
+
+@dataclass
 class ConvOp:
     packed: P.PackedConv
     ins: List[Optional[TV]]
@@ -166,6 +190,7 @@ class Program:
     ops: list = field(default_factory=list)
     inputs: Dict[str, Tuple[int, ...]] = field(default_factory=dict)    # name -> NCHW shape
     outputs: Dict[str, Tuple[int, ...]] = field(default_factory=dict)
+    dtypes: Dict[str, torch.dtype] = field(default_factory=dict)       # inputs / outputs that are not float32
 
     def buf(self, name, B, H, W, C, gemm=False, halo=False, halo_px=1) -> Buf:
         """``gemm``: the buffer is an operand of a contraction; ``halo``: that contraction has spatial taps.
@@ -493,30 +518,53 @@ def build_module_program(module, kind: str, shapes: Sequence[Optional[Tuple[int,
             prog.ops.append(ToNCHW(TV(Y, ocl, ocg), "y1")); prog.outputs["y1"] = (b, ocg, Y.H, Y.W)
     elif kind == "generator":
         build_generator_program(prog, module, shapes[0])
+    elif kind.startswith("generator_u8"):            # "generator_u8:<pad modulo>", shapes = (img, mask)
+        mod = int(kind.split(":")[1]) if ":" in kind else 8
+        b, h0, w0, _ = shapes[0]
+        h, w = -(-h0 // mod) * mod, -(-w0 // mod) * mod
+        build_generator_program(prog, module, (b, 4, h, w), u8_size=(h0, w0))
     else:
         raise ValueError(kind)
     if math == L.MATH_BF16X3 and not tc_compatible(prog):
+        if kind.startswith("generator_u8"):
+            raise ValueError("the uint8 predict path needs channel counts in multiples of 8 (tensor-core arm)")
         return build_module_program(module, kind, shapes, L.MATH_FP32)
     insert_border_ops(prog)
     return prog
 
 
-def build_generator_program(prog: Program, gen, shape):
+def build_generator_program(prog: Program, gen, shape, u8_size: Optional[Tuple[int, int]] = None):
     """FFCResNetGenerator (ffc.py:306-367) as one program: stem -> stride-2 convs -> residual blocks
-    (in place on one 512-channel buffer) -> sub-pixel transposed convs -> head."""
+    (in place on one 512-channel buffer) -> sub-pixel transposed convs -> head.
+
+    ``u8_size=(H0, W0)``: the predict-path variant.  Inputs are the decoded bytes "img"
+    (B,H0,W0,3) and "mask" (B,H0,W0); ``shape`` is the modulo-padded generator input (B,4,H,W); the output "y0" is
+    the inpainted RGB bytes (B,H0,W0,3).  Pre/post-processing lives in the pack and gather kernels."""
     stem, downs, blocks, ups, head, out_act = _generator_layout(gen)
     b, cin, h, w = shape
     dev = head.weight.device
-    prog.inputs["x0"] = tuple(shape)
+    if u8_size is None:
+        prog.inputs["x0"] = tuple(shape)
+    else:
+        h0, w0 = u8_size
+        prog.inputs["img"], prog.inputs["mask"] = (b, h0, w0, 3), (b, h0, w0)
+        prog.dtypes.update(img=torch.uint8, mask=torch.uint8, y0=torch.uint8)
     conv = stem.ffc.convl2l
     n0 = conv.out_channels
     s0, b0 = P.bn_scale_shift(stem.bn_l)
     wst, shst = P.pack_stem(conv.weight, s0, b0, device=dev)
     X = prog.buf("stem", b, h, w, n0, gemm=True, halo=True)
-    if prog.math == L.MATH_BF16X3 and cin <= 8 and n0 % 8 == 0 and os.environ.get("LAMA_B200_STEM", "tc") == "tc":
+    tc_stem = (prog.math == L.MATH_BF16X3 and cin <= 8 and n0 % 8 == 0
+               and os.environ.get("LAMA_B200_STEM", "tc") == "tc")
+    if u8_size is not None and not (tc_stem and cin == 4):
+        raise ValueError("the uint8 predict path needs the tensor-core stem (bf16x3 arithmetic, 4 input channels)")
+    if tc_stem:
         # tensor-core stem: the 7x7 window of the packed image is 7 contiguous 128-byte K blocks per pixel
         Pk = prog.buf("stem.packed", b, h + 6, w + 8, 8, gemm=True)
-        prog.ops.append(StemPackOp("x0", cin, TV(Pk)))
+        if u8_size is None:
+            prog.ops.append(StemPackOp("x0", cin, TV(Pk)))
+        else:
+            prog.ops.append(StemPackU8Op("img", "mask", h0, w0, TV(Pk)))
         pk = P.pack_stem_windowed(conv.weight, s0, b0, device=dev)
         prog.ops.append(ConvOp(pk, [TV(Pk, window=8), None], TV(X), tag="stem 7x7 (windowed)+bn+relu"))
     else:
@@ -538,16 +586,21 @@ def build_generator_program(prog: Program, gen, shape):
         for a, bb, pk in P.pack_conv_transpose_phases(ct.weight, ct.bias, sc, sh, act=L.ACT_RELU, device=dev):
             prog.ops.append(ConvOp(pk, [TV(X), None], TV(Yb, phase=(a, bb)), tag=f"convT phase {a}{bb}+bn+relu"))
         X = Yb
+    if u8_size is not None and not (tc_head and ups and head.out_channels == 3):
+        raise ValueError("the uint8 predict path needs the tensor-core head with 3 output channels")
     if tc_head and ups:
         pkh = P.pack_head_rows(head.weight, device=dev)
         Q = prog.buf("head.q", b, h, w, pkh.n_out)
         prog.ops.append(ConvOp(pkh, [TV(X), None], TV(Q), tag="head 7x7 rows"))
         bias = head.bias.detach().float().contiguous() if head.bias is not None else torch.zeros(head.out_channels)
-        prog.ops.append(HeadGatherOp(TV(Q), bias.to(dev), head.out_channels, out_act, "y0"))
+        if u8_size is None:
+            prog.ops.append(HeadGatherOp(TV(Q), bias.to(dev), head.out_channels, out_act, "y0"))
+        else:
+            prog.ops.append(HeadGatherU8Op(TV(Q), bias.to(dev), out_act, "img", "mask", h0, w0, "y0"))
     else:
         wh, bh = P.pack_head(head.weight, head.bias, device=dev)
         prog.ops.append(HeadOp(TV(X), wh, bh, head.out_channels, out_act, "y0"))
-    prog.outputs["y0"] = (b, head.out_channels, h, w)
+    prog.outputs["y0"] = (b, head.out_channels, h, w) if u8_size is None else (b, h0, w0, 3)
 
 
 def tc_compatible(prog: Program) -> bool:
@@ -579,7 +632,7 @@ def insert_border_ops(prog: Program):
                     del dirty[id(tv.buf)]
         out.append(op)
         wrote = None
-        if isinstance(op, (ToNHWC, StemOp, StemPackOp, IrfftOp, ConvOp)):
+        if isinstance(op, (ToNHWC, StemOp, StemPackOp, StemPackU8Op, IrfftOp, ConvOp)):
             wrote = op.out
         elif isinstance(op, RfftOp):
             wrote = op.spec
@@ -608,7 +661,8 @@ class CudaExecutor:
         ws_bytes = prog.fft_workspace_bytes()
         self.ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=device)
         self.ws_bytes = ws_bytes
-        self.outputs = {k: torch.empty(v, dtype=torch.float32, device=device) for k, v in prog.outputs.items()}
+        self.outputs = {k: torch.empty(v, dtype=prog.dtypes.get(k, torch.float32), device=device)
+                        for k, v in prog.outputs.items()}
         self._launches = None
         self._keep = []          # ctypes objects / tensors that must outlive the calls
         self.calls = []          # (fn, args) with a trailing stream argument appended at run time
@@ -676,6 +730,20 @@ class CudaExecutor:
             t = self._ref(self.tensor(op.out))
             self.input_slots.setdefault(op.src, []).append((len(self.calls), 0))
             self.calls.append(("ffcb_stem_pack", lib.ffcb_stem_pack, [None, bb, c, h, w, C.byref(t)]))
+        elif isinstance(op, StemPackU8Op):
+            bb = self.prog.inputs[op.img][0]
+            t = self._ref(self.tensor(op.out))
+            self.input_slots.setdefault(op.img, []).append((len(self.calls), 0))
+            self.input_slots.setdefault(op.mask, []).append((len(self.calls), 1))
+            self.calls.append(("ffcb_stem_pack_u8", lib.ffcb_stem_pack_u8, [None, None, bb, op.h0, op.w0, C.byref(t)]))
+        elif isinstance(op, HeadGatherU8Op):
+            t = self._ref(self.tensor(op.q))
+            bd = self._dev(op.bias)
+            self.input_slots.setdefault(op.img, []).append((len(self.calls), 3))
+            self.input_slots.setdefault(op.mask, []).append((len(self.calls), 4))
+            self.calls.append(("ffcb_head_gather7_blend_u8", lib.ffcb_head_gather7_blend_u8,
+                               [C.byref(t), bd.data_ptr(), op.act, None, None, op.h0, op.w0,
+                                self.outputs[op.dst].data_ptr()]))
         elif isinstance(op, HeadOp):
             t = self._ref(self.tensor(op.inp))
             wd, bd = self._dev(op.w), self._dev(op.bias)
@@ -728,8 +796,9 @@ class CudaExecutor:
             stream = torch.cuda.current_stream(self.device).cuda_stream
         for name, slots in self.input_slots.items():
             t = inputs[name]
-            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == tuple(
-                self.prog.inputs[name]), f"input {name}: expected contiguous float32 {self.prog.inputs[name]}"
+            dt = self.prog.dtypes.get(name, torch.float32)
+            assert t.is_cuda and t.dtype == dt and t.is_contiguous() and tuple(t.shape) == tuple(
+                self.prog.inputs[name]), f"input {name}: expected contiguous {dt} {self.prog.inputs[name]}"
             for ci, ai in slots:
                 self.calls[ci][2][ai] = t.data_ptr()
         first = self._launches is None
@@ -755,7 +824,8 @@ class GraphedProgram:
 
     def __init__(self, ex: CudaExecutor, warmup: int = 2):
         self.ex = ex
-        self.static_in = {k: torch.empty(v, dtype=torch.float32, device=ex.device) for k, v in ex.prog.inputs.items()}
+        self.static_in = {k: torch.empty(v, dtype=ex.prog.dtypes.get(k, torch.float32), device=ex.device)
+                          for k, v in ex.prog.inputs.items()}
         side = torch.cuda.Stream(device=ex.device)
         side.wait_stream(torch.cuda.current_stream(ex.device))
         with torch.cuda.stream(side):
@@ -789,10 +859,12 @@ def _weights_signature(module) -> Tuple:
     return tuple((t.data_ptr(), t._version) for t in st[0])
 
 
-def get_executor(module, kind: str, tensors, math: Optional[int] = None) -> CudaExecutor:
+def get_executor(module, kind: str, tensors, math: Optional[int] = None,
+                 device: Optional[torch.device] = None) -> CudaExecutor:
+    """``tensors`` only contribute their shapes (meta tensors are fine when ``device`` is given)."""
     math = default_math() if math is None else math
     shapes = tuple(tuple(t.shape) if torch.is_tensor(t) else None for t in tensors)
-    dev = next(t for t in tensors if torch.is_tensor(t)).device
+    dev = device if device is not None else next(t for t in tensors if torch.is_tensor(t)).device
     key = (kind, shapes, str(dev), math)
     cache = module.__dict__.setdefault("_ffcb_programs", {})
     sig = _weights_signature(module)

@@ -120,5 +120,62 @@ def main():
     _save("generator_ngf8_b2_40x72", x=x.numpy(), y=g(x).numpy())
 
 
+@torch.no_grad()
+def make_predict():
+    """Predict path: PNG files -> reference InpaintingDataset -> reference generator -> bytes.
+
+    The dataset / padding / decode code is the reference's own (saicinpainting/evaluation/data.py, imported from
+    its file); DefaultInpaintingTrainingModule.forward and bin/predict.py need pytorch_lightning / hydra to import,
+    so the six lines of theirs on this path are restated below with their file:line."""
+    import importlib.util
+    import tempfile
+    from PIL import Image
+    spec = importlib.util.spec_from_file_location(
+        "_ref_eval_data", os.path.join(os.environ.get("LAMA_REFERENCE_ROOT", "/root/reference"),
+                                       "saicinpainting/evaluation/data.py"))
+    data = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(data)
+    ffc = load_reference_ffc()
+    torch.set_num_threads(1)
+    g = seeded_parameters_(ffc.FFCResNetGenerator(**small_lama_kwargs(ngf=8, n_blocks=2)).eval(), seed=50, gain=1.0)
+
+    rng = np.random.default_rng(7)
+    b, h0, w0 = 3, 45, 52
+    images = rng.integers(0, 256, size=(b, h0, w0, 3), dtype=np.uint8)
+    images[0, :, :, :] = (np.linspace(0, 255, w0)[None, :, None] + np.zeros((h0, 1, 3))).astype(np.uint8)  # ramp
+    masks = np.zeros((b, h0, w0), dtype=np.uint8)
+    masks[0, 10:30, 12:40] = 255
+    masks[1, 30:, 35:] = 255                 # touches the symmetric padding
+    masks[1, 5:9, 5:9] = 1                   # "mask > 0" binarisation (predict.py:83)
+    masks[2, ::7, ::5] = 128
+    with tempfile.TemporaryDirectory() as d:
+        for i in range(b):
+            Image.fromarray(images[i]).save(os.path.join(d, f"im{i}.png"))
+            Image.fromarray(masks[i]).save(os.path.join(d, f"im{i}_mask.png"))
+        ds = data.InpaintingDataset(d, img_suffix=".png", pad_out_to_modulo=8)       # default.yaml:8-11
+        items = [ds[i] for i in range(len(ds))]
+    batch = {"image": torch.from_numpy(np.stack([it["image"] for it in items])),
+             "mask": torch.from_numpy(np.stack([it["mask"] for it in items]))}
+    unpad = items[0]["unpad_to_size"]
+    batch["mask"] = (batch["mask"] > 0) * 1                                         # bin/predict.py:83
+    img, mask = batch["image"], batch["mask"]
+    masked_img = img * (1 - mask)                                                   # trainers/default.py:59
+    masked_img = torch.cat([masked_img, mask], dim=1)                               # trainers/default.py:68
+    predicted = g(masked_img)                                                       # trainers/default.py:70
+    inpainted = mask * predicted + (1 - mask) * img                                 # trainers/default.py:71
+    outs = []
+    for i in range(b):
+        cur = inpainted[i].permute(1, 2, 0).numpy()                                 # bin/predict.py:85
+        cur = cur[:unpad[0], :unpad[1]]                                             # bin/predict.py:88-91
+        outs.append(np.clip(cur * 255, 0, 255).astype("uint8"))                     # bin/predict.py:93
+    # weights: same as generator_ngf8_b2_64x64 (state_dict stored there only)
+    _save("predict_ngf8_3x45x52", images=images, masks=masks, x=masked_img.numpy(), predicted=predicted.numpy(),
+          out=np.stack(outs))
+
+
 if __name__ == "__main__":
-    main()
+    if "--predict-only" in sys.argv:
+        make_predict()
+    else:
+        main()
+        make_predict()

@@ -34,6 +34,30 @@ class SpecInterpreter:
         else:
             t[..., tv.c0:tv.c0 + tv.channels] = val
 
+    @staticmethod
+    def _gather(q, bias, n_out, act):
+        """ffcb_head_gather7: q [B,H,W,>=7N] -> act(bias + sum_kx q[.., reflect(x+kx-3), n*7+kx]) as NCHW."""
+        w = q.shape[2]
+        xi = torch.arange(w)[:, None] + torch.arange(7)[None, :] - 3           # [W,7]
+        xi = xi.abs(); xi = torch.where(xi >= w, 2 * w - 2 - xi, xi)
+        ys = []
+        for n in range(n_out):
+            g = q[:, :, :, n * 7:n * 7 + 7]                  # [B,H,W,7]
+            ys.append(sum(g[:, :, xi[:, kx], kx] for kx in range(7)) + float(bias[n]))
+        y = torch.stack(ys, dim=1)
+        return {L.ACT_NONE: y, L.ACT_RELU: y.clamp_min(0), L.ACT_SIGMOID: torch.sigmoid(y),
+                L.ACT_TANH: torch.tanh(y)}[act]
+
+    @staticmethod
+    def _u8_front(img, mask, h, w):
+        """ffcb_stem_pack_u8 up to the reflection ring: (B,H0,W0,3) u8 + (B,H0,W0) u8 -> (B,4,H,W) float32."""
+        h0, w0 = mask.shape[1:]
+        ys = torch.arange(h); ys = torch.where(ys < h0, ys, 2 * h0 - 1 - ys)
+        xs = torch.arange(w); xs = torch.where(xs < w0, xs, 2 * w0 - 1 - xs)
+        x = (img.float() / 255)[:, ys][:, :, xs].permute(0, 3, 1, 2)
+        m = (mask > 0).float()[:, ys][:, :, xs][:, None]
+        return torch.cat([x * (1 - m), m], dim=1)
+
     def run(self, inputs):
         out = {}
         for op in self.prog.ops:
@@ -45,6 +69,17 @@ class SpecInterpreter:
                 x = torch.nn.functional.pad(inputs[op.src].double(), (3, 3, 3, 3), mode="reflect")
                 x = torch.nn.functional.pad(x, (0, 2, 0, 0, 0, 8 - op.cin))          # W+6 -> W+8, Cin -> 8 (zeros)
                 self.write(op.out, x.permute(0, 2, 3, 1))
+            elif isinstance(op, E.StemPackU8Op):
+                x = self._u8_front(inputs[op.img], inputs[op.mask], op.out.buf.H - 6, op.out.buf.W - 8)
+                x = torch.nn.functional.pad(x.double(), (3, 3, 3, 3), mode="reflect")
+                x = torch.nn.functional.pad(x, (0, 2, 0, 0, 0, 4))
+                self.write(op.out, x.permute(0, 2, 3, 1))
+            elif isinstance(op, E.HeadGatherU8Op):
+                pred = self._gather(self.read(op.q), op.bias, 3, op.act).float()[:, :, :op.h0, :op.w0]
+                img = inputs[op.img].permute(0, 3, 1, 2).float() / 255
+                hole = (inputs[op.mask] > 0)[:, None]
+                res = torch.where(hole, pred, img)                      # mask*pred + (1-mask)*img, mask in {0,1}
+                out[op.dst] = (res * 255).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
             elif isinstance(op, E.StemOp):
                 x = torch.nn.functional.pad(inputs[op.src].double(), (3, 3, 3, 3), mode="reflect")
                 cin = op.cin
@@ -60,17 +95,7 @@ class SpecInterpreter:
                      L.ACT_TANH: torch.tanh(y)}[op.act]
                 out[op.dst] = y
             elif isinstance(op, E.HeadGatherOp):
-                q = self.read(op.q)                                   # [B,H,W,>=7N]
-                w = q.shape[2]
-                xi = torch.arange(w)[:, None] + torch.arange(7)[None, :] - 3           # [W,7]
-                xi = xi.abs(); xi = torch.where(xi >= w, 2 * w - 2 - xi, xi)
-                ys = []
-                for n in range(op.n_out):
-                    g = q[:, :, :, n * 7:n * 7 + 7]                  # [B,H,W,7]
-                    ys.append(sum(g[:, :, xi[:, kx], kx] for kx in range(7)) + float(op.bias[n]))
-                y = torch.stack(ys, dim=1)
-                out[op.dst] = {L.ACT_NONE: y, L.ACT_RELU: y.clamp_min(0), L.ACT_SIGMOID: torch.sigmoid(y),
-                               L.ACT_TANH: torch.tanh(y)}[op.act]
+                out[op.dst] = self._gather(self.read(op.q), op.bias, op.n_out, op.act)
             elif isinstance(op, E.ConvOp):
                 ins = [self.read(tv) if tv is not None else None for tv in op.ins]
                 assert all(not torch.isnan(t).any() for t in ins if t is not None), f"{op.tag}: reads unwritten data"

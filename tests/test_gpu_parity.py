@@ -438,3 +438,76 @@ def test_baseline_config1_resnet_block_bs8(math_mode):
         rl, rg = otc.ffc_resnet_block(xl, xg, sd, "")
     assert _rel_err(yl.cpu().numpy(), rl.numpy()) < TOL[math_mode]
     assert _rel_err(yg.cpu().numpy(), rg.numpy()) < TOL[math_mode]
+
+
+# ------------------------------------------------------------------- predict path, uint8 I/O
+def _u8_only(mode):
+    if mode != "bf16x3":
+        pytest.skip("the uint8 front / back end exists on the tensor-core arm only")
+
+
+def test_predict_u8_bytes_match_reference_fixture(math_mode):
+    """lama_b200.predict.BatchedInpainter (decode-to-bytes fused path) against the bytes the reference pipeline
+    produced (tests/golden/predict_ngf8_3x45x52.npz: InpaintingDataset + generator + blend + x255/uint8).
+    45x52 images: symmetric padding to 48x56, 6x7 non-power-of-two FFT planes, a full and a partial batch."""
+    _u8_only(math_mode)
+    from lama_b200.predict import BatchedInpainter
+    a, _ = load_golden("predict_ngf8_3x45x52")
+    _, sd = load_golden("generator_ngf8_b2_64x64")
+    g = _load(M.FFCResNetGenerator(**small_lama_kwargs(ngf=8, n_blocks=2)), sd)
+    inp = BatchedInpainter(g, max_batch=2)
+    outs = np.stack(inp.inpaint(list(zip(a["images"], a["masks"]))))
+    hole = a["masks"] > 0
+    assert outs.dtype == np.uint8 and outs.shape == a["out"].shape
+    assert np.array_equal(outs[~hole], a["out"][~hole])            # bit-exact where the input shows through
+    d = np.abs(outs[hole].astype(int) - a["out"][hole].astype(int))
+    # prediction error ~3e-5 -> 0.008 grey levels: a truncation boundary is crossed for <~1% of the bytes
+    assert d.max() <= 1 and (d != 0).mean() < 0.05, (int(d.max()), float((d != 0).mean()))
+
+
+@pytest.mark.parametrize("h0,w0,b", [(100, 75, 2), (64, 64, 3)])
+def test_predict_u8_equals_float_program_plus_reference_glue(math_mode, h0, w0, b):
+    """The fused byte path and the float program share every kernel in between, so the bytes must be IDENTICAL to
+    the reference's elementwise glue (oracle/predict_numpy.py) wrapped around the native float generator call."""
+    _u8_only(math_mode)
+    from lama_b200.predict import BatchedInpainter
+    from oracle import predict_numpy as opn
+    _, sd = load_golden("generator_ngf8_b2_64x64")
+    g = _load(M.FFCResNetGenerator(**small_lama_kwargs(ngf=8, n_blocks=2)), sd)
+    rng = np.random.default_rng(h0 * 1000 + w0)
+    images = rng.integers(0, 256, size=(b, h0, w0, 3), dtype=np.uint8)
+    masks = (rng.random((b, h0, w0)) < 0.3).astype(np.uint8) * rng.integers(1, 256, size=(b, h0, w0), dtype=np.uint8)
+    masks[:, h0 // 2:, w0 // 2:] = 255                              # a solid hole reaching the padded corner
+    x, img, mask = opn.generator_input(images, masks, pad_mod=8)
+    with torch.no_grad():
+        pred = g(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    want = opn.finish(pred, img, mask, h0, w0)
+    got = BatchedInpainter(g, max_batch=b)(images, masks)
+    assert np.array_equal(got, want)
+    # several batches in flight through the same lane (slot and staging-buffer reuse)
+    many = [(np.roll(images[i % b], i, axis=1), np.roll(masks[i % b], i, axis=1)) for i in range(4 * b)]
+    outs = BatchedInpainter(g, max_batch=b).inpaint(many)
+    for i in (0, b + 1, 4 * b - 1):
+        xi, ii, mi = opn.generator_input(many[i][0][None], many[i][1][None], pad_mod=8)
+        with torch.no_grad():
+            pi = g(torch.from_numpy(xi).to(DEV)).cpu().numpy()
+        assert np.array_equal(outs[i], opn.finish(pi, ii, mi, h0, w0)[0])
+
+
+def test_predict_u8_abi_rejects_bad_arguments(math_mode):
+    _fp32_only(math_mode)
+    lib = L.get_lib()
+    t = torch.zeros(2, 1, 22, 24, 8, dtype=torch.bfloat16, device=DEV)          # packed view for a 16x16 image
+    pk = L.Tensor(t.data_ptr(), 22 * 24 * 8, 24 * 8, 8, 22 * 24 * 8, 1, 22, 24, 8, L.BF16X2, 0, 0, 0)
+    img = torch.zeros(1, 7, 16, 3, dtype=torch.uint8, device=DEV)
+    msk = torch.zeros(1, 7, 16, dtype=torch.uint8, device=DEV)
+    import ctypes as C
+    # 7 rows cannot be symmetric-padded to 16 (needs H - H0 <= H0)
+    assert lib.ffcb_stem_pack_u8(img.data_ptr(), msk.data_ptr(), 1, 7, 16, C.byref(pk), None) == L.EINVAL
+    assert b"symmetric" in lib.ffcb_last_error()
+    assert lib.ffcb_stem_pack_u8(None, msk.data_ptr(), 1, 16, 16, C.byref(pk), None) == L.EINVAL
+    q = torch.zeros(1, 16, 16, 24, device=DEV)
+    qt = L.Tensor(q.data_ptr(), 16 * 16 * 24, 16 * 24, 24, 0, 1, 16, 16, 24, L.F32, 0, 0, 0)
+    out = torch.zeros(1, 16, 16, 3, dtype=torch.uint8, device=DEV)
+    assert lib.ffcb_head_gather7_blend_u8(C.byref(qt), None, L.ACT_SIGMOID, img.data_ptr(), msk.data_ptr(), 17, 16,
+                                          out.data_ptr(), None) == L.EINVAL

@@ -130,3 +130,31 @@ def test_inpaint_glue():
     assert np.max(np.abs(pred - a["y"])) < 2e-6
     m = a["mask"]
     np.testing.assert_allclose(inp, m * pred + (1 - m) * a["image"], atol=1e-12)
+
+
+def _u8_agreement(got, ref, masks):
+    """Outside the hole the bytes are an exact function of the input bytes; inside, a 1e-6 difference in the
+    prediction may flip a truncation, so allow one level there (and require that to be rare)."""
+    hole = masks > 0
+    assert np.array_equal(got[~hole], ref[~hole])
+    d = np.abs(got[hole].astype(np.int16) - ref[hole].astype(np.int16))
+    assert d.max(initial=0) <= 1 and (d != 0).mean() < 0.01, (int(d.max(initial=0)), float((d != 0).mean()))
+
+
+def test_predict_u8_glue_pinned_on_reference_dataset_and_generator():
+    """oracle/predict_numpy.py against the fixture made by the reference's InpaintingDataset
+    (PNG decode, /255, symmetric pad to modulo 8) + reference generator + the restated blend / x255 / uint8."""
+    from oracle import predict_numpy as opn
+    a, _ = load_golden("predict_ngf8_3x45x52")
+    _, sd = load_golden("generator_ngf8_b2_64x64")
+    kw = small_lama_kwargs(ngf=8, n_blocks=2)
+    x, img, mask = opn.generator_input(a["images"], a["masks"], pad_mod=8)
+    assert x.dtype == np.float32 and np.array_equal(x, a["x"])                    # bit-exact front end
+    assert np.array_equal(opn.finish(a["predicted"], img, mask, 45, 52), a["out"])  # bit-exact back end
+    gen = lambda t: otc.ffc_resnet_generator(torch.from_numpy(t), _t(sd), **kw).numpy()  # noqa: E731
+    _u8_agreement(opn.predict_u8(gen, a["images"], a["masks"]), a["out"], a["masks"])
+    # outside the hole the float32 round trip u8 -> /255 -> *255 -> astype(uint8) is the identity for all 256 values
+    keep = a["masks"] == 0
+    assert np.array_equal(a["out"][keep], a["images"][keep])
+    v = np.arange(256, dtype=np.uint8)
+    assert np.array_equal(np.clip((v.astype("float32") / 255) * 255, 0, 255).astype("uint8"), v)

@@ -180,3 +180,29 @@ def test_weights_signature_tracks_changes_cheaply():
     m.ffc.convl2l.weight = torch.nn.Parameter(m.ffc.convl2l.weight.detach().clone())   # replaced object
     sigs = [E._weights_signature(m) for _ in range(E._REWALK_EVERY + 1)]
     assert sigs[-1] != s2                                   # noticed at the latest after the periodic re-walk
+
+
+def test_generator_u8_program_matches_reference_predict_bytes():
+    """the predict-path program (uint8 image + mask in, inpainted uint8 out; decode, symmetric
+    modulo padding, mask multiply / concat and blend / crop / x255 fused into the pack and gather kernels)."""
+    a, _ = load_golden("predict_ngf8_3x45x52")
+    _, sd = load_golden("generator_ngf8_b2_64x64")
+    g = _load(M.FFCResNetGenerator(**small_lama_kwargs(ngf=8, n_blocks=2)), sd)
+    img, mask = torch.from_numpy(a["images"]), torch.from_numpy(a["masks"])
+    with torch.no_grad():
+        prog = E.build_module_program(g, "generator_u8:8", (tuple(img.shape), tuple(mask.shape)), L.MATH_BF16X3)
+    assert prog.inputs == {"img": (3, 45, 52, 3), "mask": (3, 45, 52)} and prog.outputs == {"y0": (3, 45, 52, 3)}
+    assert prog.dtypes == {"img": torch.uint8, "mask": torch.uint8, "y0": torch.uint8}
+    assert isinstance(prog.ops[0], E.StemPackU8Op) and isinstance(prog.ops[-1], E.HeadGatherU8Op)
+    assert (prog.ops[0].out.buf.H, prog.ops[0].out.buf.W) == (48 + 6, 56 + 8)      # padded to modulo 8, + ring
+    # front end alone: bit-exact generator input
+    x = SpecInterpreter._u8_front(img, mask, 48, 56)
+    assert np.array_equal(x.numpy(), a["x"])
+    out = SpecInterpreter(prog).run({"img": img, "mask": mask})["y0"].numpy()
+    hole = a["masks"] > 0
+    assert out.dtype == np.uint8 and np.array_equal(out[~hole], a["out"][~hole])
+    d = np.abs(out[hole].astype(int) - a["out"][hole].astype(int))
+    assert d.max() <= 1 and (d != 0).mean() < 0.01
+    # the fp32 CUDA-core arm has no uint8 front / back end: asking for it is an error, not a silent detour
+    with pytest.raises(ValueError):
+        E.build_module_program(g, "generator_u8:8", (tuple(img.shape), tuple(mask.shape)), L.MATH_FP32)
