@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--io", default=os.environ.get("LAMA_B200_BENCH_IO", "f32"), choices=["f32", "both"],
+    ap.add_argument("--io", default=os.environ.get("LAMA_B200_BENCH_IO", "both"), choices=["f32", "both"],
                     help="both: also time the uint8 predict path (lama_b200.predict, SURVEY.md row f1) end to end")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
