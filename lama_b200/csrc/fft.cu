@@ -30,11 +30,22 @@ using namespace fftc;
 // buffer holding the result.  Ends with a barrier.
 template <int N, bool INV>
 __device__ __forceinline__ float2* fft_dispatch(float2* a, float2* b, const float2* tw, int n, int lane, int worker,
-                                                int nworkers) {
+                                                int nworkers, const RtPlan& rp) {
   if constexpr (N == 0) {
-    dft_pass<INV, kLanes>(a, b, tw, n, lane, worker, nworkers);
-    __syncthreads();
-    return b;
+    if (rp.np < 0) {                       // direct DFT
+      dft_pass<INV, kLanes>(a, b, tw, n, lane, worker, nworkers);
+      __syncthreads();
+      return b;
+    }
+    int ns = 1;                            // runtime mixed-radix Stockham (row f2)
+    for (int p = 0; p < rp.np; ++p) {
+      const int R = rp.radix[p];
+      generic_pass<INV, kLanes>(a, b, tw, n, R, ns, lane, worker, nworkers);
+      __syncthreads();
+      ns *= R;
+      float2* t = a; a = b; b = t;
+    }
+    return a;
   } else {
     stockham_pass<N, 0, INV, kLanes>(a, b, tw, lane, worker, nworkers);
     __syncthreads();
@@ -74,7 +85,7 @@ __device__ __forceinline__ void carve(float2* smem, int n, int group, float2*& t
 // Row pass, forward.  grid.x = ceil(B*ceil(H/2) / G), grid.y = ceil(C/32).
 // in (B,H,W,C) real  ->  ws[b][y][k][c] complex, k = 0..W/2   (unscaled)
 template <int N>
-__global__ void __launch_bounds__(1024) rfft_rows_kernel(View in, float2* __restrict__ ws, int n) {
+__global__ void __launch_bounds__(1024) rfft_rows_kernel(View in, float2* __restrict__ ws, int n, RtPlan rp) {
   extern __shared__ float2 smem_f2[];
   const int W = (N > 0) ? N : n;
   const int lane = threadIdx.x, worker = threadIdx.y, nworkers = blockDim.y, group = threadIdx.z;
@@ -100,7 +111,7 @@ __global__ void __launch_bounds__(1024) rfft_rows_kernel(View in, float2* __rest
     data[x * kLanes + lane] = z;
   }
   __syncthreads();
-  const float2* res = fft_dispatch<N, false>(data, tmp, tw, W, lane, worker, nworkers);
+  const float2* res = fft_dispatch<N, false>(data, tmp, tw, W, lane, worker, nworkers, rp);
 
   const int wf = W / 2 + 1;
   if (cok) {
@@ -118,7 +129,7 @@ __global__ void __launch_bounds__(1024) rfft_rows_kernel(View in, float2* __rest
 // ws[b][y][k][c] complex -> spec (B,H,Wf,2C): channel 2c = Re, 2c+1 = Im, scaled by `scale`.
 template <int N>
 __global__ void __launch_bounds__(1024) fft_cols_fwd_kernel(const float2* __restrict__ ws, View spec, int n,
-                                                            int C, float scale) {
+                                                            int C, float scale, RtPlan rp) {
   extern __shared__ float2 smem_f2[];
   const int H = (N > 0) ? N : n;
   const int lane = threadIdx.x, worker = threadIdx.y, nworkers = blockDim.y, group = threadIdx.z;
@@ -140,7 +151,7 @@ __global__ void __launch_bounds__(1024) fft_cols_fwd_kernel(const float2* __rest
     data[y * kLanes + lane] = z;
   }
   __syncthreads();
-  const float2* res = fft_dispatch<N, false>(data, tmp, tw, H, lane, worker, nworkers);
+  const float2* res = fft_dispatch<N, false>(data, tmp, tw, H, lane, worker, nworkers, rp);
 
   if (cok) {
     for (int y = worker; y < H; y += nworkers) {
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(1024) fft_cols_fwd_kernel(const float2* __rest
 
 // Column pass, inverse: spec (B,H,Wf,2C) -> ws[b][y][k][c] complex (unscaled inverse along H).
 template <int N>
-__global__ void __launch_bounds__(N > 0 && N <= 64 ? 256 : 1024, N > 0 && N <= 64 ? 6 : 1) fft_cols_inv_kernel(View spec, float2* __restrict__ ws, int n, int C) {
+__global__ void __launch_bounds__(N > 0 && N <= 64 ? 256 : 1024, N > 0 && N <= 64 ? 6 : 1) fft_cols_inv_kernel(View spec, float2* __restrict__ ws, int n, int C, RtPlan rp) {
   extern __shared__ float2 smem_f2[];
   const int H = (N > 0) ? N : n;
   const int lane = threadIdx.x, worker = threadIdx.y, nworkers = blockDim.y, group = threadIdx.z;
@@ -193,7 +204,7 @@ __global__ void __launch_bounds__(N > 0 && N <= 64 ? 256 : 1024, N > 0 && N <= 6
     data[y * kLanes + lane] = z;
   }
   __syncthreads();
-  const float2* res = fft_dispatch<N, true>(data, tmp, tw, H, lane, worker, nworkers);
+  const float2* res = fft_dispatch<N, true>(data, tmp, tw, H, lane, worker, nworkers, rp);
 
   if (cok) {
     for (int y = worker; y < H; y += nworkers)
@@ -205,7 +216,7 @@ __global__ void __launch_bounds__(N > 0 && N <= 64 ? 256 : 1024, N > 0 && N <= 6
 // out = residual + scale * c2r(ws).  Im of bins 0 and (even W) W/2 is ignored.
 template <int N>
 __global__ void __launch_bounds__(N > 0 && N <= 64 ? 256 : 1024, N > 0 && N <= 64 ? 6 : 1) irfft_rows_kernel(const float2* __restrict__ ws, View res, View out, int n,
-                                                          float scale) {
+                                                          float scale, RtPlan rp) {
   extern __shared__ float2 smem_f2[];
   const int W = (N > 0) ? N : n;
   const int lane = threadIdx.x, worker = threadIdx.y, nworkers = blockDim.y, group = threadIdx.z;
@@ -233,7 +244,7 @@ __global__ void __launch_bounds__(N > 0 && N <= 64 ? 256 : 1024, N > 0 && N <= 6
     c2r_pair_pre<kLanes>(data, W, k, lane, x1, x2);
   }
   __syncthreads();
-  const float2* fin = fft_dispatch<N, true>(data, tmp, tw, W, lane, worker, nworkers);
+  const float2* fin = fft_dispatch<N, true>(data, tmp, tw, W, lane, worker, nworkers, rp);
 
   if (cok) {
     if (N > 0) {
@@ -277,13 +288,23 @@ struct LaunchPlan {
   int n;       // runtime length
   dim3 block;  // (32, workers, groups)
   size_t smem;
+  RtPlan rp;   // N == 0: runtime radix plan (np < 0: direct DFT)
 };
+
+// Lengths without a compile-time plan: runtime mixed-radix Stockham (FFCB_FFT_MIXED_RADIX=0 selects the O(n^2)
+// direct DFT they ran in the first revision — same results to round-off, kept as the cross-check).
+bool mixed_radix_enabled() {
+  const char* e = getenv("FFCB_FFT_MIXED_RADIX");
+  return e ? atoi(e) != 0 : false;
+}
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 LaunchPlan make_plan(int n) {
   LaunchPlan p;
   p.n = n;
+  p.rp.np = -1;
+  for (int i = 0; i < kMaxRtPasses; ++i) p.rp.radix[i] = 1;
   if (is_pow2(n) && n >= 4 && n <= 256) {
     p.N = n;
     const int workers = fftc::workers_for(n);
@@ -292,7 +313,12 @@ LaunchPlan make_plan(int n) {
     p.smem = sizeof(float2) * ((size_t)n + (size_t)groups * 2 * n * kLanes);
   } else {
     p.N = 0;
-    const int workers = n >= 8 ? 8 : (n >= 4 ? 4 : 1);
+    int workers = n >= 8 ? 8 : (n >= 4 ? 4 : 1);
+    if (mixed_radix_enabled()) {
+      p.rp = make_rt_plan(n);
+      // one output per worker-iteration: ~8 outputs per worker and pass, up to a full 1024-thread CTA
+      if (n > 64) workers = (n + 7) / 8 < 32 ? (n + 7) / 8 : 32;
+    }
     const int groups = n <= 32 ? (8 / workers > 0 ? 8 / workers : 1) : 1;
     p.block = dim3(kLanes, workers, groups);
     p.smem = sizeof(float2) * ((size_t)n + (size_t)groups * 2 * n * kLanes);
@@ -363,7 +389,7 @@ int rfft2(const ffcb_tensor* in, const ffcb_tensor* spec, void* ws, size_t ws_by
     dim3 grid((pairs + p.block.z - 1) / p.block.z, cblocks);
     FFCB_DISPATCH_N(p, {
       if ((rc = set_smem(rfft_rows_kernel<NN>, p.smem))) return rc;
-      rfft_rows_kernel<NN><<<grid, p.block, p.smem, stream>>>(vin, w2, p.n);
+      rfft_rows_kernel<NN><<<grid, p.block, p.smem, stream>>>(vin, w2, p.n, p.rp);
     });
     FFCB_LAUNCH_CHECK("rfft_rows_kernel");
   }
@@ -373,7 +399,7 @@ int rfft2(const ffcb_tensor* in, const ffcb_tensor* spec, void* ws, size_t ws_by
     dim3 grid((cols + p.block.z - 1) / p.block.z, cblocks);
     FFCB_DISPATCH_N(p, {
       if ((rc = set_smem(fft_cols_fwd_kernel<NN>, p.smem))) return rc;
-      fft_cols_fwd_kernel<NN><<<grid, p.block, p.smem, stream>>>(w2, vspec, p.n, in->C, scale);
+      fft_cols_fwd_kernel<NN><<<grid, p.block, p.smem, stream>>>(w2, vspec, p.n, in->C, scale, p.rp);
     });
     FFCB_LAUNCH_CHECK("fft_cols_fwd_kernel");
   }
@@ -410,7 +436,7 @@ int irfft2(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tens
     dim3 grid((cols + p.block.z - 1) / p.block.z, cblocks);
     FFCB_DISPATCH_N(p, {
       if ((rc = set_smem(fft_cols_inv_kernel<NN>, p.smem))) return rc;
-      fft_cols_inv_kernel<NN><<<grid, p.block, p.smem, stream>>>(vspec, w2, p.n, out->C);
+      fft_cols_inv_kernel<NN><<<grid, p.block, p.smem, stream>>>(vspec, w2, p.n, out->C, p.rp);
     });
     FFCB_LAUNCH_CHECK("fft_cols_inv_kernel");
   }
@@ -420,7 +446,7 @@ int irfft2(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tens
     dim3 grid((pairs + p.block.z - 1) / p.block.z, cblocks);
     FFCB_DISPATCH_N(p, {
       if ((rc = set_smem(irfft_rows_kernel<NN>, p.smem))) return rc;
-      irfft_rows_kernel<NN><<<grid, p.block, p.smem, stream>>>(w2, vres, vout, p.n, scale);
+      irfft_rows_kernel<NN><<<grid, p.block, p.smem, stream>>>(w2, vres, vout, p.n, scale, p.rp);
     });
     FFCB_LAUNCH_CHECK("irfft_rows_kernel");
   }

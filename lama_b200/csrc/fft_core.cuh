@@ -129,6 +129,79 @@ FFCB_HD void dft_pass(const float2* src, float2* dst, const float2* tw, int n, i
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lengths without a compile-time plan (bin/predict.py pads images to multiples of 8 only, so the
+// bottleneck planes are e.g. 96x128, 135x240, 125x188): a runtime mixed-radix Stockham autosort.  The length is
+// split into factors R_0 * R_1 * ... (any integers >= 2); pass p is the textbook radix-R_p Stockham step with the
+// R-point butterfly evaluated directly, one output per iteration:
+//   dst[j0 + q*NS] = sum_r src[j + r*n/R] * w_n^{ r * (k * n/(NS*R) + q * n/R) },  k = j mod NS, j0 = (j-k)*R + k
+// so one transform costs n * sum_p R_p complex MACs instead of n^2 (a prime length degenerates to the direct DFT).
+constexpr int kMaxRtPasses = 8;
+struct RtPlan {
+  int np;                    // number of passes; < 0: use dft_pass (single direct DFT)
+  int radix[kMaxRtPasses];
+};
+
+// Factorisation minimising sum_p (R_p + 3) (the +3 prices a pass: barrier, index set-up, one smem round trip).
+// Host only.
+inline RtPlan make_rt_plan(int n) {
+  RtPlan p;
+  p.np = 0;
+  for (int i = 0; i < kMaxRtPasses; ++i) p.radix[i] = 1;
+  constexpr int kMaxN = 1024;
+  if (n < 2) return p;
+  if (n > kMaxN) { p.np = 1; p.radix[0] = n; return p; }
+  static_assert(kMaxN <= 1024, "cost tables live on the stack");
+  int cost[kMaxN + 1], pick[kMaxN + 1];
+  cost[1] = 0; pick[1] = 1;
+  for (int m = 2; m <= n; ++m) {
+    if (n % m) continue;
+    cost[m] = m + 3; pick[m] = m;
+    for (int d = 2; d * 2 <= m; ++d) {
+      if (m % d || n % (m / d)) continue;
+      const int c = d + 3 + cost[m / d];
+      if (c < cost[m]) { cost[m] = c; pick[m] = d; }
+    }
+  }
+  int m = n, radices[32], cnt = 0;
+  while (m > 1 && cnt < 32) { radices[cnt++] = pick[m]; m /= pick[m]; }
+  // more factors than slots (cannot happen for n <= 1024, where at most 5 are chosen): merge the tail
+  while (cnt > kMaxRtPasses) { radices[cnt - 2] *= radices[cnt - 1]; --cnt; }
+  // largest radix first: the early passes (NS small) need no twiddle beyond the butterfly's own
+  for (int i = 0; i < cnt; ++i)
+    for (int j = i + 1; j < cnt; ++j)
+      if (radices[j] > radices[i]) { const int t = radices[i]; radices[i] = radices[j]; radices[j] = t; }
+  p.np = cnt;
+  for (int i = 0; i < cnt; ++i) p.radix[i] = radices[i];
+  return p;
+}
+
+// One runtime-radix Stockham pass (src -> dst) for one lane; outputs o = worker, worker+nw, ...
+template <bool INV, int LS>
+FFCB_HD void generic_pass(const float2* src, float2* dst, const float2* tw, int n, int R, int NS, int lane, int worker,
+                          int nworkers) {
+  const int NB = n / R;              // butterflies
+  const int tws = n / (NS * R);      // twiddle exponent per unit of k
+  for (int o = worker; o < n; o += nworkers) {
+    const int q = o / NB, j = o - q * NB;
+    const int k = j % NS;
+    const int step = (k * tws + q * NB) % n;
+    float2 acc = make_float2(0.f, 0.f);
+    int t = 0;                       // (r * step) mod n
+    const float2* s = src + j * LS + lane;
+    for (int r = 0; r < R; ++r) {
+      float2 w = tw[t];
+      if (INV) w.y = -w.y;
+      const float2 x = s[r * NB * LS];
+      acc.x += x.x * w.x - x.y * w.y;
+      acc.y += x.x * w.y + x.y * w.x;
+      t += step;
+      if (t >= n) t -= n;
+    }
+    dst[((j - k) * R + k + q * NS) * LS + lane] = acc;
+  }
+}
+
 // Two-for-one real transforms.  z = row_a + i * row_b, Z = FFT(z) (length W, unnormalised):
 //   A[k] = (Z[k] + conj(Z[-k])) / 2,  B[k] = (Z[k] - conj(Z[-k])) / (2i),  k = 0 .. W/2
 template <int LS>

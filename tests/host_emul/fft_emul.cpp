@@ -23,6 +23,8 @@ static std::vector<float2> twiddles(int n) {
   return tw;
 }
 
+static bool g_mixed_radix = false;
+
 template <int N, bool INV>
 static float2* run_pow2(float2* a, float2* b, const float2* tw) {
   const int nw = workers_for(N);
@@ -48,9 +50,23 @@ static float2* run_any(int n, float2* a, float2* b, const float2* tw) {
       case 256: return run_pow2<256, INV>(a, b, tw);
     }
   }
-  const int nw = 8;
-  for (int w = 0; w < nw; ++w) dft_pass<INV, 1>(a, b, tw, n, 0, w, nw);
-  return b;
+  if (!g_mixed_radix) {
+    const int nw = 8;
+    for (int w = 0; w < nw; ++w) dft_pass<INV, 1>(a, b, tw, n, 0, w, nw);
+    return b;
+  }
+  // runtime mixed-radix Stockham (fft.cu: fft_dispatch<0> with an RtPlan)
+  const RtPlan rp = make_rt_plan(n);
+  const int nw = 12;
+  int ns = 1, prod = 1;
+  for (int p = 0; p < rp.np; ++p) {
+    for (int w = 0; w < nw; ++w) generic_pass<INV, 1>(a, b, tw, n, rp.radix[p], ns, 0, w, nw);
+    ns *= rp.radix[p];
+    prod *= rp.radix[p];
+    std::swap(a, b);
+  }
+  if (prod != (n < 2 ? 1 : n)) { printf("bad plan for n=%d\n", n); exit(2); }
+  return a;
 }
 
 static double check(int H, int W, bool verbose) {
@@ -78,13 +94,22 @@ static double check(int H, int W, bool verbose) {
     const float2* r = run_any<false>(H, a.data(), b.data(), twh.data());
     for (int y = 0; y < H; ++y) spec[y * wf + k] = make_float2(r[y].x * scale, r[y].y * scale);
   }
+  // double-precision reference, separable (row DFT, then column DFT) with tabulated roots of unity
+  std::vector<cd> rw(W), rh(H);
+  for (int t = 0; t < W; ++t) rw[t] = std::polar(1.0, -2 * M_PI * t / W);
+  for (int t = 0; t < H; ++t) rh[t] = std::polar(1.0, -2 * M_PI * t / H);
+  std::vector<cd> rowdft(H * wf);
+  for (int y = 0; y < H; ++y)
+    for (int kx = 0; kx < wf; ++kx) {
+      cd acc = 0;
+      for (int xx = 0; xx < W; ++xx) acc += (double)x[y * W + xx] * rw[(kx * xx) % W];
+      rowdft[y * wf + kx] = acc;
+    }
   double err_f = 0, mag = 0;
   for (int ky = 0; ky < H; ++ky)
     for (int kx = 0; kx < wf; ++kx) {
       cd acc = 0;
-      for (int y = 0; y < H; ++y)
-        for (int xx = 0; xx < W; ++xx)
-          acc += (double)x[y * W + xx] * std::polar(1.0, -2 * M_PI * ((double)ky * y / H + (double)kx * xx / W));
+      for (int y = 0; y < H; ++y) acc += rowdft[y * wf + kx] * rh[(ky * y) % H];
       acc /= std::sqrt((double)H * W);
       err_f = std::max(err_f, std::abs(acc - cd(spec[ky * wf + kx].x, spec[ky * wf + kx].y)));
       mag = std::max(mag, std::abs(acc));
@@ -115,14 +140,14 @@ static double check(int H, int W, bool verbose) {
   for (int k = 0; k < wf; ++k)
     for (int y = 0; y < H; ++y) {
       cd acc = 0;
-      for (int q = 0; q < H; ++q) acc += cd(z[q * wf + k].x, z[q * wf + k].y) * std::polar(1.0, 2 * M_PI * (double)q * y / H);
+      for (int q = 0; q < H; ++q) acc += cd(z[q * wf + k].x, z[q * wf + k].y) * std::conj(rh[(q * y) % H]);
       t[y * wf + k] = acc / std::sqrt((double)H);
     }
   for (int y = 0; y < H; ++y)
     for (int n = 0; n < W; ++n) {
       double acc = t[y * wf].real();
       const int last = (W % 2 == 0) ? wf - 1 : wf;
-      for (int k = 1; k < last; ++k) acc += 2.0 * (t[y * wf + k] * std::polar(1.0, 2 * M_PI * (double)k * n / W)).real();
+      for (int k = 1; k < last; ++k) acc += 2.0 * (t[y * wf + k] * std::conj(rw[(k * n) % W])).real();
       if (W % 2 == 0) acc += t[y * wf + wf - 1].real() * ((n % 2) ? -1.0 : 1.0);
       acc /= std::sqrt((double)W);
       err_i = std::max(err_i, std::abs(acc - (double)out[y * W + n]));
@@ -205,6 +230,18 @@ int main(int argc, char** argv) {
   double worst = 0;
   for (auto& s : sizes) worst = std::max(worst, check(s[0], s[1], verbose));
   worst = std::max(worst, check_plane64(verbose));
+  // runtime mixed-radix plans (row f2): composite, prime-power, prime and large-prime-factor lengths
+  g_mixed_radix = true;
+  const int mixed[][2] = {{15, 15}, {6, 9}, {20, 24}, {5, 9}, {7, 6}, {3, 2}, {1, 8}, {2, 2}, {125, 188}, {96, 128},
+                          {135, 240}, {100, 36}, {47, 94}, {243, 12}, {27, 250}, {49, 98}, {192, 160}, {13, 26}};
+  for (auto& s : mixed) worst = std::max(worst, check(s[0], s[1], verbose));
+  for (int n = 2; n <= 320; ++n) {            // every plan multiplies back to n with radices >= 2
+    const RtPlan rp = make_rt_plan(n);
+    int prod = 1, sum = 0;
+    for (int p = 0; p < rp.np; ++p) { prod *= rp.radix[p]; sum += rp.radix[p]; if (rp.radix[p] < 2) return 3; }
+    if (prod != n || rp.np > kMaxRtPasses) { printf("plan(%d) broken\n", n); return 3; }
+    if (verbose && (n % 8 == 0)) { printf("plan(%3d) =", n); for (int p = 0; p < rp.np; ++p) printf(" %d", rp.radix[p]); printf("  (sum %d)\n", sum); }
+  }
   printf("worst relative error %.3e\n", worst);
   return worst < 2e-6 ? 0 : 1;
 }

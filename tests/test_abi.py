@@ -65,7 +65,8 @@ def test_missing_library_is_loud(monkeypatch, tmp_path):
 
 def test_host_emulation_of_fft_kernels(tmp_path):
     """The FFT kernels' arithmetic (fft_core.cuh) compiled for the host and checked against a
-    double-precision DFT for every supported size class (pow2 Stockham + direct DFT, C2R rule)."""
+    double-precision DFT for every supported size class (pow2 Stockham, direct DFT, runtime mixed-radix Stockham
+    plans for composite / prime-power / prime lengths, C2R rule, fused 64x64 plane functors)."""
     exe = tmp_path / "fft_emul"
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-I/usr/local/cuda/include",
                            os.path.join(ROOT, "tests", "host_emul", "fft_emul.cpp"), "-o", str(exe)])

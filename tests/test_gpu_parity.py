@@ -81,6 +81,18 @@ def test_rfft2_irfft2_against_numpy(b, c, h, w, math_mode):
     _check_fft_pair(b, c, h, w)
 
 
+@pytest.mark.parametrize("mixed", ["0", "1"])
+@pytest.mark.parametrize("b,c,h,w", [(1, 4, 15, 15), (2, 4, 6, 9), (1, 8, 125, 188), (1, 36, 96, 128),
+                                     (1, 4, 135, 240), (2, 8, 47, 94), (1, 4, 7, 250), (1, 4, 3, 2)])
+def test_fft_lengths_without_compile_time_plan(b, c, h, w, mixed, math_mode, monkeypatch):
+    """SURVEY.md row f2 (bin/predict.py pads to multiples of 8 only -> 96x128, 135x240, 125x188 ... bottleneck
+    planes): runtime mixed-radix Stockham (FFCB_FFT_MIXED_RADIX=1) and the O(n^2) direct DFT (=0) against numpy —
+    composite, prime-power, prime and large-prime-factor lengths."""
+    _fp32_only(math_mode)
+    monkeypatch.setenv("FFCB_FFT_MIXED_RADIX", mixed)
+    _check_fft_pair(b, c, h, w)
+
+
 def test_two_pass_fft_kernels_at_64x64(math_mode, monkeypatch):
     """64x64 planes normally take the fused whole-plane kernels (fft_plane.cu); keep the general
     row/column kernels covered at that size too."""
