@@ -101,12 +101,23 @@ def test_two_pass_fft_kernels_at_64x64(math_mode, monkeypatch):
     _check_fft_pair(2, 40, 64, 64)
 
 
+@pytest.mark.parametrize("plane_ch", ["8", "4"])
 @pytest.mark.parametrize("variant", ["1", "2"])
-def test_inverse_plane_kernel_opt_in(math_mode, monkeypatch, variant):
-    """The fused inverse plane kernels (fft_plane.cu; 1 = packed 8-warp, 2 = 9-warp) are opt-in in round 1
-    (not faster than two-pass yet); keep them correct."""
+def test_inverse_plane_kernel_opt_in(math_mode, monkeypatch, variant, plane_ch):
+    """The fused inverse plane kernels (fft_plane.cu; 1 = packed, 2 = one task per column; 8 or 4 channels per
+    CTA) are opt-in in round 1 (not faster than two-pass yet); keep them correct."""
     _fp32_only(math_mode)
     monkeypatch.setenv("FFCB_FFT_INV_PLANE", variant)
+    monkeypatch.setenv("FFCB_FFT_PLANE_CH", plane_ch)
+    _check_fft_pair(2, 24, 64, 64)
+
+
+@pytest.mark.parametrize("occ", ["2", "3"])
+def test_forward_plane_kernel_4_channels_per_cta(math_mode, monkeypatch, occ):
+    """FFCB_FFT_PLANE_CH=4: 69 KB CTAs, two (or, registers capped, three) per SM."""
+    _fp32_only(math_mode)
+    monkeypatch.setenv("FFCB_FFT_PLANE_CH", "4")
+    monkeypatch.setenv("FFCB_FFT_PLANE_OCC", occ)
     _check_fft_pair(2, 24, 64, 64)
 
 

@@ -1,0 +1,70 @@
+"""FFT microbenchmark (CUDA events on the launch stream, warm, inputs larger than... see below):
+  * the FourierUnit shape of the headline workload (B=32, C=192, 64x64 planes) under the plane-kernel variants
+    (FFCB_FFT_PLANE_CH / FFCB_FFT_PLANE_OCC / FFCB_FFT_INV_PLANE / FFCB_FFT_TWO_PASS), forward and inverse apart;
+  * planes without a compile-time plan (row f2): direct DFT vs runtime mixed-radix Stockham.
+Run on the GPU box:  python tools/fft_microbench.py  -> one JSON line per configuration."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lama_b200 import _lib as L          # noqa: E402
+from lama_b200 import engine as E        # noqa: E402
+
+KNOBS = ("FFCB_FFT_MIXED_RADIX", "FFCB_FFT_PLANE_CH", "FFCB_FFT_PLANE_OCC", "FFCB_FFT_INV_PLANE", "FFCB_FFT_TWO_PASS")
+
+
+def time_ops(b, c, h, w, env, which, reps=10, spec_fmt_split=True):
+    for k in KNOBS:
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    wf = w // 2 + 1
+    # same formats as the FourierUnit of the generator program: real planes float32, forward spectrum split bf16
+    # (GEMM operand), post-GEMM spectrum float32, inverse output split bf16 (operand of conv2)
+    prog = E.Program("fft_bench", L.MATH_BF16X3)
+    X = prog.buf("x", b, h, w, c)
+    S = prog.buf("s", b, h, wf, 2 * c, gemm=spec_fmt_split)
+    Z = prog.buf("z", b, h, wf, 2 * c)
+    O = prog.buf("o", b, h, w, c, gemm=spec_fmt_split)
+    if which == "fwd":
+        prog.ops += [E.RfftOp(E.TV(X), E.TV(S))]
+        alg = 4 * b * h * w * c + 4 * b * h * wf * 2 * c
+    else:
+        prog.ops += [E.IrfftOp(E.TV(Z), E.TV(X), E.TV(O))]
+        alg = 4 * b * h * wf * 2 * c + 2 * 4 * b * h * w * c
+    ex = E.CudaExecutor(prog, torch.device("cuda:0"))
+    ex.storage[X.name].normal_()
+    ex.storage[Z.name].normal_()
+    for _ in range(3):
+        ex.run({})
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ex.run({})
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"op": which, "plane": f"{h}x{w}", "B": b, "C": c, "env": env, "us": round(ms * 1e3, 1),
+            "GBps_in_plus_out": round(alg / ms / 1e6, 1), "launches": ex.launches_per_run}
+
+
+if __name__ == "__main__":
+    fu = (32, 192, 64, 64)
+    if "--fu-only" in sys.argv:          # the shipped configuration only (for an ncu capture)
+        print(json.dumps(time_ops(*fu, {}, "fwd", reps=1)), flush=True)
+        print(json.dumps(time_ops(*fu, {}, "inv", reps=1)), flush=True)
+        sys.exit(0)
+    for env in [{}, {"FFCB_FFT_PLANE_CH": "4"}, {"FFCB_FFT_PLANE_CH": "4", "FFCB_FFT_PLANE_OCC": "3"},
+                {"FFCB_FFT_TWO_PASS": "1"}]:
+        print(json.dumps(time_ops(*fu, env, "fwd")), flush=True)
+    for env in [{}, {"FFCB_FFT_INV_PLANE": "1"}, {"FFCB_FFT_INV_PLANE": "2"},
+                {"FFCB_FFT_INV_PLANE": "1", "FFCB_FFT_PLANE_CH": "4"},
+                {"FFCB_FFT_INV_PLANE": "2", "FFCB_FFT_PLANE_CH": "4"}]:
+        print(json.dumps(time_ops(*fu, env, "inv")), flush=True)
+    for (h, w) in [(96, 128), (125, 188), (135, 240)]:
+        for mixed in ("0", "1"):
+            for which in ("fwd", "inv"):
+                print(json.dumps(time_ops(8, 192, h, w, {"FFCB_FFT_MIXED_RADIX": mixed}, which, reps=5)), flush=True)
