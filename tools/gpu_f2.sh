@@ -11,6 +11,6 @@ FFCB_FFT_MIXED_RADIX=1 timeout 150 python -m pytest tests/test_gpu_parity.py -q 
 echo "pytest B (mixed radix on) rc=$?"; tail -2 $OUT/f2_pytest_b.log
 timeout 120 python tools/fft_microbench.py > $OUT/f2_fft_microbench.jsonl 2> $OUT/f2_fft_microbench.err
 echo "microbench rc=$?"; cat $OUT/f2_fft_microbench.jsonl | cut -c1-230
-timeout 150 ncu --set full --clock-control none --import-source on -k regex:"fft" -c 4 -f -o $OUT/f2_fft_ncu \
+timeout 150 ncu --set full --clock-control none --import-source on -k regex:"fft" -c 3 -f -o $OUT/f2_fft_ncu \
   python tools/fft_microbench.py --fu-only > $OUT/f2_ncu.log 2>&1
 echo "ncu rc=$?"; ls -la $OUT/f2_fft_ncu.ncu-rep 2>/dev/null
