@@ -295,7 +295,7 @@ struct LaunchPlan {
 // direct DFT they ran in the first revision — same results to round-off, kept as the cross-check).
 bool mixed_radix_enabled() {
   const char* e = getenv("FFCB_FFT_MIXED_RADIX");
-  return e ? atoi(e) != 0 : false;
+  return e ? atoi(e) != 0 : true;
 }
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
