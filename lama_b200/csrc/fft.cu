@@ -364,6 +364,7 @@ int check_fft_shapes(const ffcb_tensor* real, const ffcb_tensor* spec, const cha
 bool plane64_eligible(const ffcb_tensor* real);
 int rfft2_plane64(const ffcb_tensor* in, const ffcb_tensor* spec, cudaStream_t stream);
 int irfft2_plane64(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out, cudaStream_t stream);
+int inv_plane_variant();
 
 size_t fft2_workspace_bytes(int B, int H, int W, int C) {
   return sizeof(float2) * (size_t)B * H * (W / 2 + 1) * C;
@@ -423,9 +424,12 @@ int irfft2(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tens
     return FFCB_ENOMEM;
   }
   if (out->B == 0 || out->C == 0) return FFCB_OK;
-  // the fused inverse plane kernel is correct but (round 1) slower than the two-pass kernels: opt-in only
-  if (plane64_eligible(out) && getenv("FFCB_FFT_INV_PLANE") && !getenv("FFCB_FFT_TWO_PASS"))
-    return irfft2_plane64(spec, residual, out, stream);
+  // FFCB_FFT_INV_PLANE: 0 = two-pass kernels, 1 / 2 = first-revision plane kernels (slower than two-pass),
+  // 3 = second revision; irfft2_plane64 returns 1 when the chosen variant does not apply to these views
+  if (plane64_eligible(out) && inv_plane_variant() != 0 && !getenv("FFCB_FFT_TWO_PASS")) {
+    rc = irfft2_plane64(spec, residual, out, stream);
+    if (rc <= 0) return rc;
+  }
   const View vspec = make_view(*spec), vout = make_view(*out);
   float2* w2 = reinterpret_cast<float2*>(ws);
   const int cblocks = (out->C + kLanes - 1) / kLanes;

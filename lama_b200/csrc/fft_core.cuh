@@ -385,5 +385,17 @@ FFCB_HD void plane64_rows_inv(Load&& ld, Store&& st) {
   }
 }
 
+// Inverse plane kernel, second revision (fft_plane.cu: irfft2_plane64_v2_kernel): after the C2R row transforms the
+// real results of row r are staged IN PLACE of that row's half spectrum (S row = 268 float2 = 536 floats >= 64 px x
+// 8 channels), channels-last, so that the epilogue moves whole pixels (8 channels = 32 bytes) with vector accesses.
+constexpr int kP64Pitch = 33 * 8 + 4;        // float2 per S row of the 8-channel plane kernels
+FFCB_HD int p64_stage_index(int row, int x, int c) { return row * (2 * kP64Pitch) + x * 8 + c; }   // float index
+// epilogue slot i (0..15) of a lane: warp w owns rows 8w .. 8w+7 (its four row-pair groups), 64 pixels each
+FFCB_HD void p64_store_slot(int warp, int lane, int i, int& row, int& x) {
+  const int s = i * 32 + lane;
+  row = 8 * warp + (s >> 6);
+  x = s & 63;
+}
+
 }  // namespace fftc
 }  // namespace ffcb

@@ -222,6 +222,72 @@ static double check_plane64(bool verbose) {
   return std::max(err_f / mag, err_i / mag_i);
 }
 
+// irfft2_plane64_v2_kernel (fft_plane.cu): emulate ONE CTA (8 channels) thread by thread, phase by phase, with the
+// kernel's index expressions: column tasks -> S, row tasks -> results staged in place of their rows (after every
+// thread of the row's group has its inputs in registers), channels-last epilogue slots -> output (+ residual).
+static double check_plane64_inv_v2(bool verbose) {
+  const int N = 64, WF = 33, CH = 8, P = kP64Pitch;
+  std::vector<float> spec((size_t)N * WF * 2 * CH), res((size_t)N * N * CH), out((size_t)N * N * CH, -1e30f);
+  for (auto& v : spec) v = std::max(0.f, (float)(rand() / (double)RAND_MAX * 2 - 1));
+  for (auto& v : res) v = (float)(rand() / (double)RAND_MAX);
+  const unsigned spec_sx = 2 * CH, spec_sy = WF * 2 * CH, res_sx = CH, res_sy = N * CH;
+  const float scale = 1.0f / 64.0f;
+  std::vector<float2> S((size_t)N * P, make_float2(1e30f, 1e30f));
+  for (int tid = 0; tid < WF * CH; ++tid) {           // phase A
+    const int c = tid & 7, g = tid >> 3;
+    const unsigned o0 = (unsigned)g * spec_sx + 2u * c;
+    plane64_col<true>([&](int ky) { const float* q = spec.data() + (o0 + (unsigned)ky * spec_sy); return make_float2(q[0], q[1]); },
+                      [&](int y, float2 z) { S[y * P + g * 8 + c] = z; });
+  }
+  float* R = reinterpret_cast<float*>(S.data());
+  for (int warp = 0; warp < 8; ++warp) {              // phase B, one warp at a time: compute all lanes, then write
+    std::vector<float2> held(32 * 64);
+    for (int lane = 0; lane < 32; ++lane) {
+      const int tid = warp * 32 + lane, c = tid & 7, g = tid >> 3;
+      plane64_rows_inv([&](int k, float2& x1, float2& x2) { x1 = S[(2 * g) * P + k * 8 + c]; x2 = S[(2 * g + 1) * P + k * 8 + c]; },
+                       [&](int n0, const float2* zb) { for (int j = 0; j < 16; ++j) held[lane * 64 + n0 + j] = zb[j]; });
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+      const int tid = warp * 32 + lane, c = tid & 7, g = tid >> 3;
+      for (int n = 0; n < 64; ++n) {
+        R[p64_stage_index(2 * g, n, c)] = held[lane * 64 + n].x;
+        R[p64_stage_index(2 * g + 1, n, c)] = held[lane * 64 + n].y;
+      }
+    }
+    for (int lane = 0; lane < 32; ++lane)             // phase C
+      for (int i = 0; i < 16; ++i) {
+        int row, x;
+        p64_store_slot(warp, lane, i, row, x);
+        for (int c = 0; c < CH; ++c)
+          out[(size_t)row * res_sy + x * res_sx + c] =
+              std::fma(R[p64_stage_index(row, x, 0) + c], scale, res[(size_t)row * res_sy + x * res_sx + c]);
+      }
+  }
+  double err = 0, mag = 0;
+  for (int c = 0; c < CH; ++c) {
+    std::vector<cd> t(N * WF);
+    for (int k = 0; k < WF; ++k)
+      for (int y = 0; y < N; ++y) {
+        cd acc = 0;
+        for (int q = 0; q < N; ++q)
+          acc += cd(spec[(size_t)q * spec_sy + k * spec_sx + 2 * c], spec[(size_t)q * spec_sy + k * spec_sx + 2 * c + 1]) *
+                 std::polar(1.0, 2 * M_PI * (double)q * y / N);
+        t[y * WF + k] = acc / 8.0;
+      }
+    for (int y = 0; y < N; ++y)
+      for (int n = 0; n < N; ++n) {
+        double acc = t[y * WF].real();
+        for (int k = 1; k < 32; ++k) acc += 2.0 * (t[y * WF + k] * std::polar(1.0, 2 * M_PI * (double)k * n / N)).real();
+        acc += t[y * WF + 32].real() * ((n % 2) ? -1.0 : 1.0);
+        acc = acc / 8.0 + res[(size_t)y * res_sy + n * res_sx + c];
+        err = std::max(err, std::abs(acc - (double)out[(size_t)y * res_sy + n * res_sx + c]));
+        mag = std::max(mag, std::abs(acc));
+      }
+  }
+  if (verbose) printf("plane64 inverse v2 (one CTA, 8 channels)   %.2e / %.2e\n", err, mag);
+  return err / mag;
+}
+
 int main(int argc, char** argv) {
   const bool verbose = argc > 1;
   const int sizes[][2] = {{4, 4}, {8, 8}, {16, 16}, {32, 32}, {64, 64}, {128, 128}, {256, 256}, {8, 32}, {64, 16},
@@ -230,6 +296,7 @@ int main(int argc, char** argv) {
   double worst = 0;
   for (auto& s : sizes) worst = std::max(worst, check(s[0], s[1], verbose));
   worst = std::max(worst, check_plane64(verbose));
+  worst = std::max(worst, check_plane64_inv_v2(verbose));
   // runtime mixed-radix plans (row f2): composite, prime-power, prime and large-prime-factor lengths
   g_mixed_radix = true;
   const int mixed[][2] = {{15, 15}, {6, 9}, {20, 24}, {5, 9}, {7, 6}, {3, 2}, {1, 8}, {2, 2}, {125, 188}, {96, 128},

@@ -112,6 +112,44 @@ def test_inverse_plane_kernel_opt_in(math_mode, monkeypatch, variant, plane_ch):
     _check_fft_pair(2, 24, 64, 64)
 
 
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("residual", [True, False])
+def test_plane_kernels_second_revision(math_mode, monkeypatch, split, residual):
+    """FFCB_FFT_PLANE_FWD=2 / FFCB_FFT_INV_PLANE=3: templated formats, 32-bit in-plane offsets, channels-last
+    vector epilogue staged in place of the half spectrum — all four format / residual instantiations, and
+    bit-identical results to the kernels they replace."""
+    _fp32_only(math_mode)
+    monkeypatch.setenv("FFCB_FFT_PLANE_FWD", "2")
+    monkeypatch.setenv("FFCB_FFT_INV_PLANE", "3")
+    _check_fft_pair(3, 40, 64, 64, split=split, residual=residual)
+
+
+def test_plane_kernels_second_revision_bit_identical_to_first(math_mode, monkeypatch):
+    _fp32_only(math_mode)
+    b, c, h, w = 2, 24, 64, 64
+    wf = w // 2 + 1
+
+    def run():
+        prog = E.Program("fft_cmp", L.MATH_BF16X3)
+        X = prog.buf("x", b, h, w, c); S = prog.buf("s", b, h, wf, 2 * c, gemm=True)
+        Z = prog.buf("z", b, h, wf, 2 * c); O = prog.buf("o", b, h, w, c, gemm=True)
+        prog.inputs = {"x0": (b, c, h, w), "x1": (b, 2 * c, h, wf)}
+        prog.ops += [E.ToNHWC("x0", E.TV(X)), E.RfftOp(E.TV(X), E.TV(S)), E.ToNCHW(E.TV(S), "y0"),
+                     E.ToNHWC("x1", E.TV(Z)), E.IrfftOp(E.TV(Z), E.TV(X), E.TV(O)), E.ToNCHW(E.TV(O), "y1")]
+        prog.outputs = {"y0": (b, 2 * c, h, wf), "y1": (b, c, h, w)}
+        g = torch.Generator().manual_seed(3)
+        return _run_program(prog, {"x0": torch.randn(b, c, h, w, generator=g),
+                                   "x1": torch.randn(b, 2 * c, h, wf, generator=g).clamp_min(0)})
+    monkeypatch.setenv("FFCB_FFT_PLANE_FWD", "1")
+    monkeypatch.setenv("FFCB_FFT_INV_PLANE", "2")
+    first = run()                       # first-revision plane kernels: the same per-thread transforms
+    monkeypatch.setenv("FFCB_FFT_PLANE_FWD", "2")
+    monkeypatch.setenv("FFCB_FFT_INV_PLANE", "3")
+    second = run()
+    assert torch.equal(first["y0"], second["y0"])
+    assert torch.equal(first["y1"], second["y1"])
+
+
 @pytest.mark.parametrize("occ", ["2", "3"])
 def test_forward_plane_kernel_4_channels_per_cta(math_mode, monkeypatch, occ):
     """FFCB_FFT_PLANE_CH=4: 69 KB CTAs, two (or, registers capped, three) per SM."""
@@ -121,29 +159,32 @@ def test_forward_plane_kernel_4_channels_per_cta(math_mode, monkeypatch, occ):
     _check_fft_pair(2, 24, 64, 64)
 
 
-def _check_fft_pair(b, c, h, w):
+def _check_fft_pair(b, c, h, w, split=False, residual=True):
     """ffcb_rfft2 / ffcb_irfft2 vs numpy (float64): forward spectrum, and the inverse of a NON-Hermitian
-    (ReLU'd) spectrum with the residual add — pow2 Stockham and direct-DFT sizes."""
+    (ReLU'd) spectrum with the residual add — pow2 Stockham and direct-DFT sizes.  ``split``: the formats of the
+    generator program (forward spectrum and inverse output stored as split bf16, 2^-16 per value)."""
     rng = np.random.default_rng(h * 1000 + w)
     x = rng.standard_normal((b, c, h, w)).astype(np.float32)
     wf = w // 2 + 1
-    prog = E.Program("fft_test", L.MATH_FP32)
-    X = prog.buf("x", b, h, w, c); S = prog.buf("s", b, h, wf, 2 * c)
-    Zin = prog.buf("z", b, h, wf, 2 * c); R = prog.buf("r", b, h, w, c); O = prog.buf("o", b, h, w, c)
+    prog = E.Program("fft_test", L.MATH_BF16X3 if split else L.MATH_FP32)
+    X = prog.buf("x", b, h, w, c); S = prog.buf("s", b, h, wf, 2 * c, gemm=split)
+    Zin = prog.buf("z", b, h, wf, 2 * c); R = prog.buf("r", b, h, w, c); O = prog.buf("o", b, h, w, c, gemm=split)
+    assert S.fmt == O.fmt == (L.BF16X2 if split else L.F32) and Zin.fmt == R.fmt == X.fmt == L.F32
     prog.inputs = {"x0": (b, c, h, w), "x1": (b, 2 * c, h, wf), "x2": (b, c, h, w)}
     prog.ops += [E.ToNHWC("x0", E.TV(X)), E.RfftOp(E.TV(X), E.TV(S)), E.ToNCHW(E.TV(S), "y0"),
                  E.ToNHWC("x1", E.TV(Zin)), E.ToNHWC("x2", E.TV(R)),
-                 E.IrfftOp(E.TV(Zin), E.TV(R), E.TV(O)), E.ToNCHW(E.TV(O), "y1")]
+                 E.IrfftOp(E.TV(Zin), E.TV(R) if residual else None, E.TV(O)), E.ToNCHW(E.TV(O), "y1")]
     prog.outputs = {"y0": (b, 2 * c, h, wf), "y1": (b, c, h, w)}
     z = np.maximum(rng.standard_normal((b, 2 * c, h, wf)), 0).astype(np.float32)
     res = rng.standard_normal((b, c, h, w)).astype(np.float32)
     out = _run_program(prog, {"x0": torch.from_numpy(x), "x1": torch.from_numpy(z), "x2": torch.from_numpy(res)})
+    tol = 2e-5 if split else 2e-6
     spec = onp.rfft2_ortho(x.astype(np.float64))
     want_s = np.stack((spec.real, spec.imag), axis=2).reshape(b, 2 * c, h, wf)
-    assert _rel_err(out["y0"].numpy(), want_s) < 2e-6
+    assert _rel_err(out["y0"].numpy(), want_s) < tol
     zc = z.astype(np.float64).reshape(b, c, 2, h, wf)
-    want_y = onp.irfft2_explicit(zc[:, :, 0] + 1j * zc[:, :, 1], h, w) + res
-    assert _rel_err(out["y1"].numpy(), want_y) < 2e-6
+    want_y = onp.irfft2_explicit(zc[:, :, 0] + 1j * zc[:, :, 1], h, w) + (res if residual else 0.0)
+    assert _rel_err(out["y1"].numpy(), want_y) < tol
 
 
 def test_fft_round_trip_full_size(math_mode):

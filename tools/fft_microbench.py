@@ -13,7 +13,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lama_b200 import _lib as L          # noqa: E402
 from lama_b200 import engine as E        # noqa: E402
 
-KNOBS = ("FFCB_FFT_MIXED_RADIX", "FFCB_FFT_PLANE_CH", "FFCB_FFT_PLANE_OCC", "FFCB_FFT_INV_PLANE", "FFCB_FFT_TWO_PASS")
+KNOBS = ("FFCB_FFT_MIXED_RADIX", "FFCB_FFT_PLANE_CH", "FFCB_FFT_PLANE_OCC", "FFCB_FFT_INV_PLANE", "FFCB_FFT_TWO_PASS",
+         "FFCB_FFT_PLANE_FWD")
 
 
 def time_ops(b, c, h, w, env, which, reps=10, spec_fmt_split=True, warm=3):
@@ -53,6 +54,12 @@ def time_ops(b, c, h, w, env, which, reps=10, spec_fmt_split=True, warm=3):
 
 if __name__ == "__main__":
     fu = (32, 192, 64, 64)
+    if "--v2" in sys.argv:               # first vs second revision of the plane kernels at the headline shape
+        for env in [{"FFCB_FFT_PLANE_FWD": "1"}, {"FFCB_FFT_PLANE_FWD": "2"}]:
+            print(json.dumps(time_ops(*fu, env, "fwd", reps=20)), flush=True)
+        for env in [{"FFCB_FFT_INV_PLANE": "0"}, {"FFCB_FFT_INV_PLANE": "2"}, {"FFCB_FFT_INV_PLANE": "3"}]:
+            print(json.dumps(time_ops(*fu, env, "inv", reps=20)), flush=True)
+        sys.exit(0)
     if "--fu-only" in sys.argv:          # the shipped configuration only (for an ncu capture)
         print(json.dumps(time_ops(*fu, {}, "fwd", reps=1, warm=0)), flush=True)
         print(json.dumps(time_ops(*fu, {}, "inv", reps=1, warm=0)), flush=True)
