@@ -390,8 +390,9 @@ bool inv_v2_eligible(const ffcb_tensor* spec, const ffcb_tensor* residual, const
   return vec_ok(out, out->fmt == FFCB_F32 ? 4 : 8);
 }
 
-// default: two-pass kernels (0) until the second-revision plane kernel (3) has been measured faster on the GPU
-constexpr int kDefaultInvPlaneVariant = 0;
+// default: the second-revision plane kernel (measured 135 us vs 160 us for the two-pass kernels at B=32, C=192,
+// profiles/r01_fft_microbench_v2.jsonl); 0 selects the two-pass kernels, which also take every view it cannot handle
+constexpr int kDefaultInvPlaneVariant = 3;
 int inv_plane_variant() {
   const char* e = getenv("FFCB_FFT_INV_PLANE");
   if (!e || e[0] < '0' || e[0] > '3') return kDefaultInvPlaneVariant;
