@@ -41,8 +41,10 @@ def get_activation(kind="tanh"):
 
 
 def _native_ok(*tensors) -> bool:
-    """Fast-path gate shared by all modules: CUDA fp32 tensors, inference, no autograd."""
-    if torch.is_grad_enabled():
+    """Fast-path gate shared by all modules: CUDA fp32 tensors, inference, no autograd.  Under ``torch.jit.trace``
+    (bin/to_jit.py:55-62) the modules run the reference's torch operator sequence instead, so that the exported
+    TorchScript is self-contained (a ctypes call is invisible to the tracer and would be baked in as a constant)."""
+    if torch.is_grad_enabled() or torch.jit.is_tracing():
         return False
     for t in tensors:
         if not torch.is_tensor(t):
@@ -53,7 +55,7 @@ def _native_ok(*tensors) -> bool:
 
 
 def _fallback(why: str):
-    if os.environ.get("LAMA_B200_STRICT") == "1":
+    if os.environ.get("LAMA_B200_STRICT") == "1" and not torch.jit.is_tracing():
         raise RuntimeError(f"lama_b200: native path unavailable ({why}) and LAMA_B200_STRICT=1")
 
 
