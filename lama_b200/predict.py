@@ -163,13 +163,21 @@ def list_dataset(indir: str, img_suffix: str = ".png") -> List[Tuple[str, str]]:
     return [(m.rsplit("_mask", 1)[0] + img_suffix, m) for m in masks]
 
 
+def shard_pairs(pairs: Sequence, rank: int, world: int) -> List:
+    """Files of one rank when several processes (one per GPU, e.g. under torchrun) share a directory: the path
+    shards by image, every rank writes its own outputs, no collective is needed.  Interleaved so
+    that sorted directories with size-ordered files still balance."""
+    assert 0 <= rank < world
+    return list(pairs[rank::world])
+
+
 def predict_directory(inpainter: BatchedInpainter, indir: str, outdir: str, img_suffix: str = ".png",
-                      out_ext: str = ".png", chunk: int = 256) -> int:
+                      out_ext: str = ".png", chunk: int = 256, rank: int = 0, world: int = 1) -> int:
     """bin/predict.py:63-95 for a whole directory: same file discovery and output naming, batched execution."""
     from PIL import Image
     if not indir.endswith("/"):
         indir += "/"
-    pairs = list_dataset(indir, img_suffix)
+    pairs = shard_pairs(list_dataset(indir, img_suffix), rank, world)
     for k in range(0, len(pairs), chunk):
         part = pairs[k:k + chunk]
         items = [(np.array(Image.open(i).convert("RGB")), np.array(Image.open(m).convert("L"))) for i, m in part]
@@ -191,10 +199,14 @@ def main(argv=None):
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--pad-mod", type=int, default=8)
     a = ap.parse_args(argv)
-    gen = load_generator(a.model_dir, a.checkpoint)
+    # one process per GPU (python -m torch.distributed.run --nproc-per-node N -m lama_b200.predict ...): every rank
+    # takes its share of the files; single-process runs see rank 0 of 1
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    device = f"cuda:{os.environ.get('LOCAL_RANK', '0')}"
+    gen = load_generator(a.model_dir, a.checkpoint, device=device)
     n = predict_directory(BatchedInpainter(gen, max_batch=a.batch, pad_mod=a.pad_mod), a.indir, a.outdir,
-                          a.img_suffix, a.out_ext)
-    print(f"inpainted {n} images -> {a.outdir}")
+                          a.img_suffix, a.out_ext, rank=rank, world=world)
+    print(f"[rank {rank}/{world}] inpainted {n} images -> {a.outdir}")
 
 
 if __name__ == "__main__":

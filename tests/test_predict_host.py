@@ -62,3 +62,11 @@ def test_inpaint_validates_items():
         inp.inpaint([(np.zeros((8, 8, 3), np.float32), np.zeros((8, 8), np.uint8))])
     with pytest.raises(ValueError):
         inp.inpaint([(np.zeros((8, 8, 3), np.uint8), np.zeros((8, 9), np.uint8))])
+
+
+def test_shard_pairs_partition_the_directory():
+    pairs = [(f"i{k}.png", f"i{k}_mask.png") for k in range(11)]
+    for world in (1, 2, 3, 8, 16):
+        parts = [PR.shard_pairs(pairs, r, world) for r in range(world)]
+        assert sorted(p for part in parts for p in part) == sorted(pairs)
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
