@@ -24,3 +24,15 @@ for math in ("bf16x3", "fp32"):
     del gen
 os.environ["LAMA_B200_MATH"] = "bf16x3"
 ge.smoke()
+
+# uint8 predict path (row f1) on a size whose planes have no compile-time FFT plan (row f2: 200x120 -> 25x15)
+import numpy as np  # noqa: E402
+from lama_b200.predict import BatchedInpainter  # noqa: E402
+from lama_b200.testing import small_lama_kwargs  # noqa: E402
+
+small = seeded_parameters_(M.FFCResNetGenerator(**small_lama_kwargs(ngf=8, n_blocks=2)).eval(), 1).to("cuda:0")
+rng = np.random.default_rng(0)
+imgs = rng.integers(0, 256, size=(3, 197, 118, 3), dtype=np.uint8)
+msks = (rng.random((3, 197, 118)) < 0.3).astype(np.uint8) * 255
+out = BatchedInpainter(small, max_batch=2)(imgs, msks)
+print("u8 predict", out.shape, out.dtype, int(out.mean()))
