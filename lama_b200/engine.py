@@ -887,6 +887,19 @@ def get_executor(module, kind: str, tensors, math: Optional[int] = None,
 def run_module(module, kind: str, tensors):
     """Execute ``module`` natively on NCHW float CUDA tensors; returns fresh tensors (or the int 0
     for an empty FFC side)."""
+    first = next(t for t in tensors if torch.is_tensor(t))
+    if first.shape[0] == 0:
+        # empty batch (the reference returns empty tensors of the right shape): nothing to launch; the output
+        # shapes come from the program of a one-image batch
+        shapes = tuple((1,) + tuple(t.shape[1:]) if torch.is_tensor(t) else None for t in tensors)
+        with torch.no_grad():
+            prog = build_module_program(module, kind, shapes, L.MATH_FP32)
+        outs = {k: torch.empty((0,) + tuple(v[1:]), dtype=prog.dtypes.get(k, torch.float32), device=first.device)
+                for k, v in prog.outputs.items()}
+        y0 = outs.get("y0", 0)
+        if kind in ("ffc_bn_act", "resnet_block"):
+            return y0, outs.get("y1", 0)
+        return (y0,)
     ex = get_executor(module, kind, tensors)
     feed = {}
     i = 0

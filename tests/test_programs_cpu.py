@@ -206,3 +206,19 @@ def test_generator_u8_program_matches_reference_predict_bytes():
     # the fp32 CUDA-core arm has no uint8 front / back end: asking for it is an error, not a silent detour
     with pytest.raises(ValueError):
         E.build_module_program(g, "generator_u8:8", (tuple(img.shape), tuple(mask.shape)), L.MATH_FP32)
+
+
+def test_empty_batch_returns_empty_outputs_without_launching():
+    """Empty batch -> empty outputs of the right shape: the native entry point takes the output shapes from the
+    program of a one-image batch and launches nothing (so this runs on the CPU box)."""
+    g = M.FFCResNetGenerator(**small_lama_kwargs(ngf=8, n_blocks=1)).eval()
+    (y,) = E.run_module(g, "generator", (torch.empty(0, 4, 64, 48),))
+    assert tuple(y.shape) == (0, 3, 64, 48) and y.dtype == torch.float32
+    m = M.FFC_BN_ACT(16, 32, 3, 0.5, 0.5, stride=2, padding=1, enable_lfu=False).eval()
+    yl, yg = E.run_module(m, "ffc_bn_act", (torch.empty(0, 8, 16, 16), torch.empty(0, 8, 16, 16)))
+    assert tuple(yl.shape) == (0, 16, 8, 8) and tuple(yg.shape) == (0, 16, 8, 8)
+    # (the torch composition itself cannot serve as the checker here: torch.fft on an empty batch raises an MKL
+    #  "inconsistent configuration" error on CPU — the reference has no defined behaviour for B = 0)
+    fu = M.FourierUnit(8, 8).eval()
+    (yf,) = E.run_module(fu, "fourier_unit", (torch.empty(0, 8, 16, 16),))
+    assert tuple(yf.shape) == (0, 8, 16, 16)
