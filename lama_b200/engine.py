@@ -649,8 +649,8 @@ class CudaExecutor:
         self.prog = prog
         self.device = device
         self.lib = L.get_lib()
-        L.check(self.lib.ffcb_check_device(device.index if device.index is not None else torch.cuda.current_device()),
-                "ffcb_check_device")
+        self.dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        L.check(self.lib.ffcb_check_device(self.dev_index), "ffcb_check_device")
         self.storage: Dict[str, torch.Tensor] = {}
         for b in prog.bufs:
             shape = (b.B, b.H + 2 * b.pad, b.W + 2 * b.pad, b.C)
@@ -792,6 +792,11 @@ class CudaExecutor:
     def run(self, inputs: Dict[str, torch.Tensor], stream: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """Issue every call on ``stream`` (default: torch's current stream).  Outputs are the
         executor's own tensors (overwritten by the next run)."""
+        if torch.cuda.current_device() != self.dev_index:
+            # the module lives on another GPU than the caller's current device (one process driving several GPUs):
+            # kernels must be launched with that device current, as torch's own ops do through their device guards
+            with torch.cuda.device(self.dev_index):
+                return self.run(inputs, stream)
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
         for name, slots in self.input_slots.items():
