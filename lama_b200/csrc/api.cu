@@ -125,10 +125,7 @@ void ffcb_shutdown(void) {}
 int ffcb_conv(const ffcb_conv_desc* d, ffcb_stream_t stream) {
   int rc = check_conv(d);
   if (rc) return rc;
-  if (d->math == FFCB_MATH_FP32) {
-    FFCB_REQUIRE(true, "");
-    return conv_simt(d, (cudaStream_t)stream);
-  }
+  if (d->math == FFCB_MATH_FP32) return conv_simt(d, (cudaStream_t)stream);
   if (d->math == FFCB_MATH_BF16X3) return conv_tc(d, (cudaStream_t)stream);
   set_error("conv: unknown math mode %d", d->math);
   return FFCB_EINVAL;
