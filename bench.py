@@ -371,7 +371,7 @@ def main():
     # multiply / concat, blend and x255 run inside the first / last kernels, PCIe carries 1 byte per sample.
     # Measured last and fenced: it is an extra reading, a failure here must not take the headline numbers down.
     u8_io = None
-    if args.io == "both" and math == L.MATH_BF16X3:
+    if args.io == "both" and math == L.MATH_BF16X3 and world == 1:   # single-GPU reading (no collectives in here)
         try:
             img_h = (x_host[:, :3].permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().pin_memory()
             msk_h = (x_host[:, 3] * 255).to(torch.uint8).contiguous().pin_memory()
