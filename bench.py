@@ -148,6 +148,62 @@ def _cpu_setup():
     return best
 
 
+def torch_cuda_baseline(dev, B, S, steps=5, warmup=3):
+    """The reference's own operator sequence (oracle/ffc_torch_cpu.py, bit-identical to ffc.py on CPU) run by torch
+    EAGER on this GPU — cuFFT / cuDNN / ATen, the stack the reference uses on CUDA — with cudnn.allow_tf32 True (the
+    torch default) and False.  Baseline leg only: nothing of lama_b200 runs here.
+    Returns {config: {"tf32": img/s or ms, "fp32": ...}}; timing: CUDA events, `warmup` + `steps` calls."""
+    import torch
+    from lama_b200 import modules as M
+    from lama_b200.testing import BIG_LAMA_KWARGS, seeded_parameters_, synthetic_image_mask, generator_input
+    from oracle import ffc_torch_cpu as otc
+    g = seeded_parameters_(M.FFCResNetGenerator(**BIG_LAMA_KWARGS).eval(), 0)
+    sd = {k: v.to(dev) for k, v in g.state_dict().items()}
+    del g
+    img, mask = synthetic_image_mask(B, S, 0)
+    x = generator_input(img, mask).to(dev)
+    h = S // 8
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    xl = torch.randn(8, 128, h, h, generator=gen).to(dev)
+    xg = torch.randn(8, 384, h, h, generator=gen).to(dev)
+    t = torch.randn(B, 192, h, h, generator=gen).to(dev)
+    x0 = torch.randn(1, 64, 256, 256, generator=gen).to(dev)
+    blk = "model.10."
+    fu = blk + "conv1.ffc.convg2g.fu."
+    sd0 = {"conv_layer.weight": torch.randn(128, 128, 1, 1, generator=gen).to(dev) * 0.09,
+           "bn.weight": torch.ones(128, device=dev), "bn.bias": torch.zeros(128, device=dev),
+           "bn.running_mean": torch.zeros(128, device=dev), "bn.running_var": torch.ones(128, device=dev)}
+    cases = {
+        "generator_bs%d_%d" % (B, S): (lambda: otc.ffc_resnet_generator(x, sd, **BIG_LAMA_KWARGS), B, "images/s"),
+        "resblock_bs8_%d" % S: (lambda: otc.ffc_resnet_block(xl, xg, sd, blk), None, "ms"),
+        "fourier_unit_B%d_C192_%dx%d" % (B, h, h): (lambda: otc.fourier_unit(t, sd, fu), None, "ms"),
+        "fourier_unit_1x64x256x256": (lambda: otc.fourier_unit(x0, sd0), None, "ms"),
+    }
+    out = {"stack": "torch %s eager (cuFFT/cuDNN/ATen), operator sequence of ffc.py (oracle/ffc_torch_cpu.py)" % torch.__version__}
+    keep = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for mode, tf32 in (("tf32", True), ("fp32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            for name, (fn, imgs, unit) in cases.items():
+                with torch.no_grad():
+                    for _ in range(warmup):
+                        fn()
+                    torch.cuda.synchronize(dev)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(steps):
+                        fn()
+                    e1.record()
+                    torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1) / steps
+                out.setdefault(name, {"unit": unit})[mode] = (imgs / (ms / 1e3)) if imgs else ms
+                torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = keep
+    return out
+
+
 def run_reference(args, rank, world, out):
     """Reference arm: the reference's CPU path (oracle torch-CPU port; the reference tree itself cannot
     travel to the GPU box) on all host threads.  Rank 0 only."""
@@ -197,6 +253,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-cuda-baseline", action="store_true",
+                    help="skip the torch-eager (cuFFT/cuDNN) reading of the same operator sequence on this GPU")
     ap.add_argument("--io", default=os.environ.get("LAMA_B200_BENCH_IO", "both"), choices=["f32", "both"],
                     help="both: also time the uint8 predict path (lama_b200.predict, SURVEY.md row f1) end to end")
     args = ap.parse_args()
@@ -367,6 +425,15 @@ def main():
                "sample": f"{n_img} images of 512x512 one at a time (bin/predict.py:74 batch size), torch-CPU port of "
                          f"the reference ops (oracle/ffc_torch_cpu.py), {cores} threads (calibrated)"}
 
+    # ---- the reference operator sequence under torch eager on this GPU (rank 0, N=1 only), TF32 on / off
+    tcb = None
+    if rank == 0 and world == 1 and not args.no_torch_cuda_baseline:
+        try:
+            tcb = torch_cuda_baseline(dev, B, S)
+        except Exception as ex_t:  # noqa: BLE001
+            tcb = {"error": f"{type(ex_t).__name__}: {ex_t}"[:300]}
+        torch.cuda.empty_cache()
+
     # ---- the same step through the uint8 predict path (row f1): decoded bytes in, inpainted bytes out; /255, mask
     # multiply / concat, blend and x255 run inside the first / last kernels, PCIe carries 1 byte per sample.
     # Measured last and fenced: it is an extra reading, a failure here must not take the headline numbers down.
@@ -419,7 +486,7 @@ def main():
                     "u8_io": u8_io},
             "gpu_launches": ex.launches_per_run * args.steps,
             "launches_per_step": ex.launches_per_run,
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "torch_cuda_baseline": tcb,
         }), file=out)
         out.flush()
     if world > 1:

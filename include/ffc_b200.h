@@ -22,6 +22,7 @@
  *    lives at ptr + b*sb + y*sy + x*sx + c.  Strides let one allocation hold a reflect-padded
  *    plane ([B][H+2][W+2][C], ptr at the interior origin) or a channel slice of a wider tensor
  *    (the local|global halves of an FFC feature map share one 512-channel buffer).
+ *    Tensors of the FourierUnit chain may instead be "channel-group planar" (ffcb_tensor.cg / .sg below).
  *  - storage formats: FFCB_F32 (float) and FFCB_BF16X2 ("split" bfloat16: value = hi + lo with
  *    hi = bf16(v), lo = bf16(v - hi); hi plane at ptr, lo plane at ptr + lo_off elements).
  *    The split format is what the tcgen05 path multiplies (3 bf16 products, fp32 accumulate:
@@ -37,7 +38,7 @@
 extern "C" {
 #endif
 
-#define FFCB_VERSION 100 /* 0.1.0 */
+#define FFCB_VERSION 110 /* 0.1.1: ffcb_tensor gained the channel-group fields sg / cg */
 
 enum {
   FFCB_OK = 0,
@@ -72,6 +73,13 @@ typedef struct {
   int32_t window;  /* != 0: "sliding window" view — consecutive pixels overlap (sx < C): pixel x exposes the C
                       contiguous elements starting at x*sx.  Used to feed the 7x7 stem to ffcb_conv as 7 K-segments
                       of (8 taps x 8 channels) read straight out of a packed NHWC8 image (see ffcb_stem_pack). */
+  int32_t cg;      /* 0: plain channels-last.  > 0: "channel-group planar" — channels are stored in groups of cg
+                      (4 or 8): element (b,y,x,c) lives at ptr + (c/cg)*sg + b*sb + y*sy + x*sx + (c%cg), i.e. every
+                      group of cg channels is its own dense little channels-last image.  This is the layout of the
+                      FourierUnit chain (SpectralTransform.conv1 -> rfft2 -> spectral conv -> irfft2 -> conv2,
+                      ffc.py:145-161): one (image, group) plane set is ONE contiguous block for the plane FFT kernels
+                      and the [K/8][pixel][8] "interleaved" (no-swizzle, K-major) operand tile of tcgen05.mma. */
+  int64_t sg;      /* stride between channel groups (elements); ignored when cg == 0 */
 } ffcb_tensor;
 
 /* One K-segment of an implicit-GEMM convolution: `nch` input channels starting at channel

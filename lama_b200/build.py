@@ -14,8 +14,9 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(HERE, "libffc_b200.so")
 STAMP = LIB_PATH + ".stamp"
+OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["api.cu", "fft.cu", "fft_plane.cu", "conv_simt.cu", "conv_tc.cu", "shell.cu"]
+SOURCES = ["api.cu", "fft.cu", "fft_plane.cu", "fft_plane_cg.cu", "conv_simt.cu", "conv_tc.cu", "shell.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "--expt-relaxed-constexpr",
@@ -30,15 +31,24 @@ def _nvcc():
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
-def _fingerprint():
+def _file_hash(paths):
     h = hashlib.sha256()
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "ffc_b200.h")]
-    for f in files:
+    for f in paths:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
+
+
+def _headers():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + [
+        os.path.join(INCLUDE, "ffc_b200.h")]
+
+
+def _fingerprint():
+    return _file_hash([os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] +
+                      [os.path.join(INCLUDE, "ffc_b200.h")])
 
 
 def is_current() -> bool:
@@ -48,16 +58,39 @@ def is_current() -> bool:
         return fh.read().strip() == _fingerprint()
 
 
+def _compile_one(src, verbose):
+    """One translation unit -> build/<name>.o, skipped when the source, the headers and the flags are unchanged."""
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+    tag = _file_hash([os.path.join(CSRC, src)] + _headers())
+    stamp = obj + ".stamp"
+    if os.path.isfile(obj) and os.path.isfile(stamp) and open(stamp).read().strip() == tag:
+        return obj, ""
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    proc = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src}:\n" + proc.stdout[-6000:])
+    with open(stamp, "w") as fh:
+        fh.write(tag)
+    return obj, proc.stdout
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the library if sources changed; returns its path."""
+    """Compile the library if sources changed (translation units in parallel, objects cached); returns its path."""
     if not force and is_current():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    if force and os.path.isdir(OBJ_DIR):
+        shutil.rmtree(OBJ_DIR)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(lambda s: _compile_one(s, verbose), SOURCES))
+    if verbose:
+        sys.stderr.write("".join(out for _o, out in results))
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + [o for o, _ in results]
     proc = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed building libffc_b200.so:\n" + proc.stdout[-4000:])
+        raise RuntimeError("nvcc failed linking libffc_b200.so:\n" + proc.stdout[-4000:])
     with open(STAMP, "w") as fh:
         fh.write(_fingerprint())
     return LIB_PATH

@@ -24,7 +24,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 void count_launch(int n) { g_launches += n; }
 
-int check_tensor(const ffcb_tensor* t, const char* name) {
+int check_tensor(const ffcb_tensor* t, const char* name, bool allow_cg) {
   FFCB_REQUIRE(t != nullptr, "%s: null tensor descriptor", name);
   FFCB_REQUIRE(t->B >= 0 && t->H >= 0 && t->W >= 0 && t->C >= 0, "%s: negative extent", name);
   if ((long long)t->B * t->H * t->W * t->C == 0) return FFCB_OK;
@@ -37,11 +37,18 @@ int check_tensor(const ffcb_tensor* t, const char* name) {
   FFCB_REQUIRE(((uintptr_t)t->ptr % align) == 0, "%s: pointer %p not %zu-byte aligned", name, t->ptr, (size_t)align);
   FFCB_REQUIRE(t->sx % 4 == 0 && t->sy % 4 == 0 && t->sb % 4 == 0, "%s: strides must be multiples of 4 elements",
                name);
-  FFCB_REQUIRE(t->sx >= t->C || t->window, "%s: pixel stride %lld < C=%d (only window views may overlap)", name,
-               (long long)t->sx, t->C);
+  FFCB_REQUIRE(t->sx >= t->C || t->window || t->cg, "%s: pixel stride %lld < C=%d (only window views may overlap)",
+               name, (long long)t->sx, t->C);
   if (t->fmt == FFCB_BF16X2)
     FFCB_REQUIRE(t->lo_off % 4 == 0 && t->lo_off != 0, "%s: lo_off must be a non-zero multiple of 4", name);
   FFCB_REQUIRE(t->pad >= 0 && t->pad <= 3, "%s: pad must be in [0,3]", name);
+  if (t->cg != 0) {
+    FFCB_REQUIRE(allow_cg, "%s: channel-group planar views (cg=%d) are not accepted by this entry point", name, t->cg);
+    FFCB_REQUIRE((t->cg == 4 || t->cg == 8) && t->C % t->cg == 0, "%s: cg=%d must be 4 or 8 and divide C=%d", name,
+                 t->cg, t->C);
+    FFCB_REQUIRE(t->sx >= t->cg && t->sg % 4 == 0 && t->sg > 0 && !t->window && t->pad == 0,
+                 "%s: bad channel-group strides (sx=%lld, sg=%lld)", name, (long long)t->sx, (long long)t->sg);
+  }
   (void)esz;
   return FFCB_OK;
 }
@@ -66,8 +73,9 @@ int head_gather7_blend_u8(const ffcb_tensor*, const float*, int, const uint8_t*,
 static int check_conv(const ffcb_conv_desc* d) {
   FFCB_REQUIRE(d != nullptr, "conv: null descriptor");
   int rc;
-  if ((rc = check_tensor(&d->in[0], "conv.in[0]"))) return rc;
-  if ((rc = check_tensor(&d->out, "conv.out"))) return rc;
+  const bool tc = d->math == FFCB_MATH_BF16X3;     // only the tcgen05 arm understands channel-group planar views
+  if ((rc = check_tensor(&d->in[0], "conv.in[0]", tc))) return rc;
+  if ((rc = check_tensor(&d->out, "conv.out", tc))) return rc;
   FFCB_REQUIRE(d->weight != nullptr, "conv: null weight");
   FFCB_REQUIRE(d->n_out > 0 && d->n_out % 4 == 0, "conv: n_out=%d must be a positive multiple of 4", d->n_out);
   FFCB_REQUIRE(d->out.C == d->n_out, "conv: out view has C=%d, n_out=%d", d->out.C, d->n_out);
@@ -92,7 +100,7 @@ static int check_conv(const ffcb_conv_desc* d) {
                    "conv: seg %d tap (%d,%d) reaches beyond one reflection of a %dx%d input", i, s.dy, s.dx, t.H, t.W);
     }
   }
-  if (uses1 && (rc = check_tensor(&d->in[1], "conv.in[1]"))) return rc;
+  if (uses1 && (rc = check_tensor(&d->in[1], "conv.in[1]", tc))) return rc;
   if (d->addend.ptr != nullptr) {
     if ((rc = check_tensor(&d->addend, "conv.addend"))) return rc;
     FFCB_REQUIRE(d->addend.B == d->out.B && d->addend.H == d->out.H && d->addend.W == d->out.W &&

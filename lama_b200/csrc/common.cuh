@@ -37,9 +37,9 @@ void count_launch(int n = 1);
 // ---------------------------------------------------------------- device view of ffcb_tensor
 struct View {
   char* ptr;
-  long long sb, sy, sx, lo_off;
+  long long sb, sy, sx, lo_off, sg;
   int B, H, W, C;
-  int fmt, pad, reflect_border;
+  int fmt, pad, reflect_border, cg;
 };
 
 inline View make_view(const ffcb_tensor& t) {
@@ -48,6 +48,7 @@ inline View make_view(const ffcb_tensor& t) {
   v.sb = t.sb; v.sy = t.sy; v.sx = t.sx; v.lo_off = t.lo_off;
   v.B = t.B; v.H = t.H; v.W = t.W; v.C = t.C;
   v.fmt = t.fmt; v.pad = t.pad; v.reflect_border = t.reflect_border;
+  v.cg = t.cg; v.sg = t.cg ? t.sg : 0;
   return v;
 }
 
@@ -57,11 +58,17 @@ inline View null_view() {
   return v;
 }
 
-// Validation shared by entry points: 4-channel vector access everywhere.
-int check_tensor(const ffcb_tensor* t, const char* name);
+// Validation shared by entry points: 4-channel vector access everywhere.  Channel-group planar views (cg != 0) are
+// only accepted where `allow_cg` says so (the FourierUnit chain: ffcb_conv's tcgen05 arm and the plane FFT kernels).
+int check_tensor(const ffcb_tensor* t, const char* name, bool allow_cg = false);
 
 __host__ __device__ __forceinline__ long long pix_off(const View& v, int b, int y, int x) {
   return (long long)b * v.sb + (long long)y * v.sy + (long long)x * v.sx;
+}
+
+// element offset of channel c inside a pixel: c for channels-last views, (c / cg) * sg + c % cg for channel-group planar
+__host__ __device__ __forceinline__ long long chan_off(const View& v, int c) {
+  return v.cg ? (long long)(c / v.cg) * v.sg + (c % v.cg) : (long long)c;
 }
 
 // reflect without edge repeat: -1 -> 1, n -> n-2 (valid for |overshoot| < n)

@@ -50,6 +50,15 @@ struct TcParams {
   int coord_off[2];          // +1 when in[src] is mapped with its border ring
   int obw, obh;              // epilogue store box of one warp: obw x obh pixels (obw*obh == 32)
   int nseg;
+  // channel-group planar ("interleaved") A operands: in[src] stored [C/8][B][H][W][8] per plane (ffcb_tensor.cg == 8).
+  // Their K block is loaded as eight [128 pixels][16 B] slabs with 1-D bulk copies and multiplied through a
+  // no-swizzle K-major descriptor (core matrix = 8 pixels x 16 B; SBO 128 B, LBO 2048 B).
+  int a_il[2];
+  const unsigned short* a_ptr[2];
+  long long a_sg[2], a_sb[2], a_sy[2], a_lo[2];
+  int a_H[2], a_W[2];
+  long long m_total;         // flat mode: B*H*W
+  int desc_swap;             // bring-up: exchange LBO / SBO of the no-swizzle descriptor (FFCB_TC_DESC_SWAP)
   int debug;                 // bring-up knobs (FFCB_TC_DEBUG): 1 no global ld/st in epilogue, 2 no epilogue work,
                              // 4 no MMA issue, 8 no activation loads
   ffcb_kseg seg[FFCB_MAX_KSEG];
@@ -107,6 +116,12 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes: multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -123,6 +138,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset, bits [32,46)
   d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
   d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+  return d;
+}
+
+// K-major, NO swizzle ("interleaved"): the tile is [K/8][128 rows][8 bf16]; a core matrix is 8 rows x 16 B = 128
+// contiguous bytes, 8-row groups follow each other every 128 B (SBO) and the two 16-byte K chunks of one UMMA_K = 16
+// step are one slab = 2048 B apart (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t saddr, int swap) {
+  const uint64_t lbo = swap ? 128 : 2048, sbo = swap ? 2048 : 128;
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (lbo >> 4) << 16;
+  d |= (sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
   return d;
 }
 
@@ -292,9 +320,41 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* st = smem + (size_t)stage * stage_bytes;
             const bool skip_a = (p.debug & 8) != 0;
-            mbar_expect_tx(&full[stage], (uint32_t)(skip_a ? 2 * w_bytes : stage_bytes));
+            if (skip_a || !p.a_il[g.src]) mbar_expect_tx(&full[stage], (uint32_t)(skip_a ? 2 * w_bytes : stage_bytes));
             const int cc = g.c0 + j * BK;
             if (skip_a) {
+            } else if (p.a_il[g.src]) {
+              // eight channel-group slabs per plane; rows of the tile are contiguous pixels of the group image
+              const int s = g.src;
+              uint32_t a_bytes = 0;
+              if (p.flat) {
+                const long long left = p.m_total - tc.m0;
+                const uint32_t bytes = (uint32_t)(left < BM ? left : BM) * 16u;
+                a_bytes = 16u * bytes;
+                mbar_expect_tx(&full[stage], a_bytes + 2u * (uint32_t)w_bytes);
+                const unsigned short* src = p.a_ptr[s] + (long long)(cc >> 3) * p.a_sg[s] + tc.m0 * 8;
+#pragma unroll 1
+                for (int kg = 0; kg < 8; ++kg) {
+                  bulk_load(st + kg * 2048, src + kg * p.a_sg[s], bytes, &full[stage]);
+                  bulk_load(st + kTileABytes + kg * 2048, src + kg * p.a_sg[s] + p.a_lo[s], bytes, &full[stage]);
+                }
+              } else {
+                const int x0 = tc.x0, nx = (p.a_W[s] - x0 < p.TW ? p.a_W[s] - x0 : p.TW);
+                int rows = p.a_H[s] - tc.y0;
+                rows = rows < p.TH ? rows : p.TH;
+                const uint32_t bytes = (uint32_t)nx * 16u;
+                a_bytes = 16u * bytes * (uint32_t)rows;
+                mbar_expect_tx(&full[stage], a_bytes + 2u * (uint32_t)w_bytes);
+                const unsigned short* src = p.a_ptr[s] + (long long)(cc >> 3) * p.a_sg[s] + (long long)tc.b * p.a_sb[s] +
+                                            (long long)tc.y0 * p.a_sy[s] + x0 * 8;
+#pragma unroll 1
+                for (int kg = 0; kg < 8; ++kg)
+                  for (int r = 0; r < rows; ++r) {
+                    const unsigned short* q = src + kg * p.a_sg[s] + r * p.a_sy[s];
+                    bulk_load(st + kg * 2048 + r * p.TW * 16, q, bytes, &full[stage]);
+                    bulk_load(st + kTileABytes + kg * 2048 + r * p.TW * 16, q + p.a_lo[s], bytes, &full[stage]);
+                  }
+              }
             } else if (p.flat) {
               tma_load_3d(st, map, &full[stage], cc, (int)tc.m0, 0);
               tma_load_3d(st + kTileABytes, map, &full[stage], cc, (int)tc.m0, 1);
@@ -321,24 +381,32 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
-        for (int kb = 0; kb < total_kblocks; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t a_hi = make_smem_desc(st);
-          const uint64_t a_lo = make_smem_desc(st + kTileABytes);
-          const uint64_t w_hi = make_smem_desc(st + 2 * kTileABytes);
-          const uint64_t w_lo = make_smem_desc(st + 2 * kTileABytes + w_bytes);
+        int kb = 0;
+        for (int sgi = 0; sgi < p.nseg; ++sgi) {
+          const int il = p.a_il[p.seg[sgi].src];
+          const int nblk = (p.seg[sgi].nch + BK - 1) / BK;
+          for (int j = 0; j < nblk; ++j, ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint64_t a_hi = il ? make_smem_desc_nosw(st, p.desc_swap) : make_smem_desc(st);
+            const uint64_t a_lo = il ? make_smem_desc_nosw(st + kTileABytes, p.desc_swap) : make_smem_desc(st + kTileABytes);
+            const uint64_t w_hi = make_smem_desc(st + 2 * kTileABytes);
+            const uint64_t w_lo = make_smem_desc(st + 2 * kTileABytes + w_bytes);
+            // per UMMA_K = 16 step: +32 B inside the swizzle row, or two 2048-byte slabs of the interleaved tile
+            const uint64_t a_step = il ? (uint64_t)(4096 >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
 #pragma unroll
-          for (int k = 0; k < ((p.debug & 4) ? 0 : BK / UMMA_K); ++k) {
-            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per UMMA_K inside the swizzle row
-            umma_bf16(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
-            umma_bf16(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
-            umma_bf16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+            for (int k = 0; k < ((p.debug & 4) ? 0 : BK / UMMA_K); ++k) {
+              const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+              const uint64_t aadv = (uint64_t)k * a_step;
+              umma_bf16(d_tmem, a_hi + aadv, w_hi + adv, idesc, (kb | k) != 0);
+              umma_bf16(d_tmem, a_lo + aadv, w_hi + adv, idesc, 1);
+              umma_bf16(d_tmem, a_hi + aadv, w_lo + adv, idesc, 1);
+            }
+            umma_commit(&empty[stage]);                 // smem stage reusable once these MMAs retire
+            if (kb == total_kblocks - 1) umma_commit(&acc_full[acc]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty[stage]);                 // smem stage reusable once these MMAs retire
-          if (kb == total_kblocks - 1) umma_commit(&acc_full[acc]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
@@ -424,6 +492,21 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         if (p.addend_post) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += ad[j];
+        }
+        if (p.out.cg != 0) {
+          // channel-group planar float32 output (FourierUnit chain): the lane's pixel is contiguous with its
+          // neighbours' inside every channel group, so plain 16-byte stores are whole lines — no staging tile
+          if (valid && !(p.debug & 1)) {
+            float* ob = reinterpret_cast<float*>(p.out.ptr) + pix_off(p.out, b, y, x);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int n = n0 + 4 * q;
+              if (n < p.N)
+                *reinterpret_cast<float4*>(ob + (long long)(n / p.out.cg) * p.out.sg + (n % p.out.cg)) =
+                    make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          }
+          continue;
         }
         // the previous TMA store of this warp must have finished reading the staging tile
         if (lane == 0) tma_store_wait_read();
@@ -553,6 +636,15 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     if (!used[s]) continue;
     const ffcb_tensor& t = d->in[s];
     FFCB_REQUIRE(t.fmt == FFCB_BF16X2, "conv(tc): in[%d] must be split bf16 (FFCB_BF16X2)", s);
+    if (t.cg != 0) {
+      // interleaved operand: 1x1 taps at unit stride only, whole 64-channel K blocks, dense group images
+      FFCB_REQUIRE(t.cg == 8 && !taps[s] && d->stride == 1 && t.sx == 8 && t.H == d->out.H && t.W == d->out.W,
+                   "conv(tc): channel-group planar in[%d] needs cg=8, dense pixels, 1x1 taps and stride 1", s);
+      for (int i = 0; i < d->nseg; ++i)
+        if (d->seg[i].src == s)
+          FFCB_REQUIRE(d->seg[i].nch % 64 == 0 && d->seg[i].c0 % 8 == 0,
+                       "conv(tc): segment %d of a channel-group planar input must cover whole 64-channel blocks", i);
+    }
     FFCB_REQUIRE(t.sx % 8 == 0 && t.sy % 8 == 0 && t.sb % 8 == 0 && t.lo_off % 8 == 0 && ((uintptr_t)t.ptr % 16) == 0,
                  "conv(tc): in[%d] strides / pointer not 16-byte aligned", s);
     if (taps[s] && d->border == FFCB_BORDER_REFLECT)
@@ -562,6 +654,13 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
 
   TcParams p;
   p.out = make_view(d->out);
+  if (d->out.cg != 0)
+    FFCB_REQUIRE(d->out.fmt == FFCB_F32 && d->out.sx % 4 == 0 && d->out.sy % 4 == 0 && d->out.sb % 4 == 0,
+                 "conv(tc): channel-group planar outputs are float32");
+  {
+    const char* sw = getenv("FFCB_TC_DESC_SWAP");
+    p.desc_swap = sw ? atoi(sw) : 0;
+  }
   p.addend = d->addend.ptr ? make_view(d->addend) : null_view();
   p.shift = d->shift;
   p.N = d->n_out; p.act = d->act; p.addend_post = d->addend_post;
@@ -587,8 +686,20 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     const ffcb_tensor& t = d->in[s];
     flat = t.H == H && t.W == W && t.sy == (int64_t)W * t.sx && t.sb == (int64_t)H * t.sy;
   }
+  for (int s = 0; s < 2; ++s) {
+    p.a_il[s] = 0; p.a_ptr[s] = nullptr; p.a_sg[s] = p.a_sb[s] = p.a_sy[s] = p.a_lo[s] = 0; p.a_H[s] = p.a_W[s] = 0;
+    if (!used[s] || d->in[s].cg == 0) continue;
+    const ffcb_tensor& t = d->in[s];
+    p.a_il[s] = 1;
+    p.a_ptr[s] = reinterpret_cast<const unsigned short*>(t.ptr);
+    p.a_sg[s] = t.sg; p.a_sb[s] = t.sb; p.a_sy[s] = t.sy; p.a_lo[s] = t.lo_off;
+    p.a_H[s] = t.H; p.a_W[s] = t.W;
+    FFCB_REQUIRE(t.sg % 8 == 0 && t.sb % 8 == 0 && t.sy % 8 == 0 && t.lo_off % 8 == 0,
+                 "conv(tc): channel-group planar in[%d] strides not 16-byte aligned", s);
+  }
+  p.m_total = (long long)d->out.B * H * W;
   // the epilogue stores 32-pixel boxes through a tensor map: a flattened pixel axis needs a dense output too
-  flat = flat && d->out.sy == (int64_t)W * d->out.sx && d->out.sb == (int64_t)H * d->out.sy;
+  flat = flat && (d->out.cg != 0 || (d->out.sy == (int64_t)W * d->out.sx && d->out.sb == (int64_t)H * d->out.sy));
   p.flat = flat ? 1 : 0;
   if (flat) {
     p.TW = BM; p.TH = 1; p.tiles_x = p.tiles_y = 1;
@@ -610,7 +721,7 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   alignas(64) CUtensorMap maps[4];
   int rc;
   for (int s = 0; s < 2; ++s) {
-    if (!used[s]) { maps[s] = maps[0]; p.coord_off[s] = 0; continue; }
+    if (!used[s] || p.a_il[s]) { p.coord_off[s] = 0; continue; }     // no tensor map: patched with a valid one below
     const ffcb_tensor& t = d->in[s];
     const cuuint64_t esz = 2;
     if (flat) {
@@ -633,7 +744,6 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
       if ((rc = encode(&maps[s], base, 5, dims, str, box, es, "spatial activations"))) return rc;
     }
   }
-  if (!used[0]) maps[0] = maps[1];
   {
     cuuint64_t dims[3] = {(cuuint64_t)kpad, (cuuint64_t)d->n_out, 2};
     cuuint64_t str[2] = {(cuuint64_t)kpad * 2, (cuuint64_t)kpad * d->n_out * 2};
@@ -642,7 +752,11 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     if ((rc = encode(&maps[2], const_cast<void*>(d->weight), 3, dims, str, box, es, "weights"))) return rc;
   }
 
-  {
+  for (int s = 0; s < 2; ++s)
+    if (!used[s] || p.a_il[s]) maps[s] = maps[2];      // never dereferenced by the kernel, but prefetched
+  if (d->out.cg != 0) {
+    maps[3] = maps[2];                                   // planar outputs are stored with plain vector stores
+  } else {
     // output: fp32 rows of 128 B (SWIZZLE_128B) or split bf16 rows of 64 B per plane (SWIZZLE_64B)
     const ffcb_tensor& t = d->out;
     const bool split = t.fmt == FFCB_BF16X2;

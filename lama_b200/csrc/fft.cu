@@ -365,6 +365,11 @@ bool plane64_eligible(const ffcb_tensor* real);
 int rfft2_plane64(const ffcb_tensor* in, const ffcb_tensor* spec, cudaStream_t stream);
 int irfft2_plane64(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out, cudaStream_t stream);
 int inv_plane_variant();
+// channel-group planar plane kernels (fft_plane_cg.cu)
+bool plane64_cg_fwd_eligible(const ffcb_tensor* in, const ffcb_tensor* spec);
+bool plane64_cg_inv_eligible(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out);
+int rfft2_plane64_cg(const ffcb_tensor* in, const ffcb_tensor* spec, cudaStream_t stream);
+int irfft2_plane64_cg(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out, cudaStream_t stream);
 
 size_t fft2_workspace_bytes(int B, int H, int W, int C) {
   return sizeof(float2) * (size_t)B * H * (W / 2 + 1) * C;
@@ -372,13 +377,18 @@ size_t fft2_workspace_bytes(int B, int H, int W, int C) {
 
 int rfft2(const ffcb_tensor* in, const ffcb_tensor* spec, void* ws, size_t ws_bytes, cudaStream_t stream) {
   int rc;
-  if ((rc = check_tensor(in, "rfft2.in")) || (rc = check_tensor(spec, "rfft2.spec"))) return rc;
+  if ((rc = check_tensor(in, "rfft2.in", true)) || (rc = check_tensor(spec, "rfft2.spec", true))) return rc;
   if ((rc = check_fft_shapes(in, spec, "rfft2"))) return rc;
   if (ws_bytes < fft2_workspace_bytes(in->B, in->H, in->W, in->C)) {
     set_error("rfft2: workspace %zu < %zu bytes", ws_bytes, fft2_workspace_bytes(in->B, in->H, in->W, in->C));
     return FFCB_ENOMEM;
   }
   if (in->B == 0 || in->C == 0) return FFCB_OK;
+  if (in->cg != 0 || spec->cg != 0) {
+    FFCB_REQUIRE(plane64_cg_fwd_eligible(in, spec),
+                 "rfft2: channel-group planar views need a 64x64 float32 cg=4 input and a split-bf16 cg=8 spectrum");
+    return rfft2_plane64_cg(in, spec, stream);
+  }
   if (plane64_eligible(in) && !getenv("FFCB_FFT_TWO_PASS")) return rfft2_plane64(in, spec, stream);
   const View vin = make_view(*in), vspec = make_view(*spec);
   float2* w2 = reinterpret_cast<float2*>(ws);
@@ -410,11 +420,11 @@ int rfft2(const ffcb_tensor* in, const ffcb_tensor* spec, void* ws, size_t ws_by
 int irfft2(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out, void* ws, size_t ws_bytes,
            cudaStream_t stream) {
   int rc;
-  if ((rc = check_tensor(spec, "irfft2.spec")) || (rc = check_tensor(out, "irfft2.out"))) return rc;
+  if ((rc = check_tensor(spec, "irfft2.spec", true)) || (rc = check_tensor(out, "irfft2.out", true))) return rc;
   if ((rc = check_fft_shapes(out, spec, "irfft2"))) return rc;
   View vres = null_view();
   if (residual != nullptr && residual->ptr != nullptr) {
-    if ((rc = check_tensor(residual, "irfft2.residual"))) return rc;
+    if ((rc = check_tensor(residual, "irfft2.residual", true))) return rc;
     FFCB_REQUIRE(residual->B == out->B && residual->H == out->H && residual->W == out->W && residual->C == out->C,
                  "irfft2: residual shape differs from output");
     vres = make_view(*residual);
@@ -424,6 +434,12 @@ int irfft2(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tens
     return FFCB_ENOMEM;
   }
   if (out->B == 0 || out->C == 0) return FFCB_OK;
+  if (spec->cg != 0 || out->cg != 0 || (residual && residual->ptr && residual->cg != 0)) {
+    FFCB_REQUIRE(plane64_cg_inv_eligible(spec, residual, out),
+                 "irfft2: channel-group planar views need a 64x64 plane, a float32 cg=8 spectrum, a float32 cg=4 "
+                 "residual and a split-bf16 cg=8 or float32 cg=4 output");
+    return irfft2_plane64_cg(spec, residual, out, stream);
+  }
   // FFCB_FFT_INV_PLANE: 0 = two-pass kernels, 1 / 2 = first-revision plane kernels (slower than two-pass),
   // 3 = second revision; irfft2_plane64 returns 1 when the chosen variant does not apply to these views
   if (plane64_eligible(out) && inv_plane_variant() != 0 && !getenv("FFCB_FFT_TWO_PASS")) {

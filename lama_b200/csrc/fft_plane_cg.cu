@@ -1,0 +1,217 @@
+// 64x64 plane FFT pair on channel-group planar tensors (include/ffc_b200.h: ffcb_tensor.cg) — the FourierUnit of the
+// 512x512 bottleneck, second generation.
+//
+// Round 1's plane kernels (fft_plane.cu) work on channels-last tensors: one 137 KB CTA per SM transforms 8 channels,
+// its load -> rows -> columns -> store phases run back to back and nothing overlaps them (ncu: 22% of DRAM bandwidth,
+// 13% warps active).  Here every tensor of the chain is stored in groups of 4 complex / 4 real channels
+// ([group][image][y][x][channels]), so one (image, group) plane set is ONE dense 64 KB block:
+//   * a CTA is 128 threads and 64 KB of shared memory, three CTAs share an SM and hide each other's load / store
+//     phases (12 warps per SM instead of 9 in one block);
+//   * every global access is a whole 128-byte line: 16-byte cp.async / LDG.128 with lanes along x (real planes),
+//     8 channels x 8 consecutive kx for the spectra, 8-byte half-pixels of the interleaved GEMM operand `u`;
+//   * both passes run IN PLACE in the 64 KB block (fft_plane_cg.cuh), conflict-free through XOR swizzles.
+// Formats:  forward  in  F32  cg=4  ->  spec BF16X2 cg=8 (operand of the spectral 1x1 GEMM, interleaved K groups)
+//           inverse  spec F32 cg=8  (+ residual F32 cg=4)  ->  out BF16X2 cg=8 (operand of conv2)  or  F32 cg=4
+#include <stdint.h>
+
+#include "common.cuh"
+#include "fft_plane_cg.cuh"
+
+namespace ffcb {
+namespace {
+
+using namespace fftc;
+
+struct CgArgs {
+  // element strides of each tensor for this launch (group stride, image stride, row stride, pixel stride)
+  const float* in;  long long in_sg, in_sb;  unsigned in_sy, in_sx;       // real input / residual (F32, cg 4)
+  void* spec;       long long sp_sg, sp_sb;  unsigned sp_sy, sp_sx; long long sp_lo;   // spectrum (cg 8)
+  void* out;        long long out_sg, out_sb; unsigned out_sy, out_sx; long long out_lo;
+  float scale;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// hi / lo bf16 pairs of a complex value (round to nearest even, lo = bf16(v - hi))
+__device__ __forceinline__ void split_pair(float a, float b, unsigned& hi, unsigned& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const unsigned*>(&h);
+  lo = *reinterpret_cast<const unsigned*>(&l);
+}
+
+// grid: (C/4, B).  blockIdx.x = 4-channel group of the real input = 8-channel (4 complex) group of the spectrum.
+__global__ void __launch_bounds__(kCgThreads, 3) rfft2_plane64_cg_kernel(CgArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float2* S = reinterpret_cast<float2*>(smem);
+  const int tid = threadIdx.x;
+  {   // plane set -> shared memory (real layout), 16 bytes per pixel, lanes along x
+    const float* src = a.in + (long long)blockIdx.x * a.in_sg + (long long)blockIdx.y * a.in_sb;
+    const uint32_t base = smem_addr(smem);
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      int y, x;
+      cg_pixel_slot(tid, i, y, x);
+      cp_async16(base + 4u * (unsigned)cg_real_idx(y, x, 0), src + ((unsigned)y * a.in_sy + (unsigned)x * a.in_sx));
+    }
+    cp_async_wait_all();
+  }
+  __syncthreads();
+  cg_fwd_rows(
+      tid, [&](int i) { return *reinterpret_cast<const float2*>(smem + i); }, [&]() { __syncwarp(); },
+      [&](int i2, float4 v) { *reinterpret_cast<float4*>(S + i2) = v; });
+  __syncthreads();
+  {
+    unsigned short* hi = reinterpret_cast<unsigned short*>(a.spec) + (long long)blockIdx.x * a.sp_sg +
+                         (long long)blockIdx.y * a.sp_sb;
+    unsigned short* lo = hi + a.sp_lo;
+    const float scale = a.scale;
+    cg_fwd_cols(
+        tid, [&](int i2) { return S[i2]; },
+        [&](int ky, int kx, int c, float2 z) {
+          const unsigned o = (unsigned)ky * a.sp_sy + (unsigned)kx * a.sp_sx + 2u * (unsigned)c;
+          unsigned h, l;
+          split_pair(z.x * scale, z.y * scale, h, l);
+          *reinterpret_cast<unsigned*>(hi + o) = h;
+          *reinterpret_cast<unsigned*>(lo + o) = l;
+        });
+  }
+}
+
+// grid: (C/4, B) over the REAL output's 4-channel groups; spectrum group = blockIdx.x (4 complex = 8 floats).
+template <bool HAS_RES, bool OUT_SPLIT>
+__global__ void __launch_bounds__(kCgThreads, 3) irfft2_plane64_cg_kernel(CgArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float2* S = reinterpret_cast<float2*>(smem);
+  const int tid = threadIdx.x;
+  {
+    const float* sp = reinterpret_cast<const float*>(a.spec) + (long long)blockIdx.x * a.sp_sg +
+                      (long long)blockIdx.y * a.sp_sb + 2 * (tid & 3);
+    cg_inv_cols(
+        tid,
+        [&](int ky, int kx) {
+          return __ldg(reinterpret_cast<const float2*>(sp + ((unsigned)ky * a.sp_sy + (unsigned)kx * a.sp_sx)));
+        },
+        [&](int i2, float2 z) { S[i2] = z; });
+  }
+  __syncthreads();
+  cg_inv_rows(
+      tid, [&](int i2) { return *reinterpret_cast<const float4*>(S + i2); }, [&]() { __syncwarp(); },
+      [&](int i, float2 z) { *reinterpret_cast<float2*>(smem + i) = z; });
+  __syncthreads();
+  {   // epilogue: whole pixels (4 channels), lanes along x: + residual, scale, convert, store
+    const float* res = HAS_RES ? a.in + (long long)blockIdx.x * a.in_sg + (long long)blockIdx.y * a.in_sb : nullptr;
+    const float scale = a.scale;
+#pragma unroll 4
+    for (int i0 = 0; i0 < 32; i0 += 8) {
+      float4 q[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int y, x;
+        cg_pixel_slot(tid, i0 + j, y, x);
+        q[j] = HAS_RES ? __ldg(reinterpret_cast<const float4*>(res + ((unsigned)y * a.in_sy + (unsigned)x * a.in_sx)))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int y, x;
+        cg_pixel_slot(tid, i0 + j, y, x);
+        const float4 v = *reinterpret_cast<const float4*>(smem + cg_real_idx(y, x, 0));
+        const float r0 = fmaf(v.x, scale, q[j].x), r1 = fmaf(v.y, scale, q[j].y);
+        const float r2 = fmaf(v.z, scale, q[j].z), r3 = fmaf(v.w, scale, q[j].w);
+        if constexpr (OUT_SPLIT) {
+          // out is cg = 8: this CTA's four channels are one half (8 bytes per plane) of the 16-byte pixel granule
+          unsigned short* hi = reinterpret_cast<unsigned short*>(a.out) + (long long)(blockIdx.x >> 1) * a.out_sg +
+                               (long long)blockIdx.y * a.out_sb + 4 * (blockIdx.x & 1);
+          const unsigned o = (unsigned)y * a.out_sy + (unsigned)x * a.out_sx;
+          unsigned h0, l0, h1, l1;
+          split_pair(r0, r1, h0, l0);
+          split_pair(r2, r3, h1, l1);
+          *reinterpret_cast<uint2*>(hi + o) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(hi + a.out_lo + o) = make_uint2(l0, l1);
+        } else {
+          float* op = reinterpret_cast<float*>(a.out) + (long long)blockIdx.x * a.out_sg +
+                      (long long)blockIdx.y * a.out_sb + ((unsigned)y * a.out_sy + (unsigned)x * a.out_sx);
+          *reinterpret_cast<float4*>(op) = make_float4(r0, r1, r2, r3);
+        }
+      }
+    }
+  }
+}
+
+bool offsets_fit(const ffcb_tensor* t) { return t->sy > 0 && t->sx > 0 && 64 * t->sy + 64 * t->sx < (1LL << 31); }
+
+bool real_cg4(const ffcb_tensor* t) {
+  return t->cg == 4 && t->fmt == FFCB_F32 && t->H == 64 && t->W == 64 && t->sx % 4 == 0 && t->sy % 4 == 0 &&
+         t->sb % 4 == 0 && t->sg % 4 == 0 && ((uintptr_t)t->ptr % 16) == 0 && offsets_fit(t) && t->B <= 65535;
+}
+
+}  // namespace
+
+// Do these views take the channel-group planar plane kernels?  (Anything with cg != 0 must: there is no other path.)
+bool plane64_cg_fwd_eligible(const ffcb_tensor* in, const ffcb_tensor* spec) {
+  return real_cg4(in) && spec->cg == 8 && spec->fmt == FFCB_BF16X2 && spec->sx % 2 == 0 && spec->sy % 2 == 0 &&
+         spec->sb % 2 == 0 && spec->sg % 2 == 0 && spec->lo_off % 2 == 0 && ((uintptr_t)spec->ptr % 4) == 0 &&
+         offsets_fit(spec);
+}
+
+bool plane64_cg_inv_eligible(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out) {
+  if (!(spec->cg == 8 && spec->fmt == FFCB_F32 && spec->sx % 2 == 0 && spec->sy % 2 == 0 && spec->sb % 2 == 0 &&
+        spec->sg % 2 == 0 && ((uintptr_t)spec->ptr % 8) == 0 && offsets_fit(spec) && out->H == 64 && out->W == 64 &&
+        out->B <= 65535))
+    return false;
+  if (residual && residual->ptr && !real_cg4(residual)) return false;
+  if (out->fmt == FFCB_BF16X2)
+    return out->cg == 8 && out->sx % 4 == 0 && out->sy % 4 == 0 && out->sb % 4 == 0 && out->sg % 4 == 0 &&
+           out->lo_off % 4 == 0 && ((uintptr_t)out->ptr % 8) == 0 && offsets_fit(out) && out->C % 8 == 0;
+  return real_cg4(out);
+}
+
+int rfft2_plane64_cg(const ffcb_tensor* in, const ffcb_tensor* spec, cudaStream_t stream) {
+  CgArgs a{};
+  a.in = reinterpret_cast<const float*>(in->ptr);
+  a.in_sg = in->sg; a.in_sb = in->sb; a.in_sy = (unsigned)in->sy; a.in_sx = (unsigned)in->sx;
+  a.spec = spec->ptr; a.sp_sg = spec->sg; a.sp_sb = spec->sb; a.sp_sy = (unsigned)spec->sy; a.sp_sx = (unsigned)spec->sx;
+  a.sp_lo = spec->lo_off;
+  a.scale = 1.0f / 64.0f;
+  FFCB_CUDA(cudaFuncSetAttribute(rfft2_plane64_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCgSmemBytes));
+  dim3 grid(in->C / 4, in->B);
+  rfft2_plane64_cg_kernel<<<grid, kCgThreads, kCgSmemBytes, stream>>>(a);
+  FFCB_LAUNCH_CHECK("rfft2_plane64_cg_kernel");
+  return FFCB_OK;
+}
+
+template <bool HAS_RES, bool OUT_SPLIT>
+static int launch_inv_cg(const CgArgs& a, dim3 grid, cudaStream_t stream) {
+  FFCB_CUDA(cudaFuncSetAttribute(irfft2_plane64_cg_kernel<HAS_RES, OUT_SPLIT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kCgSmemBytes));
+  irfft2_plane64_cg_kernel<HAS_RES, OUT_SPLIT><<<grid, kCgThreads, kCgSmemBytes, stream>>>(a);
+  FFCB_LAUNCH_CHECK("irfft2_plane64_cg_kernel");
+  return FFCB_OK;
+}
+
+int irfft2_plane64_cg(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out,
+                      cudaStream_t stream) {
+  const bool has_res = residual && residual->ptr;
+  CgArgs a{};
+  if (has_res) {
+    a.in = reinterpret_cast<const float*>(residual->ptr);
+    a.in_sg = residual->sg; a.in_sb = residual->sb; a.in_sy = (unsigned)residual->sy; a.in_sx = (unsigned)residual->sx;
+  }
+  a.spec = spec->ptr; a.sp_sg = spec->sg; a.sp_sb = spec->sb; a.sp_sy = (unsigned)spec->sy; a.sp_sx = (unsigned)spec->sx;
+  a.out = out->ptr; a.out_sg = out->sg; a.out_sb = out->sb; a.out_sy = (unsigned)out->sy; a.out_sx = (unsigned)out->sx;
+  a.out_lo = out->lo_off;
+  a.scale = 1.0f / 64.0f;
+  dim3 grid(out->C / 4, out->B);
+  const bool split = out->fmt == FFCB_BF16X2;
+  if (has_res) return split ? launch_inv_cg<true, true>(a, grid, stream) : launch_inv_cg<true, false>(a, grid, stream);
+  return split ? launch_inv_cg<false, true>(a, grid, stream) : launch_inv_cg<false, false>(a, grid, stream);
+}
+
+}  // namespace ffcb

@@ -1,0 +1,136 @@
+// Per-thread phases of the channel-group planar 64x64 plane FFT kernels (fft_plane_cg.cu), written against plain
+// pointers so that tests/host_emul/plane_cg_emul.cpp can run every "thread" of a CTA on the host and check the
+// shared-memory index algebra (swizzles, in-place row storage, packed DC / Nyquist slot) against a double DFT.
+//
+// One CTA = 128 threads = one plane set: 4 channels x 64 x 64 pixels of one image, 64 KB of shared memory, used in
+// place by both passes:
+//   real layout    R[y][x][c]   float  index  y*256 + ((x ^ (y & 7)) << 2) + c            (pixel = 16 B)
+//   complex layout Sx[y][k][c]  float2 index  y*128 + ((k ^ (y & 3)) << 2) + c, k = 0..31 (slot = 4 ch x 8 B)
+// Row y of either layout is the same 1 KB, so the row transforms run in place.  The XOR terms make every access of
+// the kernels conflict-free: row tasks are (row y, channel pair cp) with the two channels packed two-for-one into
+// one complex 64-point transform; column tasks are (column kx, channel c).  Slot k = 0 of the complex layout is the
+// packed pair (Re X[y][0], Re X[y][32]): the DC and Nyquist columns of a real row transform are real (forward), and
+// the C2R rule only uses their real parts (inverse) — 32 complex slots per row, not 33.
+//
+// Thread numbering:  row tasks  cp = tid & 1, y = tid >> 1  (a row's two tasks are neighbouring lanes of one warp: the
+// in-place hand-over needs only a __syncwarp);  column tasks  c = tid & 3, kx = tid >> 2.
+#pragma once
+#include "fft_core.cuh"
+
+namespace ffcb {
+namespace fftc {
+
+constexpr int kCgThreads = 128;
+constexpr int kCgSmemBytes = 64 * 64 * 4 * 4;      // 64 KB
+
+FFCB_HD int cg_real_idx(int y, int x, int c) { return y * 256 + ((x ^ (y & 7)) << 2) + c; }          // float index
+FFCB_HD int cg_cplx_idx(int y, int k, int c) { return y * 128 + ((k ^ (y & 3)) << 2) + c; }          // float2 index
+
+// ---- forward, row pass: R (real, two channels of row y) -> Sx (half spectra of both channels, packed slot 0)
+// `load`: callable(float index) -> float2 (two consecutive floats); `sync`: hand-over between reads and writes;
+// `store`: callable(float2 index, float4) writing two consecutive float2
+template <class Load, class Sync, class Store>
+FFCB_HD void cg_fwd_rows(int tid, Load&& ld2, Sync&& sync, Store&& st4) {
+  const int cp = tid & 1, y = tid >> 1;
+  float2 v[64];
+#pragma unroll
+  for (int x = 0; x < 64; ++x) v[x] = ld2(cg_real_idx(y, x, 2 * cp));
+  sync();
+  fft64_regs<false>(v);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const float2 zk = v[fft64_at(k)], zm = v[fft64_at((64 - k) & 63)];
+    float2 a = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));      // spectrum of channel 2cp
+    float2 b = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));     // spectrum of channel 2cp+1
+    if (k == 0) {
+      const float2 zn = v[fft64_at(32)];                                     // Nyquist bin: (Re A[32], Re B[32])
+      a = make_float2(zk.x, zn.x);
+      b = make_float2(zk.y, zn.y);
+    }
+    st4(cg_cplx_idx(y, k, 2 * cp), make_float4(a.x, a.y, b.x, b.y));
+  }
+}
+
+// ---- forward, column pass: Sx column (kx, c) -> spectrum values (ky, kx) [and (ky, 32) for the packed task kx = 0]
+// `emit(ky, kx, value)`: the caller scales and stores
+template <class Load, class Emit>
+FFCB_HD void cg_fwd_cols(int tid, Load&& ld, Emit&& emit) {
+  const int c = tid & 3, kx = tid >> 2;
+  const bool packed = kx == 0;
+  float2 v[64];
+#pragma unroll
+  for (int y = 0; y < 64; ++y) v[y] = ld(cg_cplx_idx(y, kx, c));
+  fft64_regs<false>(v);
+#pragma unroll
+  for (int k = 0; k < 64; ++k) {
+    const float2 wk = v[fft64_at(k)], wm = v[fft64_at((64 - k) & 63)];
+    // packed: v = X0 + i X32 with both columns real -> Hermitian split
+    const float2 x0 = make_float2(0.5f * (wk.x + wm.x), 0.5f * (wk.y - wm.y));
+    const float2 x32 = make_float2(0.5f * (wk.y + wm.y), -0.5f * (wk.x - wm.x));
+    emit(k, kx, c, packed ? x0 : wk);
+    if (packed) emit(k, 32, c, x32);
+  }
+}
+
+// ---- inverse, column pass: spectrum column (kx, c), complex inverse along ky -> Sx[y][kx][c].
+// The packed task (kx = 0) transforms Herm(Z[.,0]) + i Herm(Z[.,32]) whose inverse is Re(ifft Z0) + i Re(ifft Z32):
+// exactly the packed slot the row pass wants (C2R: imaginary parts of bins 0 and 32 are ignored after the H inverse).
+// `ld(ky, kx)`: spectrum value of this task's channel; `st(float2 index, value)`
+template <class Load, class Store>
+FFCB_HD void cg_inv_cols(int tid, Load&& ld, Store&& st) {
+  const int c = tid & 3, kx = tid >> 2;
+  const bool packed = kx == 0;
+  float2 v[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) v[k] = ld(k, kx);
+#pragma unroll
+  for (int k = 0; k <= 32; ++k) {
+    const int m = (64 - k) & 63;
+    const float2 a = v[k], b = v[m];
+    float2 cc = make_float2(0.f, 0.f), d = make_float2(0.f, 0.f);
+    if (packed) {
+      cc = ld(k, 32);
+      d = (m != k) ? ld(m, 32) : cc;
+    }
+    const float2 h0 = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+    const float2 h32 = make_float2(0.5f * (cc.x + d.x), 0.5f * (cc.y - d.y));
+    v[k] = packed ? make_float2(h0.x - h32.y, h0.y + h32.x) : a;
+    if (m != k) v[m] = packed ? make_float2(h0.x + h32.y, h32.x - h0.y) : b;
+  }
+  fft64_regs<true>(v);
+#pragma unroll
+  for (int y = 0; y < 64; ++y) st(cg_cplx_idx(y, kx, c), v[fft64_at(y)]);
+}
+
+// ---- inverse, row pass: Sx row y (both channels of pair cp) -> R[y][x][2cp..2cp+1]   (C2R along W, unnormalised)
+// `ld4(float2 index)` -> float4 = two consecutive float2 (X1[k], X2[k]); `st2(float index, float2)`
+template <class Load, class Sync, class Store>
+FFCB_HD void cg_inv_rows(int tid, Load&& ld4, Sync&& sync, Store&& st2) {
+  const int cp = tid & 1, y = tid >> 1;
+  float2 v[64];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const float4 q = ld4(cg_cplx_idx(y, k, 2 * cp));
+    if (k == 0) {
+      v[0] = make_float2(q.x, q.z);          // (Re X1[0], Re X2[0])
+      v[32] = make_float2(q.y, q.w);         // (Re X1[32], Re X2[32])
+    } else {
+      v[k] = make_float2(q.x - q.w, q.y + q.z);            // X1 + i X2
+      v[64 - k] = make_float2(q.x + q.w, q.z - q.y);       // conj(X1) + i conj(X2)
+    }
+  }
+  sync();
+  fft64_regs<true>(v);
+#pragma unroll
+  for (int x = 0; x < 64; ++x) st2(cg_real_idx(y, x, 2 * cp), v[fft64_at(x)]);
+}
+
+// pixel handled by thread `tid` in iteration i (0..31) of the load / store loops: lanes run along x
+FFCB_HD void cg_pixel_slot(int tid, int i, int& y, int& x) {
+  const int p = i * kCgThreads + tid;
+  y = p >> 6;
+  x = p & 63;
+}
+
+}  // namespace fftc
+}  // namespace ffcb

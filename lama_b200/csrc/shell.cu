@@ -261,7 +261,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, int H, i
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int xx = x0 + i, c = c0 + threadIdx.x;
-    if (xx < W && c < C) store1(out, pix_off(out, b, y, xx) + c, tile[threadIdx.x][i]);
+    if (xx < W && c < C) store1(out, pix_off(out, b, y, xx) + chan_off(out, c), tile[threadIdx.x][i]);
   }
 }
 
@@ -272,7 +272,7 @@ __global__ void nhwc_to_nchw_kernel(View in, float* __restrict__ yo) {
   const int c0 = blockIdx.y * 32, x0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int xx = x0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (xx < W && c < C) ? load1(in, pix_off(in, b, y, xx) + c) : 0.f;
+    tile[i][threadIdx.x] = (xx < W && c < C) ? load1(in, pix_off(in, b, y, xx) + chan_off(in, c)) : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -474,7 +474,7 @@ int head_conv7(const ffcb_tensor* in, const float* w, const float* bias, int N, 
 
 int nchw_to_nhwc(const float* x, int B, int C, int H, int W, const ffcb_tensor* out, cudaStream_t stream) {
   int rc;
-  if ((rc = check_tensor(out, "nchw_to_nhwc.out"))) return rc;
+  if ((rc = check_tensor(out, "nchw_to_nhwc.out", true))) return rc;
   FFCB_REQUIRE(out->B == B && out->C == C && out->H == H && out->W == W, "nchw_to_nhwc: shape mismatch");
   if ((long long)B * C * H * W == 0) return FFCB_OK;
   FFCB_REQUIRE((long long)B * H <= 65535, "nchw_to_nhwc: B*H=%lld exceeds grid.z", (long long)B * H);
@@ -486,7 +486,7 @@ int nchw_to_nhwc(const float* x, int B, int C, int H, int W, const ffcb_tensor* 
 
 int nhwc_to_nchw(const ffcb_tensor* in, float* y, cudaStream_t stream) {
   int rc;
-  if ((rc = check_tensor(in, "nhwc_to_nchw.in"))) return rc;
+  if ((rc = check_tensor(in, "nhwc_to_nchw.in", true))) return rc;
   if ((long long)in->B * in->C * in->H * in->W == 0) return FFCB_OK;
   FFCB_REQUIRE((long long)in->B * in->H <= 65535, "nhwc_to_nchw: B*H exceeds grid.z");
   dim3 grid((in->W + 31) / 32, (in->C + 31) / 32, in->B * in->H), block(32, 8);

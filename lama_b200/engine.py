@@ -47,6 +47,7 @@ class Buf:
     pad: int = 0
     fmt: int = L.F32
     reflect_border: int = 0
+    cg: int = 0        # > 0: channel-group planar storage [C/cg][B][H][W][cg] (FourierUnit chain, include/ffc_b200.h)
 
 
 @dataclass
@@ -192,15 +193,16 @@ class Program:
     outputs: Dict[str, Tuple[int, ...]] = field(default_factory=dict)
     dtypes: Dict[str, torch.dtype] = field(default_factory=dict)       # inputs / outputs that are not float32
 
-    def buf(self, name, B, H, W, C, gemm=False, halo=False, halo_px=1) -> Buf:
+    def buf(self, name, B, H, W, C, gemm=False, halo=False, halo_px=1, cg=0) -> Buf:
         """``gemm``: the buffer is an operand of a contraction; ``halo``: that contraction has spatial taps.
         FFCB_MATH_BF16X3 stores gemm operands as split bf16, and gives halo buffers a reflected border
         ring so that the TMA box of tap (dy,dx) is the tile shifted by (dx,dy); everything else (FFT
         inputs, spectra leaving the GEMM, the head's input) stays float32 without padding."""
         tc = self.math == L.MATH_BF16X3 and gemm
         ring = halo_px if (tc and halo) else 0
+        assert not (cg and ring) and (cg == 0 or C % cg == 0)
         b = Buf(f"{name}#{len(self.bufs)}", B, H, W, C, pad=ring, fmt=L.BF16X2 if tc else L.F32,
-                reflect_border=1 if ring else 0)
+                reflect_border=1 if ring else 0, cg=cg)
         self.bufs.append(b)
         return b
 
@@ -375,6 +377,20 @@ def fu_batch_chunk(batch: int, h: int, w: int, c: int) -> int:
     return batch if n <= 0 else min(batch, n)
 
 
+def fu_planar_ok(prog: Program, st, h: int, w: int) -> bool:
+    """Channel-group planar storage for the SpectralTransform chain (conv1 -> rfft2 -> spectral conv -> irfft2 ->
+    conv2): every (image, 4-channel group) plane set is one dense block for the second-generation plane FFT kernels
+    (csrc/fft_plane_cg.cu) and the GEMMs read [K/8][pixel][8] operand tiles.  Needs the tcgen05 arm, 64x64 planes
+    (the 512x512 bottleneck) and whole 64-channel K blocks on every contraction of the chain.
+    LAMA_B200_FU_LAYOUT=nhwc keeps the round-1 channels-last chain (A/B measurements)."""
+    if prog.math != L.MATH_BF16X3 or os.environ.get("LAMA_B200_FU_LAYOUT", "planar") != "planar":
+        return False
+    c = st.conv1[0].out_channels
+    fu = st.fu
+    return ((h, w) == (64, 64) and c % 64 == 0 and fu.conv_layer.in_channels == 2 * c
+            and fu.conv_layer.out_channels == 2 * c)
+
+
 def emit_fourier_unit(prog: Program, fu, t: TV, out: TV, residual: Optional[TV]):
     """FourierUnit (ffc.py:76-113): rfft2 -> [1x1 conv + BN + ReLU] on the interleaved spectrum -> irfft2,
     optionally with the SpectralTransform residual fused into the inverse (out = residual + fu(t))."""
@@ -382,8 +398,9 @@ def emit_fourier_unit(prog: Program, fu, t: TV, out: TV, residual: Optional[TV])
     h, w = t.hw
     wf = w // 2 + 1
     cin2, cout2 = fu.conv_layer.in_channels, fu.conv_layer.out_channels
-    S = prog.buf("spectrum", b, h, wf, cin2, gemm=True)
-    Z = prog.buf("spectrum_out", b, h, wf, cout2)
+    planar = t.buf.cg == 4      # FourierUnit chain in channel-group planar storage (emit_spectral_transform decides)
+    S = prog.buf("spectrum", b, h, wf, cin2, gemm=True, cg=8 if planar else 0)
+    Z = prog.buf("spectrum_out", b, h, wf, cout2, cg=8 if planar else 0)
     scale, shift = P.bn_scale_shift(fu.bn)
     pk = P.pack_conv([(fu.conv_layer.weight, 0, 0, 0)], scale, shift, act=L.ACT_RELU,
                      device=fu.conv_layer.weight.device)
@@ -403,8 +420,9 @@ def emit_spectral_transform(prog: Program, st, x: TV, u_consumer=None) -> Tuple[
     h, w = x.hw
     c = st.conv1[0].out_channels
     dev = st.conv2.weight.device
-    T = prog.buf("st.t", b, h, w, c)
-    U = prog.buf("st.u", b, h, w, c, gemm=True)
+    planar = fu_planar_ok(prog, st, h, w)
+    T = prog.buf("st.t", b, h, w, c, cg=4 if planar else 0)
+    U = prog.buf("st.u", b, h, w, c, gemm=True, cg=8 if planar else 0)
     s1, b1 = P.bn_scale_shift(st.conv1[1])
     pk1 = P.pack_conv([(st.conv1[0].weight, 0, x.c0, 0)], s1, b1, act=L.ACT_RELU, device=dev)
     prog.ops.append(ConvOp(pk1, [TV(x.buf), None], TV(T), tag="st.conv1+bn+relu"))
@@ -654,6 +672,8 @@ class CudaExecutor:
         self.storage: Dict[str, torch.Tensor] = {}
         for b in prog.bufs:
             shape = (b.B, b.H + 2 * b.pad, b.W + 2 * b.pad, b.C)
+            if b.cg:
+                shape = (b.C // b.cg, b.B, b.H, b.W, b.cg)
             if b.fmt == L.F32:
                 self.storage[b.name] = torch.empty(shape, dtype=torch.float32, device=device)
             else:
@@ -675,6 +695,16 @@ class CudaExecutor:
         b = tv.buf
         st = self.storage[b.name]
         es = 4 if b.fmt == L.F32 else 2
+        if b.cg:
+            assert tv.phase is None and not tv.window and b.pad == 0 and tv.c0 % b.cg == 0 and tv.channels % b.cg == 0
+            t = L.Tensor()
+            t.sx, t.sy, t.sb = b.cg, b.W * b.cg, b.H * b.W * b.cg
+            t.sg, t.cg = b.B * b.H * b.W * b.cg, b.cg
+            t.lo_off = b.C * b.B * b.H * b.W if b.fmt == L.BF16X2 else 0
+            t.ptr = st.data_ptr() + ((tv.c0 // b.cg) * t.sg + tv.b0 * t.sb) * es
+            t.B, t.H, t.W, t.C = tv.batch, b.H, b.W, tv.channels
+            t.fmt, t.pad, t.reflect_border = b.fmt, 0, 0
+            return t
         wp, hp = b.W + 2 * b.pad, b.H + 2 * b.pad
         sx, sy, sb = b.C, wp * b.C, hp * wp * b.C
         off = (b.pad * wp + b.pad) * b.C + tv.c0

@@ -74,6 +74,16 @@ def test_host_emulation_of_fft_kernels(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
 
 
+def test_host_emulation_of_channel_group_planar_plane_kernels(tmp_path):
+    """fft_plane_cg.cuh (the per-thread phases of the round-2 64x64 plane kernels) run for all 128 threads of a CTA
+    on the host: swizzled in-place shared-memory layout, packed DC / Nyquist slot, C2R rule — vs a float64 DFT."""
+    exe = tmp_path / "plane_cg_emul"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I/usr/local/cuda/include",
+                           os.path.join(ROOT, "tests", "host_emul", "plane_cg_emul.cpp"), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
 def test_cpu_tensor_never_touches_the_library():
     """On CPU tensors the modules run the torch composition (training / reference use); the CUDA
     library is only entered for CUDA tensors, where its absence raises."""

@@ -291,6 +291,98 @@ def test_conv_contract(case, math, math_mode):
     assert _rel_err(out["y0"].permute(0, 2, 3, 1).numpy(), want.numpy()) < tol
 
 
+
+# ------------------------------------------------------------------ channel-group planar FourierUnit chain (round 2)
+@pytest.mark.parametrize("residual", [True, False])
+@pytest.mark.parametrize("b,c", [(2, 8), (3, 24), (1, 192)])
+def test_plane_fft_pair_channel_group_planar(b, c, residual, math_mode):
+    """fft_plane_cg.cu: the 64x64 plane kernels on [C/cg][B][H][W][cg] tensors — float32 cg=4 real planes in, split
+    bf16 cg=8 spectrum out (GEMM operand format); float32 cg=8 spectrum + cg=4 residual in, split bf16 cg=8 and
+    float32 cg=4 real planes out.  Checker: numpy float64 (oracle/ffc_numpy.py), incl. the C2R rule on a ReLU'd
+    (non-Hermitian) spectrum."""
+    _fp32_only(math_mode)
+    h = w = 64
+    wf = 33
+    rng = np.random.default_rng(b * 100 + c)
+    x = rng.standard_normal((b, c, h, w)).astype(np.float32)
+    z = np.maximum(rng.standard_normal((b, 2 * c, h, wf)), 0).astype(np.float32)
+    res = rng.standard_normal((b, c, h, w)).astype(np.float32)
+    prog = E.Program("fft_cg", L.MATH_BF16X3)
+    X = prog.buf("x", b, h, w, c, cg=4); S = prog.buf("s", b, h, wf, 2 * c, gemm=True, cg=8)
+    Z = prog.buf("z", b, h, wf, 2 * c, cg=8); R = prog.buf("r", b, h, w, c, cg=4)
+    O = prog.buf("o", b, h, w, c, gemm=True, cg=8) if c % 8 == 0 else None
+    O32 = prog.buf("o32", b, h, w, c, cg=4)
+    prog.inputs = {"x0": (b, c, h, w), "x1": (b, 2 * c, h, wf), "x2": (b, c, h, w)}
+    rtv = E.TV(R) if residual else None
+    prog.ops += [E.ToNHWC("x0", E.TV(X)), E.RfftOp(E.TV(X), E.TV(S)), E.ToNCHW(E.TV(S), "y0"),
+                 E.ToNHWC("x1", E.TV(Z)), E.ToNHWC("x2", E.TV(R)),
+                 E.IrfftOp(E.TV(Z), rtv, E.TV(O32)), E.ToNCHW(E.TV(O32), "y2")]
+    prog.outputs = {"y0": (b, 2 * c, h, wf), "y2": (b, c, h, w)}
+    if O is not None:
+        prog.ops += [E.IrfftOp(E.TV(Z), rtv, E.TV(O)), E.ToNCHW(E.TV(O), "y1")]
+        prog.outputs["y1"] = (b, c, h, w)
+    out = _run_program(prog, {"x0": torch.from_numpy(x), "x1": torch.from_numpy(z), "x2": torch.from_numpy(res)})
+    spec = onp.rfft2_ortho(x.astype(np.float64))
+    want_s = np.stack((spec.real, spec.imag), axis=2).reshape(b, 2 * c, h, wf)
+    assert _rel_err(out["y0"].numpy(), want_s) < 2e-5
+    zc = z.astype(np.float64).reshape(b, c, 2, h, wf)
+    want_y = onp.irfft2_explicit(zc[:, :, 0] + 1j * zc[:, :, 1], h, w) + (res if residual else 0.0)
+    assert _rel_err(out["y2"].numpy(), want_y) < 2e-6
+    if O is not None:
+        assert _rel_err(out["y1"].numpy(), want_y) < 2e-5
+
+
+@pytest.mark.parametrize("case", ["flat_interleaved_to_planar8", "nhwc_to_planar4", "spatial_taps_plus_interleaved",
+                                  "flat_ragged_m"])
+def test_conv_tc_channel_group_planar_operands(case, math_mode):
+    """conv_tc.cu with the FourierUnit chain's layouts: [K/8][pixel][8] ("interleaved", no-swizzle descriptor, 1-D
+    bulk copies) A operands and channel-group planar float32 outputs, against the torch restatement of ffcb_conv."""
+    _fp32_only(math_mode)
+    g = torch.Generator().manual_seed(sum(map(ord, case)))
+    rn = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
+    prog = E.Program("conv_cg", L.MATH_BF16X3)
+    feed = {}
+
+    def inp(name, t, **kw):
+        bb = prog.buf(name, *t.shape, gemm=True, **kw)
+        prog.inputs[name] = (t.shape[0], t.shape[3], t.shape[1], t.shape[2])
+        prog.ops.append(E.ToNHWC(name, E.TV(bb)))
+        feed[name] = t.permute(0, 3, 1, 2).contiguous()
+        return bb
+    if case == "flat_interleaved_to_planar8":        # the spectral GEMM: S (cg 8) -> Z (cg 8 float32), ReLU
+        b, h, w, k, n = 2, 64, 33, 128, 192
+        x0 = rn(b, h, w, k)
+        pk = P.pack_conv([(rn(n, k, 1, 1) * 0.1, 0, 0, 0)], rn(n).abs() + 0.5, rn(n), act=L.ACT_RELU)
+        ins, tvs = [x0, None], [E.TV(inp("x0", x0, cg=8)), None]
+        Y = prog.buf("y", b, h, w, n, cg=8)
+    elif case == "flat_ragged_m":                     # M = 2*5*33 = 330: a partial last tile of interleaved rows
+        b, h, w, k, n = 2, 5, 33, 64, 64
+        x0 = rn(b, h, w, k)
+        pk = P.pack_conv([(rn(n, k, 1, 1) * 0.1, 0, 0, 0)], None, rn(n), act=L.ACT_NONE)
+        ins, tvs = [x0, None], [E.TV(inp("x0", x0, cg=8)), None]
+        Y = prog.buf("y", b, h, w, n, cg=8)
+    elif case == "nhwc_to_planar4":                   # SpectralTransform.conv1: ring-padded NHWC slice -> T (cg 4)
+        b, h, w, n = 2, 64, 64, 64
+        x0 = rn(b, h, w, 192)
+        pk = P.pack_conv([(rn(n, 128, 1, 1) * 0.1, 0, 64, 0)], rn(n).abs() + 0.5, rn(n), act=L.ACT_RELU)
+        ins, tvs = [x0, None], [E.TV(inp("x0", x0, halo=True)), None]
+        Y = prog.buf("y", b, h, w, n, cg=4)
+    else:                                             # the global contraction: 3x3 taps on x_l + conv2 on u (cg 8)
+        b, h, w, n = 2, 64, 64, 128
+        x0, x1 = rn(b, h, w, 64), rn(b, h, w, 128)
+        pk = P.pack_conv([(rn(n, 64, 3, 3) * 0.1, 0, 0, 1), (rn(n, 128, 1, 1) * 0.1, 1, 0, 0)], rn(n).abs() + 0.5, rn(n),
+                         act=L.ACT_RELU)
+        ins, tvs = [x0, x1], [E.TV(inp("x0", x0, halo=True)), E.TV(inp("x1", x1, cg=8))]
+        Y = prog.buf("y", b, h, w, n)
+    prog.ops.append(E.ConvOp(pk, tvs, E.TV(Y)))
+    prog.ops.append(E.ToNCHW(E.TV(Y), "y0"))
+    prog.outputs = {"y0": (Y.B, pk.n_out, Y.H, Y.W)}
+    _finish_borders(prog)
+    out = _run_program(prog, feed)
+    want = P.apply_packed_reference(pk, ins, (Y.H, Y.W))
+    assert _rel_err(out["y0"].permute(0, 2, 3, 1).numpy(), want.numpy()) < 2e-4
+
+
 def _finish_borders(prog):
     """Hand-built test programs: ToNHWC does not write reflect rings, so add explicit border ops
     (production programs get their rings from the producing kernels' epilogues)."""
