@@ -115,37 +115,29 @@ def cpu_reference_step(images, threads=None):
     return time.perf_counter() - t0, images
 
 
+CPU_THREADS = int(os.environ.get("LAMA_B200_CPU_THREADS", "16"))
+CPU_IMAGES_PER_STEP = 4
+
+
 def _cpu_setup():
-    """Build the CPU model once and pick the thread count: "all the host threads it can use" — the box
-    reports 128 logical CPUs but oversubscribed intra-op pools are far slower than a right-sized one
-    (first B200 run: 128 threads -> 0.017 img/s), so calibrate on one 256x256 image and keep the fastest."""
+    """Build the CPU model once.  Thread count: FIXED at min(16, available) in both arms (stated in the JSON line).
+    Round 1 calibrated it per run and the two arms disagreed (8 vs 16 threads on the same box); the box reports 128
+    logical CPUs but oversubscribed intra-op pools are far slower than a right-sized one (first B200 run: 128 threads
+    -> 0.017 img/s, 16 -> 1.9 img/s, 8 -> 1.4 img/s), so "all the host threads it can use" is 16 here."""
     import torch
     from lama_b200 import modules as M
     from lama_b200.testing import BIG_LAMA_KWARGS, seeded_parameters_, synthetic_image_mask, generator_input
-    from oracle import ffc_torch_cpu as otc
     try:
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 1
+    n = max(1, min(CPU_THREADS, avail))
+    torch.set_num_threads(n)
     g = seeded_parameters_(M.FFCResNetGenerator(**BIG_LAMA_KWARGS).eval(), 0)
     sd = {k: v for k, v in g.state_dict().items()}
-    img, mask = synthetic_image_mask(1, 256, 1)
-    probe = generator_input(img, mask)
-    best, best_t = 1, float("inf")
-    for n in sorted({avail, max(1, avail // 2), max(1, avail // 4), 32, 16, 8} & set(range(1, avail + 1)), reverse=True):
-        torch.set_num_threads(n)
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            otc.ffc_resnet_generator(probe, sd, **BIG_LAMA_KWARGS)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = n, dt
-        if dt > 20.0:        # pathological oversubscription: do not even try the rest at this size
-            continue
-    torch.set_num_threads(best)
-    img, mask = synthetic_image_mask(4, SIZE, 0)
+    img, mask = synthetic_image_mask(CPU_IMAGES_PER_STEP, SIZE, 0)
     cpu_reference_step.state = {"sd": sd, "x": generator_input(img, mask)}
-    return best
+    return n
 
 
 def torch_cuda_baseline(dev, B, S, steps=5, warmup=3):
@@ -210,9 +202,9 @@ def run_reference(args, rank, world, out):
     if rank != 0:
         return
     cores = _cpu_setup()
-    per_step = 1          # images per step (the reference's own batch size, predict.py:74); bounded work
+    per_step = CPU_IMAGES_PER_STEP   # bounded sample of the bs32 step: one batch of 4 of its 32 images per step
     for _ in range(args.warmup):
-        cpu_reference_step(1)
+        cpu_reference_step(per_step)
     t = 0.0
     for _ in range(args.steps):
         dt, _n = cpu_reference_step(per_step)
@@ -223,7 +215,8 @@ def run_reference(args, rank, world, out):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "big-lama FFCResNetGenerator fwd, 512x512, seeded random weights",
-                   "per_step_images": per_step, "device": "cpu"},
+                   "per_step_images": per_step, "device": "cpu", "threads": cores,
+                   "sample": "each step = one batch of %d of the 32 images of the GPU arm's step" % per_step},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step} images/step x {args.steps} steps, torch-CPU port of ffc.py (oracle/ffc_torch_cpu.py)"},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -253,6 +246,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32-arm", action="store_true", help="skip the CUDA-core fp32 reading of the same step")
     ap.add_argument("--no-torch-cuda-baseline", action="store_true",
                     help="skip the torch-eager (cuFFT/cuDNN) reading of the same operator sequence on this GPU")
     ap.add_argument("--io", default=os.environ.get("LAMA_B200_BENCH_IO", "both"), choices=["f32", "both"],
@@ -403,27 +397,68 @@ def main():
             j = fu_idx[len(fu_idx) // 2]
             fu_calls = [j, j + 1, j + 2]       # rfft2, fu conv, irfft2 (emit_fourier_unit order)
             run_calls(fu_calls * 3)
-            ms_f = timed(lambda: run_calls(fu_calls), reps, collective=False) / reps
             c = 192
             fu_bytes = 4.0 * B * h * h * (c + c) + 4.0 * (2 * c) * (2 * c) + 8.0 * (2 * c)
-            gbs = fu_bytes / (ms_f * 1e-3) / 1e9
+            flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)     # 4x the 126 MB L2
+
+            def fu_time(cold, idx):
+                """median of `reps` single runs; cold: a 512 MB write evicts L2 before every run (outside the events)"""
+                ts = []
+                for _ in range(reps):
+                    if cold:
+                        flush.fill_(1)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    run_calls(idx)
+                    e1.record(stream)
+                    torch.cuda.synchronize(dev)
+                    ts.append(e0.elapsed_time(e1))
+                ts.sort()
+                return ts[len(ts) // 2]
+            ms_cold, ms_warm = fu_time(True, fu_calls), fu_time(False, fu_calls)
+            parts = {n: {"cold_ms": fu_time(True, [k]), "warm_ms": fu_time(False, [k])}
+                     for n, k in zip(("rfft2", "spectral_gemm", "irfft2"), fu_calls)}
+            del flush
+            gbs = fu_bytes / (ms_cold * 1e-3) / 1e9
             roof["fourier_unit"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                    "frac": gbs / peaks["hbm_gbs"], "ms": ms_f, "algorithmic_bytes": fu_bytes,
-                                    "shape": [B, c, h, h], "launches": 3,
-                                    "note": "warm L2 between repetitions of the same FU; intermediates (spectrum) not counted"}
+                                    "frac": gbs / peaks["hbm_gbs"], "ms": ms_cold, "algorithmic_bytes": fu_bytes,
+                                    "shape": [B, c, h, h], "launches": 3, "l2": "cold (512 MB flush before each run)",
+                                    "warm": {"ms": ms_warm, "achieved": fu_bytes / (ms_warm * 1e-3) / 1e9,
+                                             "frac": fu_bytes / (ms_warm * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                                    "per_kernel": parts,
+                                    "layout": os.environ.get("LAMA_B200_FU_LAYOUT", "planar"),
+                                    "traffic": _ncu_traffic("FU:") if (B, S) == (32, 512) else None,
+                                    "note": "SURVEY.md 8(d): algorithmic bytes = t in + u out + weights; spectrum "
+                                            "intermediates not counted; graded figure = cold L2"}
+
+    # ---- the CUDA-core fp32 arm of the same step (reference-grade arithmetic, LAMA_B200_MATH=fp32): same-arithmetic
+    # reading beside the headline (rank 0, N=1 only; short: it is ~7x slower)
+    fp32_arm = None
+    if rank == 0 and world == 1 and math == L.MATH_BF16X3 and not args.no_fp32_arm:
+        try:
+            ex32 = E.get_executor(gen, "generator", (x_dev,), math=L.MATH_FP32)
+            ex32.run({"x0": x_dev})
+            ms32 = timed(lambda: ex32.run({"x0": x_dev}), 2, collective=False) / 2
+            fp32_arm = {"value": B / (ms32 / 1e3), "unit": "images/s", "ms_per_step": ms32, "dtype": "f32",
+                        "launches_per_step": ex32.launches_per_run}
+            del ex32
+            E.invalidate(gen)
+            torch.cuda.empty_cache()
+        except Exception as ex_f:  # noqa: BLE001
+            fp32_arm = {"error": f"{type(ex_f).__name__}: {ex_f}"[:300]}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample on all host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = _cpu_setup()
-        cpu_reference_step(1)
+        cpu_reference_step(CPU_IMAGES_PER_STEP)
         n_img, t = 0, 0.0
         while t < 10.0 and n_img < 16:
-            dt, n = cpu_reference_step(1)
+            dt, n = cpu_reference_step(CPU_IMAGES_PER_STEP)
             t += dt; n_img += n
         cpu = {"value": n_img / t, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"{n_img} images of 512x512 one at a time (bin/predict.py:74 batch size), torch-CPU port of "
-                         f"the reference ops (oracle/ffc_torch_cpu.py), {cores} threads (calibrated)"}
+               "sample": f"{n_img} images of 512x512 in batches of {CPU_IMAGES_PER_STEP}, torch-CPU port of the "
+                         f"reference ops (oracle/ffc_torch_cpu.py), {cores} threads (fixed, same as --impl reference)"}
 
     # ---- the reference operator sequence under torch eager on this GPU (rank 0, N=1 only), TF32 on / off
     tcb = None
@@ -487,6 +522,7 @@ def main():
             "gpu_launches": ex.launches_per_run * args.steps,
             "launches_per_step": ex.launches_per_run,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "torch_cuda_baseline": tcb,
+            "fp32_arm": fp32_arm,
         }), file=out)
         out.flush()
     if world > 1:

@@ -232,6 +232,15 @@ def _act_code(m: nn.Module) -> Optional[int]:
     return None
 
 
+def bn_foldable(bn) -> bool:
+    """Eval-mode BatchNorm that can be folded into the preceding weights: it must carry running statistics
+    (track_running_stats=False uses batch statistics even in eval mode — the torch composition handles that)."""
+    if isinstance(bn, nn.Identity):
+        return True
+    return (isinstance(bn, nn.BatchNorm2d) and bn.track_running_stats and bn.running_var is not None
+            and bn.running_mean is not None)
+
+
 def _plain_conv(conv, k_ok=(1, 3, 7)) -> bool:
     return (isinstance(conv, nn.Conv2d) and conv.groups == 1 and conv.dilation == (1, 1) and conv.bias is None
             and conv.kernel_size[0] == conv.kernel_size[1] and conv.kernel_size[0] in k_ok
@@ -259,7 +268,7 @@ def ffc_bn_act_supported(m) -> bool:
         if isinstance(f.convl2g, nn.Identity):      # global-only input is never produced by the generator
             return False
     for bn in (m.bn_l, m.bn_g):
-        if not isinstance(bn, (nn.BatchNorm2d, nn.Identity)):
+        if not bn_foldable(bn):
             return False
     return _act_code(m.act_l) is not None and _act_code(m.act_g) is not None
 
@@ -297,7 +306,7 @@ def _generator_layout(gen):
         if not (isinstance(stem, FFC_BN_ACT) and isinstance(stem.ffc.convl2l, nn.Conv2d)
                 and stem.ffc.convl2l.kernel_size == (7, 7) and stem.ffc.convl2l.padding == (0, 0)
                 and stem.ffc.convl2l.stride == (1, 1) and isinstance(stem.ffc.convl2g, nn.Identity)
-                and stem.ffc.global_in_num == 0 and isinstance(stem.bn_l, nn.BatchNorm2d)
+                and stem.ffc.global_in_num == 0 and isinstance(stem.bn_l, nn.BatchNorm2d) and bn_foldable(stem.bn_l)
                 and isinstance(stem.act_l, nn.ReLU) and stem.ffc.convl2l.bias is None
                 and stem.ffc.convl2l.groups == 1 and stem.ffc.convl2l.in_channels <= 16
                 and stem.ffc.convl2l.out_channels % 4 == 0 and not stem.ffc.gated):
@@ -321,7 +330,7 @@ def _generator_layout(gen):
             ct, bn, act = mods[i], mods[i + 1], mods[i + 2]
             if not (ct.kernel_size == (3, 3) and ct.stride == (2, 2) and ct.padding == (1, 1)
                     and ct.output_padding == (1, 1) and ct.groups == 1 and ct.dilation == (1, 1)
-                    and isinstance(bn, nn.BatchNorm2d) and isinstance(act, nn.ReLU)
+                    and isinstance(bn, nn.BatchNorm2d) and bn_foldable(bn) and isinstance(act, nn.ReLU)
                     and ct.in_channels % 4 == 0 and ct.out_channels % 4 == 0):
                 return None
             ups.append((ct, bn)); i += 3
@@ -879,19 +888,55 @@ class GraphedProgram:
 
 
 # ---------------------------------------------------------------------------- module entry point
-_REWALK_EVERY = 32
+# Executor caches live OUTSIDE the module (weak keys): they hold ctypes pointers / byref objects, which must never
+# end up in `module.__dict__` — the reference deep-copies the generator for its EMA copy (trainers/base.py:168) and
+# `torch.save(module)` / pickling / DataParallel replication walk `__dict__`.
+import weakref
+
+_PROGRAMS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()      # module -> {key: (signature, executor)}
+_TENSORS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()       # module -> [flat tensor list, calls since walk]
+_REWALK_EVERY = 8
+_SMALL_MODULE = 64       # modules with fewer tensors are re-walked on every call (the walk is cheap there)
 
 
-def _weights_signature(module) -> Tuple:
-    """(data_ptr, version) of every parameter / buffer: changes on load_state_dict, .to(), in-place edits.
-    Walking the module tree costs ~1.5 ms for big-lama (989 tensors) — as much as a bs1 forward — so the flat
-    tensor list is cached on the module and re-walked only every few calls (catches replaced Parameter objects)."""
-    st = module.__dict__.get("_ffcb_tensors")
-    if st is None or st[1] >= _REWALK_EVERY:
+def invalidate(module) -> None:
+    """Drop every cached program / packed weight of ``module`` (call after editing weights in a way the automatic
+    checks cannot see; load_state_dict, .to(), in-place ops and ``.data`` edits ARE seen)."""
+    _PROGRAMS.pop(module, None)
+    _TENSORS.pop(module, None)
+
+
+def _content_checksum(tensors) -> float:
+    """One number per weight version: the sum of all tensors' L2 norms (a handful of fused multi-tensor kernels and
+    one scalar read).  Catches what (data_ptr, _version) cannot: edits through ``.data`` — the reference's EMA update
+    (trainers/base.py:40) and the common ``weight.data.copy_()`` loading idiom leave ``_version`` unchanged."""
+    fl = [t for t in tensors if t.is_floating_point() and t.numel()]
+    if not fl:
+        return 0.0
+    groups = {}
+    for t in fl:
+        groups.setdefault((t.device, t.dtype), []).append(t.detach())
+    total = 0.0
+    for ts in groups.values():
+        total += float(torch.stack(torch._foreach_norm(ts)).double().sum())
+    return total
+
+
+def _weights_signature(module, content: bool = True) -> Tuple:
+    """(data_ptr, version) of every parameter / buffer — changes on load_state_dict, .to(), in-place edits — plus,
+    with ``content``, a checksum of the values (``.data`` edits).  Walking the module tree costs ~1.5 ms for big-lama
+    (989 tensors), so the flat tensor list is cached and re-walked every few calls (every call for small modules);
+    a replaced Parameter object whose storage was freed changes data_ptr and is seen at once in practice.
+    LAMA_B200_TRUST_WEIGHTS=1 skips the checksum (serving loops that never touch the weights)."""
+    st = _TENSORS.get(module)
+    if st is None or st[1] >= _REWALK_EVERY or len(st[0]) <= _SMALL_MODULE:
         st = [list(module.parameters()) + list(module.buffers()), 0]
-        module.__dict__["_ffcb_tensors"] = st
+        _TENSORS[module] = st
     st[1] += 1
-    return tuple((t.data_ptr(), t._version) for t in st[0])
+    sig = tuple((t.data_ptr(), t._version) for t in st[0])
+    if content and os.environ.get("LAMA_B200_TRUST_WEIGHTS", "0") != "1":
+        sig = sig + (_content_checksum(st[0]),)
+    return sig
 
 
 def get_executor(module, kind: str, tensors, math: Optional[int] = None,
@@ -901,7 +946,7 @@ def get_executor(module, kind: str, tensors, math: Optional[int] = None,
     shapes = tuple(tuple(t.shape) if torch.is_tensor(t) else None for t in tensors)
     dev = device if device is not None else next(t for t in tensors if torch.is_tensor(t)).device
     key = (kind, shapes, str(dev), math)
-    cache = module.__dict__.setdefault("_ffcb_programs", {})
+    cache = _PROGRAMS.setdefault(module, {})
     sig = _weights_signature(module)
     hit = cache.get(key)
     if hit is not None and hit[0] == sig:

@@ -121,7 +121,8 @@ class FourierUnit(nn.Module):
     def native_supported(self) -> bool:
         return (self.groups == 1 and self.spatial_scale_factor is None and not self.spectral_pos_encoding
                 and not self.use_se and not self.ffc3d and self.fft_norm == 'ortho' and not self.training
-                and self.conv_layer.in_channels % 8 == 0 and self.conv_layer.out_channels % 8 == 0)
+                and self.conv_layer.in_channels % 8 == 0 and self.conv_layer.out_channels % 8 == 0
+                and _engine.bn_foldable(self.bn))
 
     def forward(self, x):
         if _native_ok(x) and self.native_supported() and x.dim() == 4 and x.shape[-1] >= 2:
@@ -175,7 +176,7 @@ class SpectralTransform(nn.Module):
     def native_supported(self) -> bool:
         return (not self.enable_lfu and self.stride == 1 and self.conv1[0].groups == 1 and not self.training
                 and self.fu.native_supported() and self.conv1[0].in_channels % 4 == 0
-                and self.conv2.out_channels % 4 == 0)
+                and self.conv2.out_channels % 4 == 0 and _engine.bn_foldable(self.conv1[1]))
 
     def forward(self, x):
         if _native_ok(x) and self.native_supported() and x.shape[-1] >= 2:

@@ -33,19 +33,21 @@ MATHS = [L.MATH_FP32, L.MATH_BF16X3]
 TOL = {"fp32": 2e-5, "bf16x3": 2e-4}
 
 
-@pytest.fixture(params=["fp32", "bf16x3"], autouse=True)
-def math_mode(request):
-    """Every module-level test runs in both arithmetic modes of the library (LAMA_B200_MATH)."""
-    os.environ["LAMA_B200_MATH"] = request.param
-    os.environ["LAMA_B200_STRICT"] = "1"      # an unexpected torch fallback is a test failure
-    yield request.param
-    os.environ.pop("LAMA_B200_MATH", None)
+@pytest.fixture(autouse=True)
+def _strict_env():
+    """An unexpected torch fallback is a test failure; tests that do not depend on the arithmetic mode (the kernel
+    level ones: they pick formats / math per program) run once, with the library default left alone."""
+    os.environ["LAMA_B200_STRICT"] = "1"
+    yield
     os.environ.pop("LAMA_B200_STRICT", None)
 
 
-def _fp32_only(mode):
-    if mode != "fp32":
-        pytest.skip("test does not depend on the math mode")
+@pytest.fixture(params=["fp32", "bf16x3"])
+def math_mode(request):
+    """Module-level tests request this fixture and run in both arithmetic modes of the library (LAMA_B200_MATH)."""
+    os.environ["LAMA_B200_MATH"] = request.param
+    yield request.param
+    os.environ.pop("LAMA_B200_MATH", None)
 
 
 @pytest.fixture(autouse=True, scope="module")
@@ -76,37 +78,33 @@ def _run_program(prog, feed):
 @pytest.mark.parametrize("b,c,h,w", [(2, 8, 16, 16), (1, 32, 64, 64), (1, 4, 8, 32), (3, 36, 32, 32),
                                      (1, 8, 128, 128), (1, 4, 256, 256), (1, 4, 15, 15), (2, 4, 6, 9),
                                      (1, 4, 20, 24), (1, 8, 125, 188), (1, 4, 5, 2), (1, 40, 64, 4)])
-def test_rfft2_irfft2_against_numpy(b, c, h, w, math_mode):
-    _fp32_only(math_mode)
+def test_rfft2_irfft2_against_numpy(b, c, h, w):
     _check_fft_pair(b, c, h, w)
 
 
 @pytest.mark.parametrize("mixed", ["0", "1"])
 @pytest.mark.parametrize("b,c,h,w", [(1, 4, 15, 15), (2, 4, 6, 9), (1, 8, 125, 188), (1, 36, 96, 128),
                                      (1, 4, 135, 240), (2, 8, 47, 94), (1, 4, 7, 250), (1, 4, 3, 2)])
-def test_fft_lengths_without_compile_time_plan(b, c, h, w, mixed, math_mode, monkeypatch):
+def test_fft_lengths_without_compile_time_plan(b, c, h, w, mixed, monkeypatch):
     """SURVEY.md row f2 (bin/predict.py pads to multiples of 8 only -> 96x128, 135x240, 125x188 ... bottleneck
     planes): runtime mixed-radix Stockham (FFCB_FFT_MIXED_RADIX=1) and the O(n^2) direct DFT (=0) against numpy —
     composite, prime-power, prime and large-prime-factor lengths."""
-    _fp32_only(math_mode)
     monkeypatch.setenv("FFCB_FFT_MIXED_RADIX", mixed)
     _check_fft_pair(b, c, h, w)
 
 
-def test_two_pass_fft_kernels_at_64x64(math_mode, monkeypatch):
+def test_two_pass_fft_kernels_at_64x64(monkeypatch):
     """64x64 planes normally take the fused whole-plane kernels (fft_plane.cu); keep the general
     row/column kernels covered at that size too."""
-    _fp32_only(math_mode)
     monkeypatch.setenv("FFCB_FFT_TWO_PASS", "1")
     _check_fft_pair(2, 40, 64, 64)
 
 
 @pytest.mark.parametrize("plane_ch", ["8", "4"])
 @pytest.mark.parametrize("variant", ["1", "2"])
-def test_inverse_plane_kernel_opt_in(math_mode, monkeypatch, variant, plane_ch):
+def test_inverse_plane_kernel_opt_in(monkeypatch, variant, plane_ch):
     """The fused inverse plane kernels (fft_plane.cu; 1 = packed, 2 = one task per column; 8 or 4 channels per
     CTA) are opt-in in round 1 (not faster than two-pass yet); keep them correct."""
-    _fp32_only(math_mode)
     monkeypatch.setenv("FFCB_FFT_INV_PLANE", variant)
     monkeypatch.setenv("FFCB_FFT_PLANE_CH", plane_ch)
     _check_fft_pair(2, 24, 64, 64)
@@ -114,18 +112,16 @@ def test_inverse_plane_kernel_opt_in(math_mode, monkeypatch, variant, plane_ch):
 
 @pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("residual", [True, False])
-def test_plane_kernels_second_revision(math_mode, monkeypatch, split, residual):
+def test_plane_kernels_second_revision(monkeypatch, split, residual):
     """FFCB_FFT_PLANE_FWD=2 / FFCB_FFT_INV_PLANE=3: templated formats, 32-bit in-plane offsets, channels-last
     vector epilogue staged in place of the half spectrum — all four format / residual instantiations, and
     bit-identical results to the kernels they replace."""
-    _fp32_only(math_mode)
     monkeypatch.setenv("FFCB_FFT_PLANE_FWD", "2")
     monkeypatch.setenv("FFCB_FFT_INV_PLANE", "3")
     _check_fft_pair(3, 40, 64, 64, split=split, residual=residual)
 
 
-def test_plane_kernels_second_revision_bit_identical_to_first(math_mode, monkeypatch):
-    _fp32_only(math_mode)
+def test_plane_kernels_second_revision_bit_identical_to_first(monkeypatch):
     b, c, h, w = 2, 24, 64, 64
     wf = w // 2 + 1
 
@@ -151,9 +147,8 @@ def test_plane_kernels_second_revision_bit_identical_to_first(math_mode, monkeyp
 
 
 @pytest.mark.parametrize("occ", ["2", "3"])
-def test_forward_plane_kernel_4_channels_per_cta(math_mode, monkeypatch, occ):
+def test_forward_plane_kernel_4_channels_per_cta(monkeypatch, occ):
     """FFCB_FFT_PLANE_CH=4: 69 KB CTAs, two (or, registers capped, three) per SM."""
-    _fp32_only(math_mode)
     monkeypatch.setenv("FFCB_FFT_PLANE_CH", "4")
     monkeypatch.setenv("FFCB_FFT_PLANE_OCC", occ)
     _check_fft_pair(2, 24, 64, 64)
@@ -187,8 +182,7 @@ def _check_fft_pair(b, c, h, w, split=False, residual=True):
     assert _rel_err(out["y1"].numpy(), want_y) < tol
 
 
-def test_fft_round_trip_full_size(math_mode):
-    _fp32_only(math_mode)
+def test_fft_round_trip_full_size():
     """Size-independent property at the BASELINE shape (32 x 192 x 64 x 64): irfft2(rfft2(x)) == x and
     Parseval (ortho norm; half spectrum counted twice except the k_w = 0 and Nyquist columns)."""
     b, c, h, w = 32, 192, 64, 64
@@ -211,8 +205,7 @@ def test_fft_round_trip_full_size(math_mode):
 # ------------------------------------------------------------------------------------ conv kernel
 @pytest.mark.parametrize("math", MATHS)
 @pytest.mark.parametrize("case", ["k3_reflect", "k3_s2", "k1_two_src", "k7_nopad", "zero_border_phase", "ragged"])
-def test_conv_contract(case, math, math_mode):
-    _fp32_only(math_mode)
+def test_conv_contract(case, math):
     """ffcb_conv vs the torch restatement of its contract (packing.apply_packed_reference), covering
     reflect / zero borders, stride 2, two sources, addend before/after the activation, sub-pixel
     output phases and sizes that are not multiples of the CTA tile."""
@@ -295,12 +288,11 @@ def test_conv_contract(case, math, math_mode):
 # ------------------------------------------------------------------ channel-group planar FourierUnit chain (round 2)
 @pytest.mark.parametrize("residual", [True, False])
 @pytest.mark.parametrize("b,c", [(2, 8), (3, 24), (1, 192)])
-def test_plane_fft_pair_channel_group_planar(b, c, residual, math_mode):
+def test_plane_fft_pair_channel_group_planar(b, c, residual):
     """fft_plane_cg.cu: the 64x64 plane kernels on [C/cg][B][H][W][cg] tensors — float32 cg=4 real planes in, split
     bf16 cg=8 spectrum out (GEMM operand format); float32 cg=8 spectrum + cg=4 residual in, split bf16 cg=8 and
     float32 cg=4 real planes out.  Checker: numpy float64 (oracle/ffc_numpy.py), incl. the C2R rule on a ReLU'd
     (non-Hermitian) spectrum."""
-    _fp32_only(math_mode)
     h = w = 64
     wf = 33
     rng = np.random.default_rng(b * 100 + c)
@@ -334,10 +326,9 @@ def test_plane_fft_pair_channel_group_planar(b, c, residual, math_mode):
 
 @pytest.mark.parametrize("case", ["flat_interleaved_to_planar8", "nhwc_to_planar4", "spatial_taps_plus_interleaved",
                                   "flat_ragged_m"])
-def test_conv_tc_channel_group_planar_operands(case, math_mode):
+def test_conv_tc_channel_group_planar_operands(case):
     """conv_tc.cu with the FourierUnit chain's layouts: [K/8][pixel][8] ("interleaved", no-swizzle descriptor, 1-D
     bulk copies) A operands and channel-group planar float32 outputs, against the torch restatement of ffcb_conv."""
-    _fp32_only(math_mode)
     g = torch.Generator().manual_seed(sum(map(ord, case)))
     rn = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
     prog = E.Program("conv_cg", L.MATH_BF16X3)
@@ -451,8 +442,7 @@ def test_small_generator_golden(name, math_mode):
     assert float(np.abs(y - a["y"]).max()) < (5e-6 if math_mode == "fp32" else 1e-4)
 
 
-def test_stage_by_stage_matches_whole_program(math_mode):
-    _fp32_only(math_mode)
+def test_stage_by_stage_matches_whole_program():
     """predict_inner_features.py:84 iterates generator.model stage by stage: tuple outputs at every FFC
     stage, each stage on its own native program, same result as the fused whole-generator program."""
     a, sd = load_golden("generator_ngf8_b2_64x64")
@@ -487,8 +477,6 @@ def test_big_lama_generator_vs_oracle(size, batch, seed, math_mode):
     # 1024: 128 x 128 planes, 128-pixel-wide tiles, stride-2 boxes at the 256-element TMA limit;
     # 2048 (BASELINE config 5 resolution, plain inference): 256 x 256 planes -> 1024-thread FFT CTAs, 128 KB smem
     h, w = (size, size) if isinstance(size, int) else size
-    if math_mode == "fp32" and h * w > 512 * 512:
-        pytest.skip("large sizes are covered in the tensor-core mode only (CUDA-core arm is ~7x slower)")
     img, mask = synthetic_image_mask(batch, h, seed, width=w)
     x = generator_input(img, mask)
     with torch.no_grad():
@@ -504,18 +492,20 @@ def test_big_lama_generator_vs_oracle(size, batch, seed, math_mode):
 def test_big_lama_bs32_512_batch_independence_and_spot_oracle():
     """BASELINE config 3 (bs32, 512x512): (a) size-independent property — no cross-sample coupling
     (eval BN, per-plane FFT): images of the batch of 32 equal the same images run as a batch of 2,
-    bit for bit; (b) two images of the batch checked against the oracle."""
+    bit for bit; (b) eight seeded picks of the batch checked against the oracle (the CPU oracle needs ~0.5 s per
+    image; the other 24 are covered by (a) + the per-image independence it proves)."""
     g, sd = _big_lama(0)
     img, mask = synthetic_image_mask(32, 512, 3)
     x = generator_input(img, mask)
+    pick = sorted(torch.randperm(32, generator=torch.Generator().manual_seed(11))[:8].tolist())
     with torch.no_grad():
         y32 = g(x.to(DEV)).cpu()
-        pick = [5, 31]
-        y2 = g(x[pick].contiguous().to(DEV)).cpu()
+        y2 = torch.cat([g(x[pick[i:i + 2]].contiguous().to(DEV)).cpu() for i in range(0, 8, 2)])
         ref = otc.ffc_resnet_generator(x[pick], sd, **BIG_LAMA_KWARGS)
     assert torch.equal(y32[pick], y2), "batch coupling: results depend on batch composition"
     assert torch.isfinite(y32).all() and float(y32.min()) >= 0.0 and float(y32.max()) <= 1.0
-    assert float((y32[pick] - ref).abs().max()) < 1e-3
+    err = float((y32[pick] - ref).abs().max())
+    assert err < 3e-4, f"bs32 512x512 vs oracle on 8 images: {err:.3e}"
 
 
 def test_inpaint_glue_matches_oracle(math_mode):
@@ -532,8 +522,7 @@ def test_inpaint_glue_matches_oracle(math_mode):
     assert torch.equal(inp[(1 - mask).expand_as(inp).bool()], img[(1 - mask).expand_as(img).bool()])
 
 
-def test_errors_are_loud(math_mode):
-    _fp32_only(math_mode)
+def test_errors_are_loud():
     lib = L.get_lib()
     d = L.ConvDesc()
     with pytest.raises(ValueError):
@@ -597,16 +586,18 @@ def test_baseline_config1_resnet_block_bs8(math_mode):
 
 
 # ------------------------------------------------------------------- predict path, uint8 I/O
-def _u8_only(mode):
-    if mode != "bf16x3":
-        pytest.skip("the uint8 front / back end exists on the tensor-core arm only")
+@pytest.fixture
+def tc_math():
+    """The uint8 front / back end exists on the tensor-core arm only: run those tests once, in that mode."""
+    os.environ["LAMA_B200_MATH"] = "bf16x3"
+    yield "bf16x3"
+    os.environ.pop("LAMA_B200_MATH", None)
 
 
-def test_predict_u8_bytes_match_reference_fixture(math_mode):
+def test_predict_u8_bytes_match_reference_fixture(tc_math):
     """lama_b200.predict.BatchedInpainter (decode-to-bytes fused path) against the bytes the reference pipeline
     produced (tests/golden/predict_ngf8_3x45x52.npz: InpaintingDataset + generator + blend + x255/uint8).
     45x52 images: symmetric padding to 48x56, 6x7 non-power-of-two FFT planes, a full and a partial batch."""
-    _u8_only(math_mode)
     from lama_b200.predict import BatchedInpainter
     a, _ = load_golden("predict_ngf8_3x45x52")
     _, sd = load_golden("generator_ngf8_b2_64x64")
@@ -622,10 +613,9 @@ def test_predict_u8_bytes_match_reference_fixture(math_mode):
 
 
 @pytest.mark.parametrize("h0,w0,b", [(100, 75, 2), (64, 64, 3)])
-def test_predict_u8_equals_float_program_plus_reference_glue(math_mode, h0, w0, b):
+def test_predict_u8_equals_float_program_plus_reference_glue(tc_math, h0, w0, b):
     """The fused byte path and the float program share every kernel in between, so the bytes must be IDENTICAL to
     the reference's elementwise glue (oracle/predict_numpy.py) wrapped around the native float generator call."""
-    _u8_only(math_mode)
     from lama_b200.predict import BatchedInpainter
     from oracle import predict_numpy as opn
     _, sd = load_golden("generator_ngf8_b2_64x64")
@@ -650,8 +640,7 @@ def test_predict_u8_equals_float_program_plus_reference_glue(math_mode, h0, w0, 
         assert np.array_equal(outs[i], opn.finish(pi, ii, mi, h0, w0)[0])
 
 
-def test_predict_u8_abi_rejects_bad_arguments(math_mode):
-    _fp32_only(math_mode)
+def test_predict_u8_abi_rejects_bad_arguments():
     lib = L.get_lib()
     t = torch.zeros(2, 1, 22, 24, 8, dtype=torch.bfloat16, device=DEV)          # packed view for a 16x16 image
     pk = L.Tensor(t.data_ptr(), 22 * 24 * 8, 24 * 8, 8, 22 * 24 * 8, 1, 22, 24, 8, L.BF16X2, 0, 0, 0)

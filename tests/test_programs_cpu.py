@@ -165,8 +165,8 @@ def test_tc_incompatible_program_downgrades_to_fp32():
 
 
 def test_weights_signature_tracks_changes_cheaply():
-    """Programs are rebuilt when weights change (load_state_dict / in-place edits / replaced parameters); the
-    per-call check uses a cached flat tensor list (the module walk alone costs as much as a bs1 forward)."""
+    """Programs are rebuilt when weights change: load_state_dict, in-place edits, replaced parameters AND edits
+    through ``.data`` (the reference's EMA update, trainers/base.py:40, leaves ``_version`` alone)."""
     m = M.FFC_BN_ACT(16, 16, 3, 0.5, 0.5, padding=1, enable_lfu=False).eval()
     s0 = E._weights_signature(m)
     assert E._weights_signature(m) == s0
@@ -177,9 +177,40 @@ def test_weights_signature_tracks_changes_cheaply():
     m.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})
     s2 = E._weights_signature(m)
     assert s2 != s1
-    m.ffc.convl2l.weight = torch.nn.Parameter(m.ffc.convl2l.weight.detach().clone())   # replaced object
-    sigs = [E._weights_signature(m) for _ in range(E._REWALK_EVERY + 1)]
-    assert sigs[-1] != s2                                   # noticed at the latest after the periodic re-walk
+    v = m.ffc.convl2l.weight._version
+    m.ffc.convl2l.weight.data.mul_(0.999).add_(0.001)       # EMA-style edit: same pointer, same version
+    assert m.ffc.convl2l.weight._version == v
+    s3 = E._weights_signature(m)
+    assert s3 != s2 and s3[:-1] == s2[:-1]                  # only the content checksum moved
+    m.ffc.convl2l.weight = torch.nn.Parameter(m.ffc.convl2l.weight.detach().clone() * 2)   # replaced object
+    assert E._weights_signature(m) != s3
+    big = M.FFCResNetGenerator(**small_lama_kwargs(ngf=8, n_blocks=2)).eval()              # > _SMALL_MODULE tensors
+    b0 = E._weights_signature(big)
+    big.model[1].ffc.convl2l.weight = torch.nn.Parameter(big.model[1].ffc.convl2l.weight.detach().clone() + 1)
+    sigs = [E._weights_signature(big) for _ in range(E._REWALK_EVERY + 1)]
+    assert sigs[-1] != b0                                   # at the latest after the periodic re-walk
+    E.invalidate(big)
+    assert big not in E._PROGRAMS and big not in E._TENSORS
+
+
+def test_modules_stay_copyable_and_picklable_after_native_use():
+    """The executor caches hold ctypes pointers; they live in weak-keyed dictionaries outside the module, so the
+    reference's ``copy.deepcopy(self.generator)`` (trainers/base.py:168), ``torch.save(module)`` and pickling keep
+    working after a native forward."""
+    import copy
+    import ctypes
+    import io
+    import pickle
+    g = M.FFCResNetGenerator(**small_lama_kwargs(ngf=8, n_blocks=1)).eval()
+    fake = (ctypes.c_void_p(1), ctypes.byref(ctypes.c_int(3)))          # what a CudaExecutor keeps alive
+    E._PROGRAMS.setdefault(g, {})[("generator", ((1, 4, 64, 64),), "cuda:0", 1)] = (E._weights_signature(g), fake)
+    assert not any(k.startswith("_ffcb") for k in g.__dict__)
+    g2 = copy.deepcopy(g)
+    assert g2 not in E._PROGRAMS
+    pickle.loads(pickle.dumps(g))
+    buf = io.BytesIO()
+    torch.save(g, buf)
+    E.invalidate(g)
 
 
 def test_generator_u8_program_matches_reference_predict_bytes():
