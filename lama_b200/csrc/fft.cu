@@ -386,7 +386,7 @@ int rfft2(const ffcb_tensor* in, const ffcb_tensor* spec, void* ws, size_t ws_by
   if (in->B == 0 || in->C == 0) return FFCB_OK;
   if (in->cg != 0 || spec->cg != 0) {
     FFCB_REQUIRE(plane64_cg_fwd_eligible(in, spec),
-                 "rfft2: channel-group planar views need a 64x64 float32 cg=4 input and a split-bf16 cg=8 spectrum");
+                 "rfft2: channel-group planar views need a 64x64 / 32x32 float32 cg=4 input and a split-bf16 cg=8 spectrum");
     return rfft2_plane64_cg(in, spec, stream);
   }
   if (plane64_eligible(in) && !getenv("FFCB_FFT_TWO_PASS")) return rfft2_plane64(in, spec, stream);
@@ -436,7 +436,7 @@ int irfft2(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tens
   if (out->B == 0 || out->C == 0) return FFCB_OK;
   if (spec->cg != 0 || out->cg != 0 || (residual && residual->ptr && residual->cg != 0)) {
     FFCB_REQUIRE(plane64_cg_inv_eligible(spec, residual, out),
-                 "irfft2: channel-group planar views need a 64x64 plane, a float32 cg=8 spectrum, a float32 cg=4 "
+                 "irfft2: channel-group planar views need a 64x64 / 32x32 plane, a float32 cg=8 spectrum, a float32 cg=4 "
                  "residual and a split-bf16 cg=8 or float32 cg=4 output");
     return irfft2_plane64_cg(spec, residual, out, stream);
   }

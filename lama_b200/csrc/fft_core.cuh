@@ -273,6 +273,43 @@ FFCB_HD void fft64_regs(float2* v) {
 }
 
 
+// 32-point complex FFT in registers, same construction: n = 8a + b (a < 4, b < 8); FFT4 over a, twiddle w32^(b c), FFT8
+// over b.  X[k], k = c + 4d, is left in v[8c + d]  (fft32_at()).
+FFCB_HD int fft32_at(int k) { return 8 * (k & 3) + (k >> 2); }
+
+template <bool INV>
+FFCB_HD void fft32_regs(float2* v) {
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    float2 t0 = v[b], t1 = v[8 + b], t2 = v[16 + b], t3 = v[24 + b];
+    fft4<INV>(t0, t1, t2, t3);
+    const float2 t[4] = {t0, t1, t2, t3};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float2 y = t[c];
+      if (b * c != 0) {
+        float2 w = tw64((2 * b * c) & 63);      // w32^(bc) = w64^(2bc)
+        if (INV) w.y = -w.y;
+        y = cmul(y, w);
+      }
+      v[8 * c + b] = y;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) fft8<INV>(v + 8 * c);
+}
+
+// length-generic access to the register transforms (N = 32 or 64)
+template <int N> struct RegFft;
+template <> struct RegFft<64> {
+  template <bool INV> static FFCB_HD void run(float2* v) { fft64_regs<INV>(v); }
+  static FFCB_HD int at(int k) { return fft64_at(k); }
+};
+template <> struct RegFft<32> {
+  template <bool INV> static FFCB_HD void run(float2* v) { fft32_regs<INV>(v); }
+  static FFCB_HD int at(int k) { return fft32_at(k); }
+};
+
 // Per-thread steps of the fused 64x64 plane kernels (fft_plane.cu); functors keep them host-testable.
 //   rows forward : z[n] = (row_a[n], row_b[n]) -> half spectra A[k], B[k], k = 0..32 (two-for-one)
 //   columns      : 64-point complex transform of one (kx, channel) column, natural order in and out

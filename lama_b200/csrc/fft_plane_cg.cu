@@ -1,4 +1,4 @@
-// 64x64 plane FFT pair on channel-group planar tensors (include/ffc_b200.h: ffcb_tensor.cg) — the FourierUnit of the
+// 64x64 (and 32x32) plane FFT pair on channel-group planar tensors (include/ffc_b200.h: ffcb_tensor.cg) — the FourierUnit of the
 // 512x512 bottleneck, second generation.
 //
 // Round 1's plane kernels (fft_plane.cu) work on channels-last tensors: one 137 KB CTA per SM transforms 8 channels,
@@ -46,33 +46,37 @@ __device__ __forceinline__ void split_pair(float a, float b, unsigned& hi, unsig
   lo = *reinterpret_cast<const unsigned*>(&l);
 }
 
-// grid: (C/4, B).  blockIdx.x = 4-channel group of the real input = 8-channel (4 complex) group of the spectrum.
-__global__ void __launch_bounds__(kCgThreads, 3) rfft2_plane64_cg_kernel(CgArgs a) {
-  extern __shared__ __align__(16) float smem[];
+// grid: (C/4/sets, B).  A plane set = 4-channel group of the real input = 8-channel (4 complex) group of the spectrum.
+template <int N>
+__global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) rfft2_plane_cg_kernel(CgArgs a) {
+  using Cfg = CgCfg<N>;
+  extern __shared__ __align__(16) float smem_all[];
+  const int set = threadIdx.x / Cfg::set_threads, tid = threadIdx.x % Cfg::set_threads;
+  const int group = blockIdx.x * Cfg::sets + set;
+  float* smem = smem_all + set * Cfg::set_floats;
   float2* S = reinterpret_cast<float2*>(smem);
-  const int tid = threadIdx.x;
   {   // plane set -> shared memory (real layout), 16 bytes per pixel, lanes along x
-    const float* src = a.in + (long long)blockIdx.x * a.in_sg + (long long)blockIdx.y * a.in_sb;
+    const float* src = a.in + (long long)group * a.in_sg + (long long)blockIdx.y * a.in_sb;
     const uint32_t base = smem_addr(smem);
 #pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < Cfg::px_iters; ++i) {
       int y, x;
-      cg_pixel_slot(tid, i, y, x);
-      cp_async16(base + 4u * (unsigned)cg_real_idx(y, x, 0), src + ((unsigned)y * a.in_sy + (unsigned)x * a.in_sx));
+      cg_pixel_slot<N>(tid, i, y, x);
+      cp_async16(base + 4u * (unsigned)cg_real_idx<N>(y, x, 0), src + ((unsigned)y * a.in_sy + (unsigned)x * a.in_sx));
     }
     cp_async_wait_all();
   }
   __syncthreads();
-  cg_fwd_rows(
+  cg_fwd_rows<N>(
       tid, [&](int i) { return *reinterpret_cast<const float2*>(smem + i); }, [&]() { __syncwarp(); },
       [&](int i2, float4 v) { *reinterpret_cast<float4*>(S + i2) = v; });
   __syncthreads();
   {
-    unsigned short* hi = reinterpret_cast<unsigned short*>(a.spec) + (long long)blockIdx.x * a.sp_sg +
+    unsigned short* hi = reinterpret_cast<unsigned short*>(a.spec) + (long long)group * a.sp_sg +
                          (long long)blockIdx.y * a.sp_sb;
     unsigned short* lo = hi + a.sp_lo;
     const float scale = a.scale;
-    cg_fwd_cols(
+    cg_fwd_cols<N>(
         tid, [&](int i2) { return S[i2]; },
         [&](int ky, int kx, int c, float2 z) {
           const unsigned o = (unsigned)ky * a.sp_sy + (unsigned)kx * a.sp_sx + 2u * (unsigned)c;
@@ -84,16 +88,19 @@ __global__ void __launch_bounds__(kCgThreads, 3) rfft2_plane64_cg_kernel(CgArgs 
   }
 }
 
-// grid: (C/4, B) over the REAL output's 4-channel groups; spectrum group = blockIdx.x (4 complex = 8 floats).
-template <bool HAS_RES, bool OUT_SPLIT>
-__global__ void __launch_bounds__(kCgThreads, 3) irfft2_plane64_cg_kernel(CgArgs a) {
-  extern __shared__ __align__(16) float smem[];
+// grid: (C/4/sets, B) over the REAL output's 4-channel groups; spectrum group = the same index (4 complex = 8 floats).
+template <int N, bool HAS_RES, bool OUT_SPLIT>
+__global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) irfft2_plane_cg_kernel(CgArgs a) {
+  using Cfg = CgCfg<N>;
+  extern __shared__ __align__(16) float smem_all[];
+  const int set = threadIdx.x / Cfg::set_threads, tid = threadIdx.x % Cfg::set_threads;
+  const int group = blockIdx.x * Cfg::sets + set;
+  float* smem = smem_all + set * Cfg::set_floats;
   float2* S = reinterpret_cast<float2*>(smem);
-  const int tid = threadIdx.x;
   {
-    const float* sp = reinterpret_cast<const float*>(a.spec) + (long long)blockIdx.x * a.sp_sg +
+    const float* sp = reinterpret_cast<const float*>(a.spec) + (long long)group * a.sp_sg +
                       (long long)blockIdx.y * a.sp_sb + 2 * (tid & 3);
-    cg_inv_cols(
+    cg_inv_cols<N>(
         tid,
         [&](int ky, int kx) {
           return __ldg(reinterpret_cast<const float2*>(sp + ((unsigned)ky * a.sp_sy + (unsigned)kx * a.sp_sx)));
@@ -101,34 +108,34 @@ __global__ void __launch_bounds__(kCgThreads, 3) irfft2_plane64_cg_kernel(CgArgs
         [&](int i2, float2 z) { S[i2] = z; });
   }
   __syncthreads();
-  cg_inv_rows(
+  cg_inv_rows<N>(
       tid, [&](int i2) { return *reinterpret_cast<const float4*>(S + i2); }, [&]() { __syncwarp(); },
       [&](int i, float2 z) { *reinterpret_cast<float2*>(smem + i) = z; });
   __syncthreads();
   {   // epilogue: whole pixels (4 channels), lanes along x: + residual, scale, convert, store
-    const float* res = HAS_RES ? a.in + (long long)blockIdx.x * a.in_sg + (long long)blockIdx.y * a.in_sb : nullptr;
+    const float* res = HAS_RES ? a.in + (long long)group * a.in_sg + (long long)blockIdx.y * a.in_sb : nullptr;
     const float scale = a.scale;
-#pragma unroll 4
-    for (int i0 = 0; i0 < 32; i0 += 8) {
+#pragma unroll 2
+    for (int i0 = 0; i0 < Cfg::px_iters; i0 += 8) {
       float4 q[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         int y, x;
-        cg_pixel_slot(tid, i0 + j, y, x);
+        cg_pixel_slot<N>(tid, i0 + j, y, x);
         q[j] = HAS_RES ? __ldg(reinterpret_cast<const float4*>(res + ((unsigned)y * a.in_sy + (unsigned)x * a.in_sx)))
                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         int y, x;
-        cg_pixel_slot(tid, i0 + j, y, x);
-        const float4 v = *reinterpret_cast<const float4*>(smem + cg_real_idx(y, x, 0));
+        cg_pixel_slot<N>(tid, i0 + j, y, x);
+        const float4 v = *reinterpret_cast<const float4*>(smem + cg_real_idx<N>(y, x, 0));
         const float r0 = fmaf(v.x, scale, q[j].x), r1 = fmaf(v.y, scale, q[j].y);
         const float r2 = fmaf(v.z, scale, q[j].z), r3 = fmaf(v.w, scale, q[j].w);
         if constexpr (OUT_SPLIT) {
-          // out is cg = 8: this CTA's four channels are one half (8 bytes per plane) of the 16-byte pixel granule
-          unsigned short* hi = reinterpret_cast<unsigned short*>(a.out) + (long long)(blockIdx.x >> 1) * a.out_sg +
-                               (long long)blockIdx.y * a.out_sb + 4 * (blockIdx.x & 1);
+          // out is cg = 8: this plane set's four channels are one half (8 bytes per plane) of the 16-byte pixel granule
+          unsigned short* hi = reinterpret_cast<unsigned short*>(a.out) + (long long)(group >> 1) * a.out_sg +
+                               (long long)blockIdx.y * a.out_sb + 4 * (group & 1);
           const unsigned o = (unsigned)y * a.out_sy + (unsigned)x * a.out_sx;
           unsigned h0, l0, h1, l1;
           split_pair(r0, r1, h0, l0);
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(kCgThreads, 3) irfft2_plane64_cg_kernel(CgArgs
           *reinterpret_cast<uint2*>(hi + o) = make_uint2(h0, h1);
           *reinterpret_cast<uint2*>(hi + a.out_lo + o) = make_uint2(l0, l1);
         } else {
-          float* op = reinterpret_cast<float*>(a.out) + (long long)blockIdx.x * a.out_sg +
+          float* op = reinterpret_cast<float*>(a.out) + (long long)group * a.out_sg +
                       (long long)blockIdx.y * a.out_sb + ((unsigned)y * a.out_sy + (unsigned)x * a.out_sx);
           *reinterpret_cast<float4*>(op) = make_float4(r0, r1, r2, r3);
         }
@@ -147,8 +154,11 @@ __global__ void __launch_bounds__(kCgThreads, 3) irfft2_plane64_cg_kernel(CgArgs
 
 bool offsets_fit(const ffcb_tensor* t) { return t->sy > 0 && t->sx > 0 && 64 * t->sy + 64 * t->sx < (1LL << 31); }
 
+// plane sizes with a register transform: 64x64 (512x512 images) and 32x32 (256x256); two 32x32 plane sets share a CTA
+bool plane_ok(int h, int w, int c) { return (h == 64 && w == 64) || (h == 32 && w == 32 && c % 8 == 0); }
+
 bool real_cg4(const ffcb_tensor* t) {
-  return t->cg == 4 && t->fmt == FFCB_F32 && t->H == 64 && t->W == 64 && t->sx % 4 == 0 && t->sy % 4 == 0 &&
+  return t->cg == 4 && t->fmt == FFCB_F32 && plane_ok(t->H, t->W, t->C) && t->sx % 4 == 0 && t->sy % 4 == 0 &&
          t->sb % 4 == 0 && t->sg % 4 == 0 && ((uintptr_t)t->ptr % 16) == 0 && offsets_fit(t) && t->B <= 65535;
 }
 
@@ -163,7 +173,7 @@ bool plane64_cg_fwd_eligible(const ffcb_tensor* in, const ffcb_tensor* spec) {
 
 bool plane64_cg_inv_eligible(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out) {
   if (!(spec->cg == 8 && spec->fmt == FFCB_F32 && spec->sx % 2 == 0 && spec->sy % 2 == 0 && spec->sb % 2 == 0 &&
-        spec->sg % 2 == 0 && ((uintptr_t)spec->ptr % 8) == 0 && offsets_fit(spec) && out->H == 64 && out->W == 64 &&
+        spec->sg % 2 == 0 && ((uintptr_t)spec->ptr % 8) == 0 && offsets_fit(spec) && plane_ok(out->H, out->W, out->C) &&
         out->B <= 65535))
     return false;
   if (residual && residual->ptr && !real_cg4(residual)) return false;
@@ -173,27 +183,44 @@ bool plane64_cg_inv_eligible(const ffcb_tensor* spec, const ffcb_tensor* residua
   return real_cg4(out);
 }
 
+template <int N>
+static int launch_fwd_cg(const CgArgs& a, int groups, int batch, cudaStream_t stream) {
+  using Cfg = CgCfg<N>;
+  FFCB_CUDA(cudaFuncSetAttribute(rfft2_plane_cg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes));
+  dim3 grid(groups / Cfg::sets, batch);
+  rfft2_plane_cg_kernel<N><<<grid, kCgThreads, Cfg::smem_bytes, stream>>>(a);
+  FFCB_LAUNCH_CHECK("rfft2_plane_cg_kernel");
+  return FFCB_OK;
+}
+
 int rfft2_plane64_cg(const ffcb_tensor* in, const ffcb_tensor* spec, cudaStream_t stream) {
   CgArgs a{};
   a.in = reinterpret_cast<const float*>(in->ptr);
   a.in_sg = in->sg; a.in_sb = in->sb; a.in_sy = (unsigned)in->sy; a.in_sx = (unsigned)in->sx;
   a.spec = spec->ptr; a.sp_sg = spec->sg; a.sp_sb = spec->sb; a.sp_sy = (unsigned)spec->sy; a.sp_sx = (unsigned)spec->sx;
   a.sp_lo = spec->lo_off;
-  a.scale = 1.0f / 64.0f;
-  FFCB_CUDA(cudaFuncSetAttribute(rfft2_plane64_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCgSmemBytes));
-  dim3 grid(in->C / 4, in->B);
-  rfft2_plane64_cg_kernel<<<grid, kCgThreads, kCgSmemBytes, stream>>>(a);
-  FFCB_LAUNCH_CHECK("rfft2_plane64_cg_kernel");
+  a.scale = 1.0f / (float)in->H;
+  return in->H == 64 ? launch_fwd_cg<64>(a, in->C / 4, in->B, stream) : launch_fwd_cg<32>(a, in->C / 4, in->B, stream);
+}
+
+template <int N, bool HAS_RES, bool OUT_SPLIT>
+static int launch_inv_cg(const CgArgs& a, int groups, int batch, cudaStream_t stream) {
+  using Cfg = CgCfg<N>;
+  FFCB_CUDA(cudaFuncSetAttribute(irfft2_plane_cg_kernel<N, HAS_RES, OUT_SPLIT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes));
+  dim3 grid(groups / Cfg::sets, batch);
+  irfft2_plane_cg_kernel<N, HAS_RES, OUT_SPLIT><<<grid, kCgThreads, Cfg::smem_bytes, stream>>>(a);
+  FFCB_LAUNCH_CHECK("irfft2_plane_cg_kernel");
   return FFCB_OK;
 }
 
-template <bool HAS_RES, bool OUT_SPLIT>
-static int launch_inv_cg(const CgArgs& a, dim3 grid, cudaStream_t stream) {
-  FFCB_CUDA(cudaFuncSetAttribute(irfft2_plane64_cg_kernel<HAS_RES, OUT_SPLIT>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kCgSmemBytes));
-  irfft2_plane64_cg_kernel<HAS_RES, OUT_SPLIT><<<grid, kCgThreads, kCgSmemBytes, stream>>>(a);
-  FFCB_LAUNCH_CHECK("irfft2_plane64_cg_kernel");
-  return FFCB_OK;
+template <int N>
+static int dispatch_inv_cg(const CgArgs& a, int groups, int batch, bool has_res, bool split, cudaStream_t stream) {
+  if (has_res)
+    return split ? launch_inv_cg<N, true, true>(a, groups, batch, stream)
+                 : launch_inv_cg<N, true, false>(a, groups, batch, stream);
+  return split ? launch_inv_cg<N, false, true>(a, groups, batch, stream)
+               : launch_inv_cg<N, false, false>(a, groups, batch, stream);
 }
 
 int irfft2_plane64_cg(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out,
@@ -207,11 +234,10 @@ int irfft2_plane64_cg(const ffcb_tensor* spec, const ffcb_tensor* residual, cons
   a.spec = spec->ptr; a.sp_sg = spec->sg; a.sp_sb = spec->sb; a.sp_sy = (unsigned)spec->sy; a.sp_sx = (unsigned)spec->sx;
   a.out = out->ptr; a.out_sg = out->sg; a.out_sb = out->sb; a.out_sy = (unsigned)out->sy; a.out_sx = (unsigned)out->sx;
   a.out_lo = out->lo_off;
-  a.scale = 1.0f / 64.0f;
-  dim3 grid(out->C / 4, out->B);
+  a.scale = 1.0f / (float)out->H;
   const bool split = out->fmt == FFCB_BF16X2;
-  if (has_res) return split ? launch_inv_cg<true, true>(a, grid, stream) : launch_inv_cg<true, false>(a, grid, stream);
-  return split ? launch_inv_cg<false, true>(a, grid, stream) : launch_inv_cg<false, false>(a, grid, stream);
+  return out->H == 64 ? dispatch_inv_cg<64>(a, out->C / 4, out->B, has_res, split, stream)
+                      : dispatch_inv_cg<32>(a, out->C / 4, out->B, has_res, split, stream);
 }
 
 }  // namespace ffcb

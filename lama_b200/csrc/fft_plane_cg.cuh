@@ -20,55 +20,69 @@
 namespace ffcb {
 namespace fftc {
 
+// The same construction serves N x N planes for N = 64 (one plane set per 128-thread CTA, 64 KB) and N = 32 (the
+// 256x256 bottleneck: a plane set is 16 KB and 64 tasks per pass, so a CTA carries two of them).  Row pitch = 4N floats
+// = 2N float2; the XOR swizzles only touch the low three (two) bits of the pixel (slot) index, the bank analysis is
+// the same for both sizes.
 constexpr int kCgThreads = 128;
-constexpr int kCgSmemBytes = 64 * 64 * 4 * 4;      // 64 KB
+template <int N> struct CgCfg {
+  static constexpr int set_threads = 2 * N;                   // tasks per pass of one plane set
+  static constexpr int sets = kCgThreads / set_threads;       // plane sets per CTA (1 or 2)
+  static constexpr int set_floats = N * N * 4;
+  static constexpr int smem_bytes = sets * set_floats * 4;
+  static constexpr int px_iters = N * N / set_threads;        // pixels per thread in the load / store loops
+  static constexpr int ctas_per_sm = N == 64 ? 3 : 4;      // register-limited: 168 / 128 per thread
+};
+constexpr int kCgSmemBytes = CgCfg<64>::smem_bytes;      // 64 KB
 
-FFCB_HD int cg_real_idx(int y, int x, int c) { return y * 256 + ((x ^ (y & 7)) << 2) + c; }          // float index
-FFCB_HD int cg_cplx_idx(int y, int k, int c) { return y * 128 + ((k ^ (y & 3)) << 2) + c; }          // float2 index
+template <int N> FFCB_HD int cg_real_idx(int y, int x, int c) { return y * (4 * N) + ((x ^ (y & 7)) << 2) + c; }   // float index
+template <int N> FFCB_HD int cg_cplx_idx(int y, int k, int c) { return y * (2 * N) + ((k ^ (y & 3)) << 2) + c; }   // float2 index
 
 // ---- forward, row pass: R (real, two channels of row y) -> Sx (half spectra of both channels, packed slot 0)
 // `load`: callable(float index) -> float2 (two consecutive floats); `sync`: hand-over between reads and writes;
 // `store`: callable(float2 index, float4) writing two consecutive float2
-template <class Load, class Sync, class Store>
+template <int N, class Load, class Sync, class Store>
 FFCB_HD void cg_fwd_rows(int tid, Load&& ld2, Sync&& sync, Store&& st4) {
+  using F = RegFft<N>;
   const int cp = tid & 1, y = tid >> 1;
-  float2 v[64];
+  float2 v[N];
 #pragma unroll
-  for (int x = 0; x < 64; ++x) v[x] = ld2(cg_real_idx(y, x, 2 * cp));
+  for (int x = 0; x < N; ++x) v[x] = ld2(cg_real_idx<N>(y, x, 2 * cp));
   sync();
-  fft64_regs<false>(v);
+  F::template run<false>(v);
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const float2 zk = v[fft64_at(k)], zm = v[fft64_at((64 - k) & 63)];
+  for (int k = 0; k < N / 2; ++k) {
+    const float2 zk = v[F::at(k)], zm = v[F::at((N - k) & (N - 1))];
     float2 a = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));      // spectrum of channel 2cp
     float2 b = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));     // spectrum of channel 2cp+1
     if (k == 0) {
-      const float2 zn = v[fft64_at(32)];                                     // Nyquist bin: (Re A[32], Re B[32])
+      const float2 zn = v[F::at(N / 2)];                                     // Nyquist bin: (Re A[N/2], Re B[N/2])
       a = make_float2(zk.x, zn.x);
       b = make_float2(zk.y, zn.y);
     }
-    st4(cg_cplx_idx(y, k, 2 * cp), make_float4(a.x, a.y, b.x, b.y));
+    st4(cg_cplx_idx<N>(y, k, 2 * cp), make_float4(a.x, a.y, b.x, b.y));
   }
 }
 
 // ---- forward, column pass: Sx column (kx, c) -> spectrum values (ky, kx) [and (ky, 32) for the packed task kx = 0]
 // `emit(ky, kx, value)`: the caller scales and stores
-template <class Load, class Emit>
+template <int N, class Load, class Emit>
 FFCB_HD void cg_fwd_cols(int tid, Load&& ld, Emit&& emit) {
+  using F = RegFft<N>;
   const int c = tid & 3, kx = tid >> 2;
   const bool packed = kx == 0;
-  float2 v[64];
+  float2 v[N];
 #pragma unroll
-  for (int y = 0; y < 64; ++y) v[y] = ld(cg_cplx_idx(y, kx, c));
-  fft64_regs<false>(v);
+  for (int y = 0; y < N; ++y) v[y] = ld(cg_cplx_idx<N>(y, kx, c));
+  F::template run<false>(v);
 #pragma unroll
-  for (int k = 0; k < 64; ++k) {
-    const float2 wk = v[fft64_at(k)], wm = v[fft64_at((64 - k) & 63)];
+  for (int k = 0; k < N; ++k) {
+    const float2 wk = v[F::at(k)], wm = v[F::at((N - k) & (N - 1))];
     // packed: v = X0 + i X32 with both columns real -> Hermitian split
     const float2 x0 = make_float2(0.5f * (wk.x + wm.x), 0.5f * (wk.y - wm.y));
     const float2 x32 = make_float2(0.5f * (wk.y + wm.y), -0.5f * (wk.x - wm.x));
     emit(k, kx, c, packed ? x0 : wk);
-    if (packed) emit(k, 32, c, x32);
+    if (packed) emit(k, N / 2, c, x32);
   }
 }
 
@@ -76,60 +90,63 @@ FFCB_HD void cg_fwd_cols(int tid, Load&& ld, Emit&& emit) {
 // The packed task (kx = 0) transforms Herm(Z[.,0]) + i Herm(Z[.,32]) whose inverse is Re(ifft Z0) + i Re(ifft Z32):
 // exactly the packed slot the row pass wants (C2R: imaginary parts of bins 0 and 32 are ignored after the H inverse).
 // `ld(ky, kx)`: spectrum value of this task's channel; `st(float2 index, value)`
-template <class Load, class Store>
+template <int N, class Load, class Store>
 FFCB_HD void cg_inv_cols(int tid, Load&& ld, Store&& st) {
+  using F = RegFft<N>;
   const int c = tid & 3, kx = tid >> 2;
   const bool packed = kx == 0;
-  float2 v[64];
+  float2 v[N];
 #pragma unroll
-  for (int k = 0; k < 64; ++k) v[k] = ld(k, kx);
+  for (int k = 0; k < N; ++k) v[k] = ld(k, kx);
 #pragma unroll
-  for (int k = 0; k <= 32; ++k) {
-    const int m = (64 - k) & 63;
+  for (int k = 0; k <= N / 2; ++k) {
+    const int m = (N - k) & (N - 1);
     const float2 a = v[k], b = v[m];
     float2 cc = make_float2(0.f, 0.f), d = make_float2(0.f, 0.f);
     if (packed) {
-      cc = ld(k, 32);
-      d = (m != k) ? ld(m, 32) : cc;
+      cc = ld(k, N / 2);
+      d = (m != k) ? ld(m, N / 2) : cc;
     }
     const float2 h0 = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
     const float2 h32 = make_float2(0.5f * (cc.x + d.x), 0.5f * (cc.y - d.y));
     v[k] = packed ? make_float2(h0.x - h32.y, h0.y + h32.x) : a;
     if (m != k) v[m] = packed ? make_float2(h0.x + h32.y, h32.x - h0.y) : b;
   }
-  fft64_regs<true>(v);
+  F::template run<true>(v);
 #pragma unroll
-  for (int y = 0; y < 64; ++y) st(cg_cplx_idx(y, kx, c), v[fft64_at(y)]);
+  for (int y = 0; y < N; ++y) st(cg_cplx_idx<N>(y, kx, c), v[F::at(y)]);
 }
 
 // ---- inverse, row pass: Sx row y (both channels of pair cp) -> R[y][x][2cp..2cp+1]   (C2R along W, unnormalised)
 // `ld4(float2 index)` -> float4 = two consecutive float2 (X1[k], X2[k]); `st2(float index, float2)`
-template <class Load, class Sync, class Store>
+template <int N, class Load, class Sync, class Store>
 FFCB_HD void cg_inv_rows(int tid, Load&& ld4, Sync&& sync, Store&& st2) {
+  using F = RegFft<N>;
   const int cp = tid & 1, y = tid >> 1;
-  float2 v[64];
+  float2 v[N];
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const float4 q = ld4(cg_cplx_idx(y, k, 2 * cp));
+  for (int k = 0; k < N / 2; ++k) {
+    const float4 q = ld4(cg_cplx_idx<N>(y, k, 2 * cp));
     if (k == 0) {
-      v[0] = make_float2(q.x, q.z);          // (Re X1[0], Re X2[0])
-      v[32] = make_float2(q.y, q.w);         // (Re X1[32], Re X2[32])
+      v[0] = make_float2(q.x, q.z);              // (Re X1[0], Re X2[0])
+      v[N / 2] = make_float2(q.y, q.w);          // (Re X1[N/2], Re X2[N/2])
     } else {
       v[k] = make_float2(q.x - q.w, q.y + q.z);            // X1 + i X2
-      v[64 - k] = make_float2(q.x + q.w, q.z - q.y);       // conj(X1) + i conj(X2)
+      v[N - k] = make_float2(q.x + q.w, q.z - q.y);        // conj(X1) + i conj(X2)
     }
   }
   sync();
-  fft64_regs<true>(v);
+  F::template run<true>(v);
 #pragma unroll
-  for (int x = 0; x < 64; ++x) st2(cg_real_idx(y, x, 2 * cp), v[fft64_at(x)]);
+  for (int x = 0; x < N; ++x) st2(cg_real_idx<N>(y, x, 2 * cp), v[F::at(x)]);
 }
 
-// pixel handled by thread `tid` in iteration i (0..31) of the load / store loops: lanes run along x
+// pixel handled by task `tid` (0 .. 2N-1 within its plane set) in iteration i of the load / store loops: lanes run along x
+template <int N>
 FFCB_HD void cg_pixel_slot(int tid, int i, int& y, int& x) {
-  const int p = i * kCgThreads + tid;
-  y = p >> 6;
-  x = p & 63;
+  const int p = i * CgCfg<N>::set_threads + tid;
+  y = p / N;
+  x = p % N;
 }
 
 }  // namespace fftc

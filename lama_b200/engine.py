@@ -389,14 +389,14 @@ def fu_batch_chunk(batch: int, h: int, w: int, c: int) -> int:
 def fu_planar_ok(prog: Program, st, h: int, w: int) -> bool:
     """Channel-group planar storage for the SpectralTransform chain (conv1 -> rfft2 -> spectral conv -> irfft2 ->
     conv2): every (image, 4-channel group) plane set is one dense block for the second-generation plane FFT kernels
-    (csrc/fft_plane_cg.cu) and the GEMMs read [K/8][pixel][8] operand tiles.  Needs the tcgen05 arm, 64x64 planes
-    (the 512x512 bottleneck) and whole 64-channel K blocks on every contraction of the chain.
+    (csrc/fft_plane_cg.cu) and the GEMMs read [K/8][pixel][8] operand tiles.  Needs the tcgen05 arm, 64x64 or 32x32
+    planes (the 512x512 / 256x256 bottleneck) and whole 64-channel K blocks on every contraction of the chain.
     LAMA_B200_FU_LAYOUT=nhwc keeps the round-1 channels-last chain (A/B measurements)."""
     if prog.math != L.MATH_BF16X3 or os.environ.get("LAMA_B200_FU_LAYOUT", "planar") != "planar":
         return False
     c = st.conv1[0].out_channels
     fu = st.fu
-    return ((h, w) == (64, 64) and c % 64 == 0 and fu.conv_layer.in_channels == 2 * c
+    return ((h, w) in ((64, 64), (32, 32)) and c % 64 == 0 and fu.conv_layer.in_channels == 2 * c
             and fu.conv_layer.out_channels == 2 * c)
 
 

@@ -21,35 +21,35 @@ typedef std::complex<double> cd;
 
 static double frand() { return (double)rand() / RAND_MAX * 2.0 - 1.0; }
 
-int main() {
-  srand(7);
-  const int N = 64, WF = 33;
+template <int N>
+static bool run_size() {
+  const int WF = N / 2 + 1, T = CgCfg<N>::set_threads, PX = CgCfg<N>::px_iters;
   // ---------------------------------------------------------------- forward
   std::vector<float> plane(N * N * 4);            // [y][x][4]  (one (image, group) block of a cg=4 tensor)
   for (auto& v : plane) v = (float)frand();
   std::vector<float> smem(N * N * 4), snap;
   // load phase: pixel (y,x) -> real layout
-  for (int tid = 0; tid < kCgThreads; ++tid)
-    for (int i = 0; i < 32; ++i) {
+  for (int tid = 0; tid < T; ++tid)
+    for (int i = 0; i < PX; ++i) {
       int y, x;
-      cg_pixel_slot(tid, i, y, x);
-      memcpy(&smem[cg_real_idx(y, x, 0)], &plane[(y * N + x) * 4], 16);
+      cg_pixel_slot<N>(tid, i, y, x);
+      memcpy(&smem[cg_real_idx<N>(y, x, 0)], &plane[(y * N + x) * 4], 16);
     }
   snap = smem;
   float2* S = reinterpret_cast<float2*>(smem.data());
-  for (int tid = 0; tid < kCgThreads; ++tid)
-    cg_fwd_rows(
+  for (int tid = 0; tid < T; ++tid)
+    cg_fwd_rows<N>(
         tid, [&](int i) { return make_float2(snap[i], snap[i + 1]); }, [] {},
         [&](int i2, float4 v) { S[i2] = make_float2(v.x, v.y); S[i2 + 1] = make_float2(v.z, v.w); });
   snap = smem;
   const float2* Sn = reinterpret_cast<const float2*>(snap.data());
   std::vector<float> spec(N * WF * 8, 1e30f);     // [ky][kx][8]: (re, im) x 4 channels
-  for (int tid = 0; tid < kCgThreads; ++tid)
-    cg_fwd_cols(
+  for (int tid = 0; tid < T; ++tid)
+    cg_fwd_cols<N>(
         tid, [&](int i2) { return Sn[i2]; },
         [&](int ky, int kx, int c, float2 z) {
-          spec[(ky * WF + kx) * 8 + 2 * c] = z.x / 64.f;
-          spec[(ky * WF + kx) * 8 + 2 * c + 1] = z.y / 64.f;
+          spec[(ky * WF + kx) * 8 + 2 * c] = z.x / (float)N;
+          spec[(ky * WF + kx) * 8 + 2 * c + 1] = z.y / (float)N;
         });
   double err_f = 0;
   for (int c = 0; c < 4; ++c)
@@ -58,26 +58,26 @@ int main() {
         cd acc = 0;
         for (int y = 0; y < N; ++y)
           for (int x = 0; x < N; ++x)
-            acc += (double)plane[(y * N + x) * 4 + c] * std::polar(1.0, -2 * M_PI * (ky * y + kx * x) / 64.0);
-        acc /= 64.0;
+            acc += (double)plane[(y * N + x) * 4 + c] * std::polar(1.0, -2 * M_PI * (ky * y + kx * x) / (double)N);
+        acc /= (double)N;
         err_f = fmax(err_f, std::abs(acc - cd(spec[(ky * WF + kx) * 8 + 2 * c], spec[(ky * WF + kx) * 8 + 2 * c + 1])));
       }
-  printf("forward max abs err %.3e\n", err_f);
+  printf("N=%d forward max abs err %.3e\n", N, err_f);
 
   // ---------------------------------------------------------------- inverse (generic complex spectrum)
   std::vector<float> z(N * WF * 8), res(N * N * 4);
   for (auto& v : z) v = (float)frand();
   for (auto& v : res) v = (float)frand();
   std::fill(smem.begin(), smem.end(), 1e30f);
-  for (int tid = 0; tid < kCgThreads; ++tid) {
+  for (int tid = 0; tid < T; ++tid) {
     const int c = tid & 3;
-    cg_inv_cols(
+    cg_inv_cols<N>(
         tid, [&](int ky, int kx) { return make_float2(z[(ky * WF + kx) * 8 + 2 * c], z[(ky * WF + kx) * 8 + 2 * c + 1]); },
         [&](int i2, float2 v) { S[i2] = v; });
   }
   snap = smem;
-  for (int tid = 0; tid < kCgThreads; ++tid)
-    cg_inv_rows(
+  for (int tid = 0; tid < T; ++tid)
+    cg_inv_rows<N>(
         tid,
         [&](int i2) {
           const float2* q = reinterpret_cast<const float2*>(snap.data());
@@ -85,12 +85,12 @@ int main() {
         },
         [] {}, [&](int i, float2 v) { smem[i] = v.x; smem[i + 1] = v.y; });
   std::vector<float> out(N * N * 4, 1e30f);
-  for (int tid = 0; tid < kCgThreads; ++tid)
-    for (int i = 0; i < 32; ++i) {
+  for (int tid = 0; tid < T; ++tid)
+    for (int i = 0; i < PX; ++i) {
       int y, x;
-      cg_pixel_slot(tid, i, y, x);
+      cg_pixel_slot<N>(tid, i, y, x);
       for (int c = 0; c < 4; ++c)
-        out[(y * N + x) * 4 + c] = smem[cg_real_idx(y, x, c)] / 64.f + res[(y * N + x) * 4 + c];
+        out[(y * N + x) * 4 + c] = smem[cg_real_idx<N>(y, x, c)] / (float)N + res[(y * N + x) * 4 + c];
     }
   double err_i = 0;
   for (int c = 0; c < 4; ++c) {
@@ -100,19 +100,24 @@ int main() {
       for (int k = 0; k < WF; ++k) {
         cd acc = 0;
         for (int q = 0; q < N; ++q)
-          acc += cd(z[(q * WF + k) * 8 + 2 * c], z[(q * WF + k) * 8 + 2 * c + 1]) * std::polar(1.0, 2 * M_PI * q * r / 64.0);
+          acc += cd(z[(q * WF + k) * 8 + 2 * c], z[(q * WF + k) * 8 + 2 * c + 1]) * std::polar(1.0, 2 * M_PI * q * r / (double)N);
         T[r * WF + k] = acc;
       }
     for (int r = 0; r < N; ++r)
       for (int n = 0; n < N; ++n) {
-        double acc = T[r * WF].real() + ((n & 1) ? -1.0 : 1.0) * T[r * WF + 32].real();
-        for (int k = 1; k < 32; ++k) acc += 2.0 * (T[r * WF + k] * std::polar(1.0, 2 * M_PI * k * n / 64.0)).real();
-        acc = acc / 64.0 + res[(r * N + n) * 4 + c];
+        double acc = T[r * WF].real() + ((n & 1) ? -1.0 : 1.0) * T[r * WF + N / 2].real();
+        for (int k = 1; k < N / 2; ++k) acc += 2.0 * (T[r * WF + k] * std::polar(1.0, 2 * M_PI * k * n / (double)N)).real();
+        acc = acc / (double)N + res[(r * N + n) * 4 + c];
         err_i = fmax(err_i, fabs(acc - out[(r * N + n) * 4 + c]));
       }
   }
-  printf("inverse max abs err %.3e\n", err_i);
-  const bool ok = err_f < 2e-5 && err_i < 2e-5;
+  printf("N=%d inverse max abs err %.3e\n", N, err_i);
+  return err_f < 2e-5 && err_i < 2e-5;
+}
+
+int main() {
+  srand(7);
+  const bool ok = run_size<64>() & run_size<32>();
   printf(ok ? "OK\n" : "FAILED\n");
   return ok ? 0 : 1;
 }

@@ -287,14 +287,14 @@ def test_conv_contract(case, math):
 
 # ------------------------------------------------------------------ channel-group planar FourierUnit chain (round 2)
 @pytest.mark.parametrize("residual", [True, False])
-@pytest.mark.parametrize("b,c", [(2, 8), (3, 24), (1, 192)])
-def test_plane_fft_pair_channel_group_planar(b, c, residual):
+@pytest.mark.parametrize("b,c,h", [(2, 8, 64), (3, 24, 64), (1, 192, 64), (3, 8, 32), (2, 40, 32)])
+def test_plane_fft_pair_channel_group_planar(b, c, h, residual):
     """fft_plane_cg.cu: the 64x64 plane kernels on [C/cg][B][H][W][cg] tensors — float32 cg=4 real planes in, split
     bf16 cg=8 spectrum out (GEMM operand format); float32 cg=8 spectrum + cg=4 residual in, split bf16 cg=8 and
     float32 cg=4 real planes out.  Checker: numpy float64 (oracle/ffc_numpy.py), incl. the C2R rule on a ReLU'd
     (non-Hermitian) spectrum."""
-    h = w = 64
-    wf = 33
+    w = h
+    wf = w // 2 + 1
     rng = np.random.default_rng(b * 100 + c)
     x = rng.standard_normal((b, c, h, w)).astype(np.float32)
     z = np.maximum(rng.standard_normal((b, 2 * c, h, wf)), 0).astype(np.float32)
