@@ -60,6 +60,7 @@ class TV:
     window: int = 0                           # sliding-window view: pixel x exposes pixels x..x+window-1 (C*window channels)
     b0: int = 0                               # batch slice [b0, b0+nb)
     nb: Optional[int] = None
+    win: Optional[Tuple[int, int, int, int]] = None   # spatial sub-rectangle (y0, x0, h, w) of the buffer (LFU quadrants)
 
     @property
     def channels(self) -> int:
@@ -72,12 +73,14 @@ class TV:
         return self.buf.B - self.b0 if self.nb is None else self.nb
 
     def bslice(self, b0: int, nb: int) -> "TV":
-        return TV(self.buf, self.c0, self.C, self.phase, self.window, self.b0 + b0, nb)
+        return TV(self.buf, self.c0, self.C, self.phase, self.window, self.b0 + b0, nb, self.win)
 
     @property
     def hw(self) -> Tuple[int, int]:
         if self.window:
             return (self.buf.H, self.buf.W - self.window)
+        if self.win is not None:
+            return (self.win[2], self.win[3])
         return (self.buf.H // 2, self.buf.W // 2) if self.phase else (self.buf.H, self.buf.W)
 
 
@@ -289,8 +292,12 @@ def ffc_bn_act_shapes_ok(m, x_l, x_g) -> bool:
         return False
     if h + 2 * p < k or w + 2 * p < k:
         return False
-    if not isinstance(f.convg2g, nn.Identity) and w < 2:
-        return False
+    if not isinstance(f.convg2g, nn.Identity):
+        st = f.convg2g
+        if st_out_hw(st, h, w)[1] < 2 or not st.native_supported((h, w)):   # LFU needs even square planes
+            return False
+        if st.stride == 2 and (c.stride[0] != 2 or ((h + 2 * p - k) // 2 + 1, (w + 2 * p - k) // 2 + 1) != (h // 2, w // 2)):
+            return False
     return True
 
 
@@ -396,6 +403,8 @@ def fu_planar_ok(prog: Program, st, h: int, w: int) -> bool:
         return False
     c = st.conv1[0].out_channels
     fu = st.fu
+    if st.enable_lfu and not ((h, w) == (64, 64) and c % 32 == 0):      # LFU quadrants: 32x32 planes, c/4 % 8 == 0
+        return False
     return ((h, w) in ((64, 64), (32, 32)) and c % 64 == 0 and fu.conv_layer.in_channels == 2 * c
             and fu.conv_layer.out_channels == 2 * c)
 
@@ -422,20 +431,60 @@ def emit_fourier_unit(prog: Program, fu, t: TV, out: TV, residual: Optional[TV])
                                 out.bslice(b0, nb)))
 
 
+def st_out_hw(st, h: int, w: int) -> Tuple[int, int]:
+    """Spatial size SpectralTransform works at: AvgPool2d(2, 2) first when stride == 2 (ffc.py:122-125)."""
+    return (h // 2, w // 2) if st.stride == 2 else (h, w)
+
+
+def lfu_supported(st, h: int, w: int) -> bool:
+    """LFU (ffc.py:148-157) natively: the first c/4 channels, cut into 2x2 quadrants stacked as channels — the
+    reference splits rows AND columns by h // 2, which only type-checks for even square planes; quadrant views carry
+    c/4 channels and every view needs a multiple of 4."""
+    c = st.conv1[0].out_channels
+    return h == w and h % 2 == 0 and h >= 4 and c % 16 == 0 and st.lfu.native_supported()
+
+
 def emit_spectral_transform(prog: Program, st, x: TV, u_consumer=None) -> Tuple[TV, P.PackedConv]:
     """SpectralTransform (ffc.py:142-163) up to, but not including, conv2: returns the view holding
-    ``x1 + fu(x1)`` and lets the caller fuse conv2 into its own contraction."""
+    ``x1 + fu(x1) [+ tile(lfu(quadrants(x1)))]`` and lets the caller fuse conv2 into its own contraction.
+    stride 2: AvgPool2d(2,2) + the 1x1 conv1 are ONE 2x2 stride-2 contraction (four taps with conv1.weight / 4)."""
     b = x.buf.B
-    h, w = x.hw
+    h, w = st_out_hw(st, *x.hw)
     c = st.conv1[0].out_channels
     dev = st.conv2.weight.device
     planar = fu_planar_ok(prog, st, h, w)
     T = prog.buf("st.t", b, h, w, c, cg=4 if planar else 0)
     U = prog.buf("st.u", b, h, w, c, gemm=True, cg=8 if planar else 0)
     s1, b1 = P.bn_scale_shift(st.conv1[1])
-    pk1 = P.pack_conv([(st.conv1[0].weight, 0, x.c0, 0)], s1, b1, act=L.ACT_RELU, device=dev)
-    prog.ops.append(ConvOp(pk1, [TV(x.buf), None], TV(T), tag="st.conv1+bn+relu"))
-    emit_fourier_unit(prog, st.fu, TV(T), TV(U), residual=TV(T))
+    if st.stride == 2:
+        w1 = st.conv1[0].weight.detach().repeat(1, 1, 2, 2) / 4.0
+        pk1 = P.pack_conv([(w1, 0, x.c0, 0)], s1, b1, stride=2, act=L.ACT_RELU, device=dev)
+        tag = "st.avgpool2x2+conv1+bn+relu"
+    else:
+        pk1 = P.pack_conv([(st.conv1[0].weight, 0, x.c0, 0)], s1, b1, act=L.ACT_RELU, device=dev)
+        tag = "st.conv1+bn+relu"
+    prog.ops.append(ConvOp(pk1, [TV(x.buf), None], TV(T), tag=tag))
+    residual = TV(T)
+    if st.enable_lfu:
+        # xs = lfu(quadrants of the first c/4 channels) tiled 2x2; XS = T + tile(xs) becomes the residual of the main
+        # inverse transform, so  U = T + fu(T) + tile(xs)  (ffc.py:161) costs no extra pass over U
+        lfu, c4, s = st.lfu, c // 4, h // 2
+        sf = s // 2 + 1
+        XS = prog.buf("st.xs", b, h, w, c, cg=4 if planar else 0)
+        LS = prog.buf("lfu.spectrum", b, s, sf, 2 * c, gemm=True, cg=8 if planar else 0)
+        LZ = prog.buf("lfu.spectrum_out", b, s, sf, 2 * c, cg=8 if planar else 0)
+        # channel order of the two torch.cat calls (ffc.py:152-155): top-left, bottom-left, top-right, bottom-right
+        for q, (qy, qx) in enumerate([(0, 0), (1, 0), (0, 1), (1, 1)]):
+            prog.ops.append(RfftOp(TV(T, 0, c4, win=(qy * s, qx * s, s, s)), TV(LS, q * 2 * c4, 2 * c4)))
+        sc, sh = P.bn_scale_shift(lfu.bn)
+        pkl = P.pack_conv([(lfu.conv_layer.weight, 0, 0, 0)], sc, sh, act=L.ACT_RELU, device=dev)
+        prog.ops.append(ConvOp(pkl, [TV(LS), None], TV(LZ), tag="lfu.conv_layer+bn+relu"))
+        for ty in (0, 1):
+            for tx in (0, 1):          # .repeat(1, 1, 2, 2) (ffc.py:157): the same s x s result in all four quadrants
+                wq = (ty * s, tx * s, s, s)
+                prog.ops.append(IrfftOp(TV(LZ), TV(T, win=wq), TV(XS, win=wq)))
+        residual = TV(XS)
+    emit_fourier_unit(prog, st.fu, TV(T), TV(U), residual=residual)
     return TV(U)
 
 
@@ -481,14 +530,25 @@ def emit_ffc_bn_act(prog: Program, m, X: Buf, in_cl: int, in_cg: int, residual: 
     if out_cg > 0:
         parts = [(f.convl2g.weight, 0, 0, p)]     # ffc_bn_act_supported() guarantees convl2g exists
         ins = [TV(X), None]
+        pre = None
         if has_spectral:
             U = emit_spectral_transform(prog, f.convg2g, TV(X, in_cl, in_cg))
-            parts.append((f.convg2g.conv2.weight, 1, 0, 0))
-            ins[1] = U
+            if s == 1:
+                parts.append((f.convg2g.conv2.weight, 1, 0, 0))
+                ins[1] = U
+            else:
+                # stride-2 FFC (ffc.py:122-125, 221-224): convl2g samples X with stride 2 while conv2 reads the already
+                # pooled u with stride 1 — one ffcb_conv has one stride, so conv2 (with bn_g's scale folded, no shift)
+                # runs first and joins the 3x3 contraction as its pre-activation addend.  Never a residual layer.
+                assert residual is None
+                A = prog.buf("st.conv2.out", X.B, ho, wo, out_cg)
+                pk2 = P.pack_conv([(f.convg2g.conv2.weight, 0, 0, 0)], sg, None, device=dev)
+                prog.ops.append(ConvOp(pk2, [U, None], TV(A), tag="st.conv2 (x bn_g scale)"))
+                pre = TV(A)
         # y_g = act(bn_g(convl2g(x_l) + conv2(x1 + fu(x1)))): conv2 rides as one more K-segment.
         pk = P.pack_conv(parts, sg, bg, stride=s, act=act_g, device=dev)
-        prog.ops.append(ConvOp(pk, ins, TV(Y, out_cl, out_cg), addend=res_g, addend_post=True,
-                               tag="convl2g+st.conv2+bn_g+act"))
+        prog.ops.append(ConvOp(pk, ins, TV(Y, out_cl, out_cg), addend=pre if pre is not None else res_g,
+                               addend_post=pre is None, tag="convl2g+st.conv2+bn_g+act"))
     return Y, out_cl, out_cg
 
 
@@ -516,10 +576,11 @@ def build_module_program(module, kind: str, shapes: Sequence[Optional[Tuple[int,
     elif kind == "spectral_transform":
         b, c, h, w = shapes[0]
         prog.inputs["x0"] = shapes[0]
-        X = prog.buf("in", b, h, w, c, gemm=True)
+        X = prog.buf("in", b, h, w, c, gemm=True, halo=module.stride == 2)
         prog.ops.append(ToNHWC("x0", TV(X)))
         U = emit_spectral_transform(prog, module, TV(X))
         co = module.conv2.out_channels
+        h, w = st_out_hw(module, h, w)
         O = prog.buf("out", b, h, w, co)
         pk = P.pack_conv([(module.conv2.weight, 0, 0, 0)], None, None, device=module.conv2.weight.device)
         prog.ops.append(ConvOp(pk, [U, None], TV(O), tag="st.conv2"))
@@ -710,8 +771,13 @@ class CudaExecutor:
             t.sx, t.sy, t.sb = b.cg, b.W * b.cg, b.H * b.W * b.cg
             t.sg, t.cg = b.B * b.H * b.W * b.cg, b.cg
             t.lo_off = b.C * b.B * b.H * b.W if b.fmt == L.BF16X2 else 0
-            t.ptr = st.data_ptr() + ((tv.c0 // b.cg) * t.sg + tv.b0 * t.sb) * es
-            t.B, t.H, t.W, t.C = tv.batch, b.H, b.W, tv.channels
+            off = (tv.c0 // b.cg) * t.sg + tv.b0 * t.sb
+            h, w = b.H, b.W
+            if tv.win is not None:
+                y0, x0, h, w = tv.win
+                off += y0 * t.sy + x0 * t.sx
+            t.ptr = st.data_ptr() + off * es
+            t.B, t.H, t.W, t.C = tv.batch, h, w, tv.channels
             t.fmt, t.pad, t.reflect_border = b.fmt, 0, 0
             return t
         wp, hp = b.W + 2 * b.pad, b.H + 2 * b.pad
@@ -722,6 +788,10 @@ class CudaExecutor:
             a, bb = tv.phase
             off += a * sy + bb * sx
             sy, sx, h, w = 2 * sy, 2 * sx, b.H // 2, b.W // 2
+        if tv.win is not None:
+            assert tv.phase is None and not tv.window
+            y0, x0, h, w = tv.win
+            off += y0 * sy + x0 * sx
         t = L.Tensor()
         t.ptr = 0  # set below (after the batch-slice offset)
         t.sb, t.sy, t.sx = sb, sy, sx
@@ -730,7 +800,7 @@ class CudaExecutor:
         t.ptr = st.data_ptr() + off * es
         t.B, t.H, t.W, t.C = tv.batch, h, w, tv.channels
         t.fmt, t.pad, t.reflect_border = b.fmt, b.pad, b.reflect_border
-        if tv.phase is not None:     # a sub-pixel phase is not a contiguous image: no ring semantics
+        if tv.phase is not None or tv.win is not None:     # not a whole image: no ring semantics
             t.pad, t.reflect_border = 0, 0
         if tv.window:                # pixel x exposes the buf.C * window contiguous elements starting at x * sx
             t.W, t.C, t.window = b.W - tv.window, b.C * tv.window, 1

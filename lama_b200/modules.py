@@ -173,13 +173,21 @@ class SpectralTransform(nn.Module):
             self.lfu = FourierUnit(half, half, groups)
         self.conv2 = nn.Conv2d(half, out_channels, kernel_size=1, groups=groups, bias=False)
 
-    def native_supported(self) -> bool:
-        return (not self.enable_lfu and self.stride == 1 and self.conv1[0].groups == 1 and not self.training
-                and self.fu.native_supported() and self.conv1[0].in_channels % 4 == 0
-                and self.conv2.out_channels % 4 == 0 and _engine.bn_foldable(self.conv1[1]))
+    def native_supported(self, hw=None) -> bool:
+        """``hw``: spatial size of the input; the LFU branch (ffc.py:148-157) is native for even square planes after the
+        optional stride-2 pooling and c % 16 == 0 (quadrant views of c/4 channels), else the torch composition runs."""
+        ok = (self.stride in (1, 2) and self.conv1[0].groups == 1 and not self.training
+              and self.fu.native_supported() and self.conv1[0].in_channels % 4 == 0
+              and self.conv2.out_channels % 4 == 0 and _engine.bn_foldable(self.conv1[1]))
+        if ok and self.enable_lfu:
+            if hw is None:
+                return self.conv1[0].out_channels % 16 == 0 and self.lfu.native_supported()
+            ok = _engine.lfu_supported(self, *_engine.st_out_hw(self, *hw))
+        return ok
 
     def forward(self, x):
-        if _native_ok(x) and self.native_supported() and x.shape[-1] >= 2:
+        if (_native_ok(x) and x.dim() == 4 and self.native_supported(tuple(x.shape[-2:]))
+                and _engine.st_out_hw(self, *x.shape[-2:])[1] >= 2):
             return _engine.run_module(self, "spectral_transform", (x,))[0]
         _fallback("SpectralTransform options / mode")
         x = self.conv1(self.downsample(x))

@@ -173,9 +173,46 @@ def make_predict():
           out=np.stack(outs))
 
 
+@torch.no_grad()
+def make_f4():
+    """Round 2, SURVEY.md row f4: optional FFC flags that became native — LFU (ffc.py:148-157) and the stride-2
+    SpectralTransform (ffc.py:122-125), alone and inside an FFC_BN_ACT / FFCResnetBlock.  Channel counts large enough
+    for the native views (LFU quadrants carry c/4 channels, every view needs a multiple of 4)."""
+    ffc = load_reference_ffc()
+    torch.set_num_threads(1)
+    relu = torch.nn.ReLU
+    st_cases = {
+        "st_32to32_lfu_8x8": dict(ci=32, co=32, stride=1, lfu=True, hw=(8, 8)),
+        "st_32to32_s2_lfu_16x16": dict(ci=32, co=32, stride=2, lfu=True, hw=(16, 16)),
+        "st_32to64_s2_12x20": dict(ci=32, co=64, stride=2, lfu=False, hw=(12, 20)),
+    }
+    for i, (name, c) in enumerate(st_cases.items()):
+        m = seeded_parameters_(ffc.SpectralTransform(c["ci"], c["co"], stride=c["stride"],
+                                                     enable_lfu=c["lfu"]).eval(), seed=60 + i, gain=1.0)
+        x = _randn((2, c["ci"]) + c["hw"], 600 + i)
+        _save(name, x=x.numpy(), y=m(x).numpy(), **_sd_np(m))
+    # FFC_BN_ACT with a global input AND stride 2 (the spectral branch pools, the 3x3 convs stride), LFU on
+    m = seeded_parameters_(ffc.FFC_BN_ACT(in_channels=64, out_channels=64, kernel_size=3, ratio_gin=0.5, ratio_gout=0.5,
+                                          stride=2, padding=1, activation_layer=relu, enable_lfu=True).eval(),
+                           seed=70, gain=1.0)
+    xl, xg = _randn((2, 32, 16, 16), 700), _randn((2, 32, 16, 16), 701)
+    yl, yg = m((xl, xg))
+    _save("ffcbnact_64_s2_lfu_16x16", x_l=xl.numpy(), x_g=xg.numpy(), y_l=yl.numpy(), y_g=yg.numpy(), **_sd_np(m))
+    # residual block with LFU (the reference's default enable_lfu=True flavour, e.g. configs/training/lama-fourier)
+    m = seeded_parameters_(
+        ffc.FFCResnetBlock(64, padding_type="reflect", norm_layer=torch.nn.BatchNorm2d, activation_layer=relu,
+                           ratio_gin=0.5, ratio_gout=0.5, enable_lfu=True).eval(), seed=71)
+    xl, xg = _randn((1, 32, 8, 8), 710), _randn((1, 32, 8, 8), 711)
+    yl, yg = m((xl, xg))
+    _save("resblock_64_lfu_8x8", x_l=xl.numpy(), x_g=xg.numpy(), y_l=yl.numpy(), y_g=yg.numpy(), **_sd_np(m))
+
+
 if __name__ == "__main__":
-    if "--predict-only" in sys.argv:
+    if "--f4-only" in sys.argv:
+        make_f4()
+    elif "--predict-only" in sys.argv:
         make_predict()
     else:
         main()
         make_predict()
+        make_f4()

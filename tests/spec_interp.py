@@ -24,6 +24,9 @@ class SpecInterpreter:
         if tv.phase is not None:
             a, b = tv.phase
             t = t[:, a::2, b::2]
+        if tv.win is not None:
+            y0, x0, h, w = tv.win
+            t = t[:, y0:y0 + h, x0:x0 + w]
         return t[..., tv.c0:tv.c0 + tv.channels]
 
     def write(self, tv: E.TV, val: torch.Tensor):
@@ -31,6 +34,9 @@ class SpecInterpreter:
         if tv.phase is not None:
             a, b = tv.phase
             t[:, a::2, b::2, tv.c0:tv.c0 + tv.channels] = val
+        elif tv.win is not None:
+            y0, x0, h, w = tv.win
+            t[:, y0:y0 + h, x0:x0 + w, tv.c0:tv.c0 + tv.channels] = val
         else:
             t[..., tv.c0:tv.c0 + tv.channels] = val
 

@@ -50,6 +50,14 @@ def math_mode(request):
     os.environ.pop("LAMA_B200_MATH", None)
 
 
+@pytest.fixture
+def tc_math():
+    """Tests of things that exist on the tensor-core arm only (uint8 front / back end, planar chain): run once, in that mode."""
+    os.environ["LAMA_B200_MATH"] = "bf16x3"
+    yield "bf16x3"
+    os.environ.pop("LAMA_B200_MATH", None)
+
+
 @pytest.fixture(autouse=True, scope="module")
 def _need_gpu():
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
@@ -401,6 +409,48 @@ def test_spectral_transform_golden(math_mode):
     assert _rel_err(y, a["y"]) < TOL[math_mode]
 
 
+@pytest.mark.parametrize("name,ci,co,stride,lfu", [("st_16to16_s2_16x16", 16, 16, 2, False),
+                                                    ("st_32to64_s2_12x20", 32, 64, 2, False),
+                                                    ("st_32to32_lfu_8x8", 32, 32, 1, True),
+                                                    ("st_32to32_s2_lfu_16x16", 32, 32, 2, True)])
+def test_spectral_transform_stride2_and_lfu_golden(name, ci, co, stride, lfu, math_mode):
+    """SURVEY.md row f4 on the native path (LAMA_B200_STRICT=1: a torch fallback would fail the test): stride-2
+    SpectralTransform (ffc.py:122-125) and LFU (ffc.py:148-157) against goldens from the unmodified reference."""
+    a, sd = load_golden(name)
+    m = _load(M.SpectralTransform(ci, co, stride=stride, enable_lfu=lfu), sd)
+    with torch.no_grad():
+        y = m(torch.from_numpy(a["x"]).to(DEV)).cpu().numpy()
+    assert _rel_err(y, a["y"]) < TOL[math_mode]
+
+
+def test_ffc_bn_act_stride2_global_lfu_and_resblock_lfu_golden(math_mode):
+    a, sd = load_golden("ffcbnact_64_s2_lfu_16x16")
+    m = _load(M.FFC_BN_ACT(in_channels=64, out_channels=64, kernel_size=3, ratio_gin=0.5, ratio_gout=0.5, stride=2,
+                           padding=1, activation_layer=torch.nn.ReLU, enable_lfu=True), sd)
+    with torch.no_grad():
+        yl, yg = m((torch.from_numpy(a["x_l"]).to(DEV), torch.from_numpy(a["x_g"]).to(DEV)))
+    assert _rel_err(yl.cpu().numpy(), a["y_l"]) < TOL[math_mode] and _rel_err(yg.cpu().numpy(), a["y_g"]) < TOL[math_mode]
+    a, sd = load_golden("resblock_64_lfu_8x8")
+    m = _load(M.FFCResnetBlock(64, padding_type="reflect", norm_layer=torch.nn.BatchNorm2d,
+                               activation_layer=torch.nn.ReLU, ratio_gin=0.5, ratio_gout=0.5, enable_lfu=True), sd)
+    with torch.no_grad():
+        yl, yg = m((torch.from_numpy(a["x_l"]).to(DEV), torch.from_numpy(a["x_g"]).to(DEV)))
+    assert _rel_err(yl.cpu().numpy(), a["y_l"]) < TOL[math_mode] and _rel_err(yg.cpu().numpy(), a["y_g"]) < TOL[math_mode]
+
+
+def test_lfu_on_the_planar_chain_at_the_bottleneck_size(tc_math):
+    """LFU inside the channel-group planar chain: 64x64 planes -> 32x32 quadrant planes (both register-transform
+    sizes of fft_plane_cg.cu), c = 64; checker: the torch-CPU oracle port."""
+    torch.manual_seed(5)
+    m = seeded_parameters_(M.SpectralTransform(128, 128, enable_lfu=True).eval(), 5)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(2, 128, 64, 64, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        y = m.to(DEV)(x.to(DEV)).cpu()
+        ref = otc.spectral_transform(x, sd, enable_lfu=True)
+    assert _rel_err(y.numpy(), ref.numpy()) < TOL["bf16x3"]
+
+
 @pytest.mark.parametrize("name,kw,has_g", [
     ("ffcbnact_32_k3_075", dict(in_channels=32, out_channels=32, kernel_size=3, ratio_gin=0.75, ratio_gout=0.75,
                                 padding=1), True),
@@ -586,12 +636,6 @@ def test_baseline_config1_resnet_block_bs8(math_mode):
 
 
 # ------------------------------------------------------------------- predict path, uint8 I/O
-@pytest.fixture
-def tc_math():
-    """The uint8 front / back end exists on the tensor-core arm only: run those tests once, in that mode."""
-    os.environ["LAMA_B200_MATH"] = "bf16x3"
-    yield "bf16x3"
-    os.environ.pop("LAMA_B200_MATH", None)
 
 
 def test_predict_u8_bytes_match_reference_fixture(tc_math):

@@ -65,7 +65,8 @@ def test_fft_known_answers():
 
 
 @pytest.mark.parametrize("name,stride,lfu", [("st_16to24_8x8", 1, False), ("st_16to16_s2_16x16", 2, False),
-                                              ("st_16to16_lfu_8x8", 1, True)])
+                                              ("st_16to16_lfu_8x8", 1, True), ("st_32to32_lfu_8x8", 1, True),
+                                              ("st_32to32_s2_lfu_16x16", 2, True), ("st_32to64_s2_12x20", 2, False)])
 def test_spectral_transform(name, stride, lfu):
     a, sd = load_golden(name)
     _close(onp.spectral_transform(a["x"].astype(np.float64), _f64(sd), stride=stride, enable_lfu=lfu), a["y"], 2e-6)

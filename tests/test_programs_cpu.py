@@ -52,6 +52,44 @@ def test_spectral_transform_program():
     _close(out["y0"], a["y"])
 
 
+@pytest.mark.parametrize("name,ci,co,stride,lfu", [("st_16to16_s2_16x16", 16, 16, 2, False),
+                                                    ("st_32to64_s2_12x20", 32, 64, 2, False),
+                                                    ("st_32to32_lfu_8x8", 32, 32, 1, True),
+                                                    ("st_32to32_s2_lfu_16x16", 32, 32, 2, True)])
+def test_spectral_transform_stride2_and_lfu_programs(name, ci, co, stride, lfu):
+    """AvgPool2d(2,2) + conv1 as one 2x2 stride-2 contraction (ffc.py:122-125, 145); LFU as four
+    quadrant FFTs into channel slices of one spectrum, one spectral GEMM, four tiled inverses (ffc.py:148-157)."""
+    a, sd = load_golden(name)
+    m = _load(M.SpectralTransform(ci, co, stride=stride, enable_lfu=lfu), sd)
+    x = torch.from_numpy(a["x"])
+    assert m.native_supported(tuple(x.shape[-2:]))
+    out, prog = _run(m, "spectral_transform", (x,))
+    _close(out["y0"], a["y"])
+    assert sum(isinstance(o, E.RfftOp) for o in prog.ops) == (5 if lfu else 1)
+    assert sum(isinstance(o, E.IrfftOp) for o in prog.ops) == (5 if lfu else 1)
+
+
+def test_ffc_bn_act_stride2_global_with_lfu_program():
+    a, sd = load_golden("ffcbnact_64_s2_lfu_16x16")
+    m = _load(M.FFC_BN_ACT(in_channels=64, out_channels=64, kernel_size=3, ratio_gin=0.5, ratio_gout=0.5, stride=2,
+                           padding=1, activation_layer=torch.nn.ReLU, enable_lfu=True), sd)
+    xl, xg = torch.from_numpy(a["x_l"]), torch.from_numpy(a["x_g"])
+    assert m.native_supported() and E.ffc_bn_act_shapes_ok(m, xl, xg)
+    out, _ = _run(m, "ffc_bn_act", (xl, xg))
+    _close(out["y0"], a["y_l"]); _close(out["y1"], a["y_g"])
+    # LFU only type-checks for even square planes (the reference splits rows and columns by h // 2): 12 x 20 -> torch
+    assert not E.ffc_bn_act_shapes_ok(m, torch.zeros(1, 32, 12, 20), torch.zeros(1, 32, 12, 20))
+
+
+def test_resnet_block_with_lfu_program():
+    a, sd = load_golden("resblock_64_lfu_8x8")
+    m = _load(M.FFCResnetBlock(64, padding_type="reflect", norm_layer=torch.nn.BatchNorm2d,
+                               activation_layer=torch.nn.ReLU, ratio_gin=0.5, ratio_gout=0.5, enable_lfu=True), sd)
+    assert m.native_supported()
+    out, _ = _run(m, "resnet_block", (torch.from_numpy(a["x_l"]), torch.from_numpy(a["x_g"])))
+    _close(out["y0"], a["y_l"]); _close(out["y1"], a["y_g"])
+
+
 @pytest.mark.parametrize("name,kw,has_g", [
     ("ffcbnact_32_k3_075", dict(in_channels=32, out_channels=32, kernel_size=3, ratio_gin=0.75, ratio_gout=0.75,
                                 padding=1), True),
@@ -100,7 +138,9 @@ def test_generator_program(name):
 def test_unsupported_options_are_not_native():
     assert not M.FourierUnit(8, 8, spectral_pos_encoding=True).eval().native_supported()
     assert not M.FourierUnit(8, 8, fft_norm="backward").eval().native_supported()
-    assert not M.SpectralTransform(16, 16, enable_lfu=True).eval().native_supported()
+    assert not M.SpectralTransform(16, 16, enable_lfu=True).eval().native_supported()       # c/4 = 2 channels
+    lf = M.SpectralTransform(32, 32, enable_lfu=True).eval()
+    assert lf.native_supported() and lf.native_supported((8, 8)) and not lf.native_supported((8, 12))
     assert not M.FFC_BN_ACT(16, 16, 3, 0.5, 0.5, padding=1, enable_lfu=False, gated=True).eval().native_supported()
     assert not M.FFC_BN_ACT(16, 16, 3, 0.5, 0.5, padding=2, dilation=2, enable_lfu=False).eval().native_supported()
     m = M.FFC_BN_ACT(16, 16, 3, 0.5, 0.5, padding=1, enable_lfu=False)
