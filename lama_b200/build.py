@@ -19,7 +19,7 @@ OBJ_DIR = os.path.join(HERE, "build")
 SOURCES = ["api.cu", "fft.cu", "fft_plane.cu", "fft_plane_cg.cu", "conv_simt.cu", "conv_tc.cu", "shell.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "--expt-relaxed-constexpr",
+    "-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC", "-shared",
 ]
 

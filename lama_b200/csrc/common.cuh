@@ -139,8 +139,8 @@ __device__ __forceinline__ void store1(const View& v, long long off, float r) {
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case FFCB_ACT_RELU: return fmaxf(v, 0.f);
-    case FFCB_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
-    case FFCB_ACT_TANH: return tanhf(v);
+    case FFCB_ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-v));   // explicit fast intrinsics: ~2 ulp
+    case FFCB_ACT_TANH: return tanhf(v);                              // precise (no --use_fast_math)
     default: return v;
   }
 }
@@ -162,7 +162,7 @@ static __device__ __noinline__ void store4_ring_copies(const View& v, int b, int
 }
 
 static __device__ __noinline__ float slow_act(float v, int act) {
-  return act == FFCB_ACT_SIGMOID ? 1.f / (1.f + __expf(-v)) : tanhf(v);
+  return act == FFCB_ACT_SIGMOID ? __fdividef(1.f, 1.f + __expf(-v)) : tanhf(v);
 }
 #endif  // __CUDACC__
 

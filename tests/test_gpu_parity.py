@@ -492,6 +492,22 @@ def test_small_generator_golden(name, math_mode):
     assert float(np.abs(y - a["y"]).max()) < (5e-6 if math_mode == "fp32" else 1e-4)
 
 
+def test_generator_with_the_constructor_default_tanh_head(math_mode):
+    """add_out_act=True (the constructor default, ffc.py:362) ends the generator with tanh: precise tanhf in the head
+    epilogue (the library is built without --use_fast_math), both head implementations."""
+    kw = small_lama_kwargs(ngf=8, n_blocks=1)
+    kw["add_out_act"] = True
+    g = seeded_parameters_(M.FFCResNetGenerator(**kw).eval(), 9, gain=1.0)
+    sd = {k: v.clone() for k, v in g.state_dict().items()}
+    img, mask = synthetic_image_mask(2, 64, 9)
+    x = generator_input(img, mask)
+    with torch.no_grad():
+        y = g.to(DEV)(x.to(DEV)).cpu()
+        ref = otc.ffc_resnet_generator(x, sd, **kw)
+    assert float(ref.min()) < -0.05, "tanh head should produce negative values on this input"
+    assert float((y - ref).abs().max()) < (5e-6 if math_mode == "fp32" else 1e-4)
+
+
 def test_stage_by_stage_matches_whole_program():
     """predict_inner_features.py:84 iterates generator.model stage by stage: tuple outputs at every FFC
     stage, each stage on its own native program, same result as the fused whole-generator program."""
