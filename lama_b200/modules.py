@@ -345,6 +345,18 @@ class FFCResNetGenerator(nn.Module):
                  add_out_act=True, max_features=1024, out_ffc=False, out_ffc_kwargs={}):
         assert n_blocks >= 0
         super().__init__()
+        # constructor arguments as JSON when they are plain data (default layer classes): lets a torch.jit.trace on
+        # CUDA record the native generator call as ONE custom op (lama_b200/ops.py) instead of cuFFT / cuDNN ops
+        defaults = (norm_layer is nn.BatchNorm2d and activation_layer is nn.ReLU and up_norm_layer is nn.BatchNorm2d
+                    and isinstance(up_activation, nn.ReLU) and spatial_transform_layers is None)
+        self._ffcb_spec = None
+        if defaults:
+            from .ops import spec_of
+            self._ffcb_spec = spec_of(dict(
+                input_nc=input_nc, output_nc=output_nc, ngf=ngf, n_downsampling=n_downsampling, n_blocks=n_blocks,
+                padding_type=padding_type, init_conv_kwargs=init_conv_kwargs,
+                downsample_conv_kwargs=downsample_conv_kwargs, resnet_conv_kwargs=resnet_conv_kwargs,
+                add_out_act=add_out_act, max_features=max_features, out_ffc=out_ffc, out_ffc_kwargs=out_ffc_kwargs))
         stages = [nn.ReflectionPad2d(3),
                   FFC_BN_ACT(input_nc, ngf, kernel_size=7, padding=0, norm_layer=norm_layer,
                              activation_layer=activation_layer, **init_conv_kwargs)]
@@ -379,6 +391,12 @@ class FFCResNetGenerator(nn.Module):
     def forward(self, input):
         if _native_ok(input) and not self.training and _engine.generator_supported(self, input):
             return _engine.run_module(self, "generator", (input,))[0]
+        if (torch.jit.is_tracing() and self._ffcb_spec is not None and not self.training and torch.is_tensor(input)
+                and input.is_cuda and input.dtype == torch.float32 and not torch.is_grad_enabled()
+                and os.environ.get("LAMA_B200_TRACE_NATIVE", "1") == "1" and _engine.generator_supported(self, input)):
+            # bin/to_jit.py:55-62 on a CUDA box: the traced graph keeps the native kernels as one custom-op node
+            from .ops import traced_generator_call
+            return traced_generator_call(self, input)
         _fallback("FFCResNetGenerator topology / mode")
         return self.model(input)
 

@@ -508,6 +508,43 @@ def test_generator_with_the_constructor_default_tanh_head(math_mode):
     assert float((y - ref).abs().max()) < (5e-6 if math_mode == "fp32" else 1e-4)
 
 
+def test_to_jit_trace_on_cuda_keeps_the_native_kernels(tc_math, tmp_path):
+    """bin/to_jit.py:49-72 on a CUDA box: the traced + saved + reloaded model must still run libffc_b200.so — the
+    generator is ONE ``lama_b200::ffc_generator`` node (lama_b200/ops.py), its weights travel inside the file."""
+    import lama_b200.ops  # noqa: F401  (registers the op; a fresh process loading the file does the same)
+
+    class JITWrapper(torch.nn.Module):            # to_jit.py:14-25 + trainers/default.py:59-71
+        def __init__(self, generator):
+            super().__init__()
+            self.generator = generator
+
+        def forward(self, image, mask):
+            masked = torch.cat([image * (1 - mask), mask], dim=1)
+            return mask * self.generator(masked) + (1 - mask) * image
+
+    g = seeded_parameters_(M.FFCResNetGenerator(**small_lama_kwargs(ngf=8, n_blocks=2)).eval(), seed=1).to(DEV)
+    w = JITWrapper(g).eval()
+    gen = torch.Generator().manual_seed(0)
+    image = torch.rand(1, 3, 120, 120, generator=gen).to(DEV)
+    mask = (torch.rand(1, 1, 120, 120, generator=gen) > 0.7).float().to(DEV)
+    L.get_lib().ffcb_reset_launch_count()
+    with torch.no_grad():
+        eager = w(image, mask)
+        assert L.get_lib().ffcb_launch_count() > 0
+        traced = torch.jit.trace(w, (image, mask), strict=False)
+    assert "lama_b200::ffc_generator" in str(traced.inlined_graph)
+    path = str(tmp_path / "lama.pt")
+    traced.save(path)
+    loaded = torch.jit.load(path)
+    L.get_lib().ffcb_reset_launch_count()
+    with torch.no_grad():
+        out = loaded(image, mask)
+        out2 = loaded(image.flip(-1).contiguous(), mask.flip(-1).contiguous())     # not a baked-in constant
+        want2 = w(image.flip(-1).contiguous(), mask.flip(-1).contiguous())
+    assert L.get_lib().ffcb_launch_count() > 0, "the reloaded TorchScript did not launch the native kernels"
+    assert torch.equal(out, eager) and torch.equal(out2, want2)
+
+
 def test_stage_by_stage_matches_whole_program():
     """predict_inner_features.py:84 iterates generator.model stage by stage: tuple outputs at every FFC
     stage, each stage on its own native program, same result as the fused whole-generator program."""
