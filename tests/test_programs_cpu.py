@@ -244,7 +244,7 @@ def test_modules_stay_copyable_and_picklable_after_native_use():
     g = M.FFCResNetGenerator(**small_lama_kwargs(ngf=8, n_blocks=1)).eval()
     fake = (ctypes.c_void_p(1), ctypes.byref(ctypes.c_int(3)))          # what a CudaExecutor keeps alive
     E._PROGRAMS.setdefault(g, {})[("generator", ((1, 4, 64, 64),), "cuda:0", 1)] = (E._weights_signature(g), fake)
-    assert not any(k.startswith("_ffcb") for k in g.__dict__)
+    assert all(isinstance(v, (str, type(None))) for k, v in g.__dict__.items() if k.startswith("_ffcb"))   # plain data only
     g2 = copy.deepcopy(g)
     assert g2 not in E._PROGRAMS
     pickle.loads(pickle.dumps(g))
