@@ -16,9 +16,25 @@
 namespace ffcb {
 namespace fftc {
 
+// Complex arithmetic.  On sm_100 the (re, im) pair is one 64-bit register pair and add / sub / multiply are the packed
+// FADD2 / FMUL2 / FFMA2 instructions (two fp32 results per issue slot; negation, the re<->im swap of a multiplication
+// by +-i and scalar broadcast are operand modifiers — `FADD2 R6, R6.F32x2.HI_LO, R6.F32x2.LO_HI.NP`), which halves the
+// floating-point instruction count of the butterflies.  Every operation is still an IEEE round-to-nearest fp32 add /
+// mul / fma, so the host build (tests/host_emul) computes the same values up to fma contraction.
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(FFCB_NO_F32X2)
+#define FFCB_F32X2 1
+FFCB_HD float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+FFCB_HD float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+FFCB_HD float2 cmul(float2 a, float2 b) {
+  return __ffma2_rn(make_float2(-a.y, a.y), make_float2(b.y, b.x), __fmul2_rn(make_float2(a.x, a.x), b));
+}
+FFCB_HD float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+#else
 FFCB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 FFCB_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 FFCB_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+FFCB_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+#endif
 
 // multiply by -i (forward transform) or +i (inverse)
 template <bool INV>
@@ -47,15 +63,15 @@ FFCB_HD void fft8(float2* v) {
   fft4<INV>(v[0], v[2], v[4], v[6]);  // E[0..3] -> v[0], v[2], v[4], v[6]
   fft4<INV>(v[1], v[3], v[5], v[7]);  // O[0..3] -> v[1], v[3], v[5], v[7]
   const float h = 0.70710678118654752440f;
-  float2 o1, o2, o3;  // w^q * O[q], w = exp(-+ 2 pi i / 8)
+  float2 o1, o2, o3;  // w^q * O[q], w = exp(-+ 2 pi i / 8):  w^1 z = h (z -+ i z),  w^2 z = -+ i z,  w^3 z = h (-z -+ i z)
   if (INV) {
-    o1 = make_float2(h * (v[3].x - v[3].y), h * (v[3].x + v[3].y));
-    o2 = make_float2(-v[5].y, v[5].x);
-    o3 = make_float2(-h * (v[7].x + v[7].y), h * (v[7].x - v[7].y));
+    o1 = cscale(cadd(v[3], make_float2(-v[3].y, v[3].x)), h);        // h (z + i z)
+    o2 = make_float2(-v[5].y, v[5].x);                               // i z
+    o3 = cscale(csub(make_float2(-v[7].y, v[7].x), v[7]), h);        // h (i z - z)
   } else {
-    o1 = make_float2(h * (v[3].x + v[3].y), h * (v[3].y - v[3].x));
-    o2 = make_float2(v[5].y, -v[5].x);
-    o3 = make_float2(h * (v[7].y - v[7].x), -h * (v[7].x + v[7].y));
+    o1 = cscale(cadd(v[3], make_float2(v[3].y, -v[3].x)), h);        // h (z - i z)
+    o2 = make_float2(v[5].y, -v[5].x);                               // -i z
+    o3 = cscale(csub(make_float2(v[7].y, -v[7].x), v[7]), h);        // h (-i z - z)
   }
   const float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
   v[0] = cadd(e0, o0); v[4] = csub(e0, o0);

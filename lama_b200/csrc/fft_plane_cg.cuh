@@ -53,8 +53,9 @@ FFCB_HD void cg_fwd_rows(int tid, Load&& ld2, Sync&& sync, Store&& st4) {
 #pragma unroll
   for (int k = 0; k < N / 2; ++k) {
     const float2 zk = v[F::at(k)], zm = v[F::at((N - k) & (N - 1))];
-    float2 a = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));      // spectrum of channel 2cp
-    float2 b = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));     // spectrum of channel 2cp+1
+    const float2 cm = make_float2(zm.x, -zm.y), df = csub(zk, cm);
+    float2 a = cscale(cadd(zk, cm), 0.5f);                                   // spectrum of channel 2cp:   (Z[k] + conj Z[-k]) / 2
+    float2 b = cscale(make_float2(df.y, -df.x), 0.5f);                       // spectrum of channel 2cp+1: (Z[k] - conj Z[-k]) / 2i
     if (k == 0) {
       const float2 zn = v[F::at(N / 2)];                                     // Nyquist bin: (Re A[N/2], Re B[N/2])
       a = make_float2(zk.x, zn.x);
@@ -79,8 +80,9 @@ FFCB_HD void cg_fwd_cols(int tid, Load&& ld, Emit&& emit) {
   for (int k = 0; k < N; ++k) {
     const float2 wk = v[F::at(k)], wm = v[F::at((N - k) & (N - 1))];
     // packed: v = X0 + i X32 with both columns real -> Hermitian split
-    const float2 x0 = make_float2(0.5f * (wk.x + wm.x), 0.5f * (wk.y - wm.y));
-    const float2 x32 = make_float2(0.5f * (wk.y + wm.y), -0.5f * (wk.x - wm.x));
+    const float2 cm = make_float2(wm.x, -wm.y), df = csub(wk, cm);
+    const float2 x0 = cscale(cadd(wk, cm), 0.5f);
+    const float2 x32 = cscale(make_float2(df.y, -df.x), 0.5f);
     emit(k, kx, c, packed ? x0 : wk);
     if (packed) emit(k, N / 2, c, x32);
   }
@@ -107,10 +109,12 @@ FFCB_HD void cg_inv_cols(int tid, Load&& ld, Store&& st) {
       cc = ld(k, N / 2);
       d = (m != k) ? ld(m, N / 2) : cc;
     }
-    const float2 h0 = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
-    const float2 h32 = make_float2(0.5f * (cc.x + d.x), 0.5f * (cc.y - d.y));
-    v[k] = packed ? make_float2(h0.x - h32.y, h0.y + h32.x) : a;
-    if (m != k) v[m] = packed ? make_float2(h0.x + h32.y, h32.x - h0.y) : b;
+    const float2 h0 = cscale(cadd(a, make_float2(b.x, -b.y)), 0.5f);          // Hermitian parts of the two columns
+    const float2 h32 = cscale(cadd(cc, make_float2(d.x, -d.y)), 0.5f);
+    const float2 ih = make_float2(-h32.y, h32.x);                            // i * h32
+    const float2 lo = cadd(h0, ih), hi = csub(h0, ih);                       // h0 + i h32,  h0 - i h32
+    v[k] = packed ? lo : a;
+    if (m != k) v[m] = packed ? make_float2(hi.x, -hi.y) : b;                // conj(h0) + i conj(h32) = conj(h0 - i h32)
   }
   F::template run<true>(v);
 #pragma unroll
@@ -131,8 +135,9 @@ FFCB_HD void cg_inv_rows(int tid, Load&& ld4, Sync&& sync, Store&& st2) {
       v[0] = make_float2(q.x, q.z);              // (Re X1[0], Re X2[0])
       v[N / 2] = make_float2(q.y, q.w);          // (Re X1[N/2], Re X2[N/2])
     } else {
-      v[k] = make_float2(q.x - q.w, q.y + q.z);            // X1 + i X2
-      v[N - k] = make_float2(q.x + q.w, q.z - q.y);        // conj(X1) + i conj(X2)
+      const float2 x1 = make_float2(q.x, q.y), ix2 = make_float2(-q.w, q.z), dd = csub(x1, ix2);
+      v[k] = cadd(x1, ix2);                                // X1 + i X2
+      v[N - k] = make_float2(dd.x, -dd.y);                 // conj(X1) + i conj(X2) = conj(X1 - i X2)
     }
   }
   sync();
