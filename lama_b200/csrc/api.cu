@@ -1,6 +1,7 @@
 // extern "C" surface of libffc_b200.so (see include/ffc_b200.h) + error / launch bookkeeping.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -23,6 +24,11 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 void count_launch(int n) { g_launches += n; }
+
+bool l2_hints_enabled() {
+  const char* e = getenv("FFCB_L2_HINTS");
+  return e ? atoi(e) != 0 : true;
+}
 
 int check_tensor(const ffcb_tensor* t, const char* name, bool allow_cg) {
   FFCB_REQUIRE(t != nullptr, "%s: null tensor descriptor", name);

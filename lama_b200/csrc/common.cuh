@@ -12,6 +12,7 @@ namespace ffcb {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
+bool l2_hints_enabled();     // FFCB_L2_HINTS (default on)
 
 #define FFCB_REQUIRE(cond, ...)                 \
   do {                                          \
@@ -143,6 +144,39 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case FFCB_ACT_TANH: return tanhf(v);                              // precise (no --use_fast_math)
     default: return v;
   }
+}
+
+// ---- L2 residency hints (createpolicy + .L2::cache_hint accesses).  The FourierUnit chain hands two spectra from
+// kernel to kernel (rfft2 -> spectral GEMM -> irfft2); they should stay in the 126 MB L2 while the planes that are
+// only streamed through (t in, u out) should not push them out: producers store intermediates with evict_last,
+// consumers read them (and everything read once) with evict_first.  FFCB_L2_HINTS=0 makes every policy "normal".
+__device__ __forceinline__ uint64_t l2_policy(int kind) {     // 0 normal, 1 evict_first, 2 evict_last
+  uint64_t p;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void st_hint_b32(void* p, unsigned v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint_v2(void* p, uint2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint_f4(void* p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float2 ld_hint_f2(const void* p, uint64_t pol) {
+  float2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float4 ld_hint_f4(const void* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
 }
 
 // Mirror targets of an interior pixel in the reflected border ring of a pad==1 view (H, W >= 4):

@@ -58,6 +58,7 @@ struct TcParams {
   long long a_sg[2], a_sb[2], a_sy[2], a_lo[2];
   int a_H[2], a_W[2];
   long long m_total;         // flat mode: B*H*W
+  int hints;                 // L2 residency hints for the planar (FourierUnit chain) outputs
   int desc_swap;             // bring-up: exchange LBO / SBO of the no-swizzle descriptor (FFCB_TC_DESC_SWAP)
   int debug;                 // bring-up knobs (FFCB_TC_DEBUG): 1 no global ld/st in epilogue, 2 no epilogue work,
                              // 4 no MMA issue, 8 no activation loads
@@ -498,12 +499,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           // neighbours' inside every channel group, so plain 16-byte stores are whole lines — no staging tile
           if (valid && !(p.debug & 1)) {
             float* ob = reinterpret_cast<float*>(p.out.ptr) + pix_off(p.out, b, y, x);
+            const uint64_t pol = l2_policy(p.hints ? 2 : 0);       // consumed by the next kernel of the chain
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const int n = n0 + 4 * q;
               if (n < p.N)
-                *reinterpret_cast<float4*>(ob + (long long)(n / p.out.cg) * p.out.sg + (n % p.out.cg)) =
-                    make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                st_hint_f4(ob + (long long)(n / p.out.cg) * p.out.sg + (n % p.out.cg),
+                           make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), pol);
             }
           }
           continue;
@@ -660,6 +662,7 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   {
     const char* sw = getenv("FFCB_TC_DESC_SWAP");
     p.desc_swap = sw ? atoi(sw) : 0;
+    p.hints = l2_hints_enabled() ? 1 : 0;
   }
   p.addend = d->addend.ptr ? make_view(d->addend) : null_view();
   p.shift = d->shift;

@@ -28,12 +28,13 @@ struct CgArgs {
   void* spec;       long long sp_sg, sp_sb;  unsigned sp_sy, sp_sx; long long sp_lo;   // spectrum (cg 8)
   void* out;        long long out_sg, out_sb; unsigned out_sy, out_sx; long long out_lo;
   float scale;
+  int hints;      // L2 residency hints on (common.cuh: l2_policy)
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -58,11 +59,13 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) rfft2_plane
   {   // plane set -> shared memory (real layout), 16 bytes per pixel, lanes along x
     const float* src = a.in + (long long)group * a.in_sg + (long long)blockIdx.y * a.in_sb;
     const uint32_t base = smem_addr(smem);
+    const uint64_t pol_in = l2_policy(a.hints ? 1 : 0);       // the real planes are streamed through
 #pragma unroll 8
     for (int i = 0; i < Cfg::px_iters; ++i) {
       int y, x;
       cg_pixel_slot<N>(tid, i, y, x);
-      cp_async16(base + 4u * (unsigned)cg_real_idx<N>(y, x, 0), src + ((unsigned)y * a.in_sy + (unsigned)x * a.in_sx));
+      cp_async16(base + 4u * (unsigned)cg_real_idx<N>(y, x, 0), src + ((unsigned)y * a.in_sy + (unsigned)x * a.in_sx),
+                 pol_in);
     }
     cp_async_wait_all();
   }
@@ -76,14 +79,16 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) rfft2_plane
                          (long long)blockIdx.y * a.sp_sb;
     unsigned short* lo = hi + a.sp_lo;
     const float scale = a.scale;
+    const uint64_t pol_sp = l2_policy(a.hints ? 2 : 0);       // the spectrum is the next kernel's GEMM operand: keep it in L2
     cg_fwd_cols<N>(
         tid, [&](int i2) { return S[i2]; },
         [&](int ky, int kx, int c, float2 z) {
           const unsigned o = (unsigned)ky * a.sp_sy + (unsigned)kx * a.sp_sx + 2u * (unsigned)c;
           unsigned h, l;
-          split_pair(z.x * scale, z.y * scale, h, l);
-          *reinterpret_cast<unsigned*>(hi + o) = h;
-          *reinterpret_cast<unsigned*>(lo + o) = l;
+          const float2 zs = cscale(z, scale);
+          split_pair(zs.x, zs.y, h, l);
+          st_hint_b32(hi + o, h, pol_sp);
+          st_hint_b32(lo + o, l, pol_sp);
         });
   }
 }
@@ -100,11 +105,10 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) irfft2_plan
   {
     const float* sp = reinterpret_cast<const float*>(a.spec) + (long long)group * a.sp_sg +
                       (long long)blockIdx.y * a.sp_sb + 2 * (tid & 3);
+    const uint64_t pol_sp = l2_policy(a.hints ? 1 : 0);       // last use of the post-GEMM spectrum
     cg_inv_cols<N>(
         tid,
-        [&](int ky, int kx) {
-          return __ldg(reinterpret_cast<const float2*>(sp + ((unsigned)ky * a.sp_sy + (unsigned)kx * a.sp_sx)));
-        },
+        [&](int ky, int kx) { return ld_hint_f2(sp + ((unsigned)ky * a.sp_sy + (unsigned)kx * a.sp_sx), pol_sp); },
         [&](int i2, float2 z) { S[i2] = z; });
   }
   __syncthreads();
@@ -115,6 +119,7 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) irfft2_plan
   {   // epilogue: whole pixels (4 channels), lanes along x: + residual, scale, convert, store
     const float* res = HAS_RES ? a.in + (long long)group * a.in_sg + (long long)blockIdx.y * a.in_sb : nullptr;
     const float scale = a.scale;
+    const uint64_t pol_res = l2_policy(a.hints ? 1 : 0), pol_out = l2_policy(a.hints ? 2 : 0);   // u feeds the next contraction
 #pragma unroll 2
     for (int i0 = 0; i0 < Cfg::px_iters; i0 += 8) {
       float4 q[8];
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) irfft2_plan
       for (int j = 0; j < 8; ++j) {
         int y, x;
         cg_pixel_slot<N>(tid, i0 + j, y, x);
-        q[j] = HAS_RES ? __ldg(reinterpret_cast<const float4*>(res + ((unsigned)y * a.in_sy + (unsigned)x * a.in_sx)))
+        q[j] = HAS_RES ? ld_hint_f4(res + ((unsigned)y * a.in_sy + (unsigned)x * a.in_sx), pol_res)
                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
@@ -140,12 +145,12 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) irfft2_plan
           unsigned h0, l0, h1, l1;
           split_pair(r0, r1, h0, l0);
           split_pair(r2, r3, h1, l1);
-          *reinterpret_cast<uint2*>(hi + o) = make_uint2(h0, h1);
-          *reinterpret_cast<uint2*>(hi + a.out_lo + o) = make_uint2(l0, l1);
+          st_hint_v2(hi + o, make_uint2(h0, h1), pol_out);
+          st_hint_v2(hi + a.out_lo + o, make_uint2(l0, l1), pol_out);
         } else {
           float* op = reinterpret_cast<float*>(a.out) + (long long)group * a.out_sg +
                       (long long)blockIdx.y * a.out_sb + ((unsigned)y * a.out_sy + (unsigned)x * a.out_sx);
-          *reinterpret_cast<float4*>(op) = make_float4(r0, r1, r2, r3);
+          st_hint_f4(op, make_float4(r0, r1, r2, r3), pol_out);
         }
       }
     }
@@ -200,6 +205,7 @@ int rfft2_plane64_cg(const ffcb_tensor* in, const ffcb_tensor* spec, cudaStream_
   a.spec = spec->ptr; a.sp_sg = spec->sg; a.sp_sb = spec->sb; a.sp_sy = (unsigned)spec->sy; a.sp_sx = (unsigned)spec->sx;
   a.sp_lo = spec->lo_off;
   a.scale = 1.0f / (float)in->H;
+  a.hints = l2_hints_enabled() ? 1 : 0;
   return in->H == 64 ? launch_fwd_cg<64>(a, in->C / 4, in->B, stream) : launch_fwd_cg<32>(a, in->C / 4, in->B, stream);
 }
 
@@ -235,6 +241,7 @@ int irfft2_plane64_cg(const ffcb_tensor* spec, const ffcb_tensor* residual, cons
   a.out = out->ptr; a.out_sg = out->sg; a.out_sb = out->sb; a.out_sy = (unsigned)out->sy; a.out_sx = (unsigned)out->sx;
   a.out_lo = out->lo_off;
   a.scale = 1.0f / (float)out->H;
+  a.hints = l2_hints_enabled() ? 1 : 0;
   const bool split = out->fmt == FFCB_BF16X2;
   return out->H == 64 ? dispatch_inv_cg<64>(a, out->C / 4, out->B, has_res, split, stream)
                       : dispatch_inv_cg<32>(a, out->C / 4, out->B, has_res, split, stream);
