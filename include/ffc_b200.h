@@ -222,6 +222,22 @@ int ffcb_nhwc_to_nchw(const ffcb_tensor* in, float* y_nchw, ffcb_stream_t stream
 /* (re)write the reflected 1-pixel border ring of a pad==1 view from its interior */
 int ffcb_fill_reflect_border(const ffcb_tensor* t, ffcb_stream_t stream);
 
+/*
+ * Input gradients through FFCResnetBlock (reference: evaluation/refinement.py:137-167 optimises the
+ * block inputs by back-propagation).  With eval-mode BN folded, the backward pass of the block re-uses ffcb_conv (3x3
+ * taps flipped, zero border, transposed weights) and the ffcb_rfft2 / ffcb_irfft2 pair itself; these two elementwise
+ * steps complete it:
+ *   ffcb_relu_bwd:            out = dy * [y > 0]   — nn.ReLU backward with the forward activation y (ffc.py:101,
+ *                             133, 253-254); any storage format / layout on each of the three views
+ *   ffcb_fold_reflect_border: adjoint of the reflect padding of ffc.py:189 (padding_mode='reflect', pad 1):
+ *                             out[b,y,x,c] = sum of gpad over the padded positions that reflect onto (y,x)
+ *                                           (+ add0[b,y,x,c-add0_c0] + add1[b,y,x,c-add1_c0] where defined);
+ *                             gpad is (B,H+2,W+2,C); addends are optional (NULL) channel slices of the output
+ */
+int ffcb_relu_bwd(const ffcb_tensor* dy, const ffcb_tensor* y, const ffcb_tensor* out, ffcb_stream_t stream);
+int ffcb_fold_reflect_border(const ffcb_tensor* gpad, const ffcb_tensor* add0, int add0_c0, const ffcb_tensor* add1,
+                             int add1_c0, const ffcb_tensor* out, ffcb_stream_t stream);
+
 /* number of kernel launches issued by this library on the calling thread since the last
  * ffcb_reset_launch_count() — bench.py reports it as "gpu_launches" */
 long long ffcb_launch_count(void);

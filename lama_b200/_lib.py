@@ -63,6 +63,8 @@ SIGNATURES = {
     "ffcb_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _PT, C.c_void_p]),
     "ffcb_nhwc_to_nchw": (C.c_int, [_PT, C.c_void_p, C.c_void_p]),
     "ffcb_fill_reflect_border": (C.c_int, [_PT, C.c_void_p]),
+    "ffcb_relu_bwd": (C.c_int, [_PT, _PT, _PT, C.c_void_p]),
+    "ffcb_fold_reflect_border": (C.c_int, [_PT, _PT, C.c_int, _PT, C.c_int, _PT, C.c_void_p]),
     "ffcb_launch_count": (C.c_longlong, []),
     "ffcb_reset_launch_count": (None, []),
 }

@@ -75,6 +75,9 @@ int head_gather7(const ffcb_tensor*, const float*, int, int, float*, cudaStream_
 int stem_pack_u8(const uint8_t*, const uint8_t*, int, int, int, const ffcb_tensor*, cudaStream_t);
 int head_gather7_blend_u8(const ffcb_tensor*, const float*, int, const uint8_t*, const uint8_t*, int, int, uint8_t*,
                           cudaStream_t);
+int relu_bwd(const ffcb_tensor*, const ffcb_tensor*, const ffcb_tensor*, cudaStream_t);
+int fold_reflect_border(const ffcb_tensor*, const ffcb_tensor*, int, const ffcb_tensor*, int, const ffcb_tensor*,
+                        cudaStream_t);
 
 static int check_conv(const ffcb_conv_desc* d) {
   FFCB_REQUIRE(d != nullptr, "conv: null descriptor");
@@ -194,6 +197,15 @@ int ffcb_nhwc_to_nchw(const ffcb_tensor* in, float* y, ffcb_stream_t stream) {
 
 int ffcb_fill_reflect_border(const ffcb_tensor* t, ffcb_stream_t stream) {
   return fill_reflect_border(t, (cudaStream_t)stream);
+}
+
+int ffcb_relu_bwd(const ffcb_tensor* dy, const ffcb_tensor* y, const ffcb_tensor* out, ffcb_stream_t stream) {
+  return relu_bwd(dy, y, out, (cudaStream_t)stream);
+}
+
+int ffcb_fold_reflect_border(const ffcb_tensor* gpad, const ffcb_tensor* add0, int add0_c0, const ffcb_tensor* add1,
+                             int add1_c0, const ffcb_tensor* out, ffcb_stream_t stream) {
+  return fold_reflect_border(gpad, add0, add0_c0, add1, add1_c0, out, (cudaStream_t)stream);
 }
 
 long long ffcb_launch_count(void) { return g_launches; }

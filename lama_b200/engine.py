@@ -187,6 +187,28 @@ class BorderOp:
 
 
 @dataclass
+class ReluBwdOp:
+    """out = dy * [y > 0] (ffcb_relu_bwd): ReLU backward with the forward activation."""
+    dy: TV
+    y: TV
+    out: TV
+
+
+@dataclass
+class FoldOp:
+    """Adjoint of the 1-pixel reflect padding (ffcb_fold_reflect_border): gradient w.r.t. the padded plane ``gpad``
+    (B,H+2,W+2,C) folded onto the interior, plus optional addends written as (view, first output channel)."""
+    gpad: TV
+    addends: List[Tuple[TV, int]]
+    out: TV
+
+
+@dataclass
+class SplitOp:
+    """Boundary between the forward and the backward part of a forward+backward program (no kernel)."""
+
+
+@dataclass
 class Program:
     kind: str
     math: int
@@ -195,6 +217,7 @@ class Program:
     inputs: Dict[str, Tuple[int, ...]] = field(default_factory=dict)    # name -> NCHW shape
     outputs: Dict[str, Tuple[int, ...]] = field(default_factory=dict)
     dtypes: Dict[str, torch.dtype] = field(default_factory=dict)       # inputs / outputs that are not float32
+    meta: Dict[tuple, dict] = field(default_factory=dict)              # buffers a backward program needs (per module)
 
     def buf(self, name, B, H, W, C, gemm=False, halo=False, halo_px=1, cg=0) -> Buf:
         """``gemm``: the buffer is an operand of a contraction; ``halo``: that contraction has spatial taps.
@@ -419,6 +442,7 @@ def emit_fourier_unit(prog: Program, fu, t: TV, out: TV, residual: Optional[TV])
     planar = t.buf.cg == 4      # FourierUnit chain in channel-group planar storage (emit_spectral_transform decides)
     S = prog.buf("spectrum", b, h, wf, cin2, gemm=True, cg=8 if planar else 0)
     Z = prog.buf("spectrum_out", b, h, wf, cout2, cg=8 if planar else 0)
+    prog.meta[("fu", id(fu))] = dict(S=S, Z=Z)
     scale, shift = P.bn_scale_shift(fu.bn)
     pk = P.pack_conv([(fu.conv_layer.weight, 0, 0, 0)], scale, shift, act=L.ACT_RELU,
                      device=fu.conv_layer.weight.device)
@@ -464,6 +488,7 @@ def emit_spectral_transform(prog: Program, st, x: TV, u_consumer=None) -> Tuple[
         pk1 = P.pack_conv([(st.conv1[0].weight, 0, x.c0, 0)], s1, b1, act=L.ACT_RELU, device=dev)
         tag = "st.conv1+bn+relu"
     prog.ops.append(ConvOp(pk1, [TV(x.buf), None], TV(T), tag=tag))
+    prog.meta[("st", id(st))] = dict(T=T, U=U)
     residual = TV(T)
     if st.enable_lfu:
         # xs = lfu(quadrants of the first c/4 channels) tiled 2x2; XS = T + tile(xs) becomes the residual of the main
@@ -561,6 +586,114 @@ def emit_resnet_block(prog: Program, blk, X: Buf, cl: int, cg: int, in_place: bo
     return out
 
 
+def block_grad_supported(blk) -> bool:
+    """Input gradients exist for the residual-block flavour of the shipped generators: two
+    FFC_BN_ACT with local and global halves on both sides, 3x3 reflect convs, stride 1, ReLU, no LFU / gating."""
+    if blk.inline or not blk.native_supported():
+        return False
+    for m in (blk.conv1, blk.conv2):
+        f = m.ffc
+        if any(isinstance(c, nn.Identity) for c in (f.convl2l, f.convl2g, f.convg2l, f.convg2g)):
+            return False
+        st = f.convg2g
+        if (f.convl2l.kernel_size != (3, 3) or f.convl2l.stride != (1, 1) or f.convl2l.padding != (1, 1)
+                or st.enable_lfu or st.stride != 1 or _act_code(m.act_l) != L.ACT_RELU or _act_code(m.act_g) != L.ACT_RELU):
+            return False
+    return True
+
+
+def _flip_t(w: torch.Tensor) -> torch.Tensor:
+    """[N, C, k, k] forward conv weight -> [C, N, k, k] weight of the gradient convolution (taps flipped)."""
+    return w.detach().double().flip(-1, -2).transpose(0, 1).contiguous()
+
+
+def emit_ffc_bn_act_backward(prog: Program, m, Y: Buf, DO: TV, in_cl: int, in_cg: int,
+                             extra: Optional[TV] = None) -> Buf:
+    """Gradient of one FFC_BN_ACT (ffc.py:205-225, 251-255; eval-mode BN) w.r.t. its input [x_l | x_g], given the
+    gradient ``DO`` w.r.t. its output and the forward activations kept in ``prog`` (Y, t, z).  Every step is one of
+    the forward's own operations with transposed weights:
+      dP   = dO * [Y > 0]
+      d[x_l|x_g]_pad = 3x3 gradient convolutions of dP (flipped taps, zero border) -> folded back (reflect adjoint)
+      du   = W2^T (s_g dP_g);  dz = rfft2(du) * [z > 0];  ds = Wf^T (s_f dz);  dt = du + irfft2(ds)
+             (the half-spectrum weights 2 and 1/2 of the two adjoint transforms cancel around the per-position GEMM)
+      dx_g += W1^T (s_1 (dt * [t > 0]))
+    ``extra``: one more gradient added into the result (the block's identity path)."""
+    f = m.ffc
+    st = f.convg2g
+    dev = f.convl2l.weight.device
+    b, h, w = Y.B, Y.H, Y.W
+    out_cl, out_cg = f.convl2l.out_channels, f.convl2g.out_channels
+    sl, _ = _fold(m.bn_l, out_cl, dev)
+    sg, _ = _fold(m.bn_g, out_cg, dev)
+    s1, _ = P.bn_scale_shift(st.conv1[1])
+    sf, _ = P.bn_scale_shift(st.fu.bn)
+    saved_st, saved_fu = prog.meta[("st", id(st))], prog.meta[("fu", id(st.fu))]
+    T, Z = saved_st["T"], saved_fu["Z"]
+    planar = T.cg == 4
+    c = st.conv1[0].out_channels
+    wf_ = w // 2 + 1
+    k4 = lambda t: t[:, :, None, None]      # noqa: E731
+    col = lambda v: v.double()[:, None, None, None]   # noqa: E731
+
+    DP = prog.buf("grad.dP", b, h, w, out_cl + out_cg, gemm=True)
+    prog.ops.append(ReluBwdOp(DO, TV(Y), TV(DP)))
+    GP = prog.buf("grad.gpad", b, h + 2, w + 2, in_cl + in_cg)
+    w_to_l = torch.cat([f.convl2l.weight.detach().double() * col(sl), f.convl2g.weight.detach().double() * col(sg)], dim=0)
+    pk_a = P.pack_conv([(_flip_t(w_to_l), 0, 0, 2)], None, None, border=L.BORDER_ZERO, device=dev)
+    prog.ops.append(ConvOp(pk_a, [TV(DP), None], TV(GP, 0, in_cl), tag="grad: d x_l (3x3^T of dP_l|dP_g)"))
+    pk_b = P.pack_conv([(_flip_t(f.convg2l.weight.detach().double() * col(sl)), 0, 0, 2)], None, None,
+                       border=L.BORDER_ZERO, device=dev)
+    prog.ops.append(ConvOp(pk_b, [TV(DP), None], TV(GP, in_cl, in_cg), tag="grad: d x_g (3x3^T of dP_l)"))
+
+    DU = prog.buf("grad.du", b, h, w, c, cg=4 if planar else 0)
+    w2 = st.conv2.weight.detach().double()[:, :, 0, 0] * sg.double()[:, None]            # [out_cg, c]
+    pk2 = P.pack_conv([(k4(w2.t().contiguous()), 0, out_cl, 0)], None, None, device=dev)
+    prog.ops.append(ConvOp(pk2, [TV(DP), None], TV(DU), tag="grad: du = conv2^T"))
+    DZ = prog.buf("grad.dz", b, h, wf_, 2 * c, gemm=True, cg=8 if planar else 0)
+    prog.ops.append(RfftOp(TV(DU), TV(DZ)))
+    DPZ = prog.buf("grad.dpz", b, h, wf_, 2 * c, gemm=True, cg=8 if planar else 0)
+    prog.ops.append(ReluBwdOp(TV(DZ), TV(Z), TV(DPZ)))
+    DS = prog.buf("grad.ds", b, h, wf_, 2 * c, cg=8 if planar else 0)
+    wfu = st.fu.conv_layer.weight.detach().double()[:, :, 0, 0] * sf.double()[:, None]  # [2c out, 2c in]
+    pkf = P.pack_conv([(k4(wfu.t().contiguous()), 0, 0, 0)], None, None, device=dev)
+    prog.ops.append(ConvOp(pkf, [TV(DPZ), None], TV(DS), tag="grad: ds = fu.conv_layer^T"))
+    DT = prog.buf("grad.dt", b, h, w, c, cg=4 if planar else 0)
+    prog.ops.append(IrfftOp(TV(DS), TV(DU), TV(DT)))
+    DPT = prog.buf("grad.dpt", b, h, w, c, gemm=True, cg=8 if planar else 0)
+    prog.ops.append(ReluBwdOp(TV(DT), TV(T), TV(DPT)))
+    DG = prog.buf("grad.dg", b, h, w, in_cg)
+    w1 = st.conv1[0].weight.detach().double()[:, :, 0, 0] * s1.double()[:, None]        # [c, in_cg]
+    pk1 = P.pack_conv([(k4(w1.t().contiguous()), 0, 0, 0)], None, None, device=dev)
+    prog.ops.append(ConvOp(pk1, [TV(DPT), None], TV(DG), tag="grad: d x_g += conv1^T"))
+    DX = prog.buf("grad.dx", b, h, w, in_cl + in_cg)
+    prog.ops.append(FoldOp(TV(GP), [(TV(DG), in_cl)] + ([(extra, 0)] if extra is not None else []), TV(DX)))
+    return DX
+
+
+def build_block_grad_program(prog: Program, blk, sl: Tuple[int, ...], sg: Tuple[int, ...]):
+    """Forward of FFCResnetBlock WITHOUT the identity add (all activations kept) | SplitOp | input-gradient program.
+    inputs  x0, x1 (forward), g0, g1 (gradient w.r.t. the block outputs);
+    outputs y0, y1 = conv2(conv1(x)) halves, dx0, dx1 = gradients w.r.t. x_l, x_g (identity path included)."""
+    b, cl, h, w = sl
+    cg = sg[1]
+    prog.inputs.update(x0=tuple(sl), x1=tuple(sg), g0=tuple(sl), g1=tuple(sg))
+    X = prog.buf("in", b, h, w, cl + cg, gemm=True, halo=True)
+    prog.ops.append(ToNHWC("x0", TV(X, 0, cl)))
+    prog.ops.append(ToNHWC("x1", TV(X, cl, cg)))
+    Y1, _, _ = emit_ffc_bn_act(prog, blk.conv1, X, cl, cg)
+    Y2, _, _ = emit_ffc_bn_act(prog, blk.conv2, Y1, cl, cg)
+    prog.ops.append(ToNCHW(TV(Y2, 0, cl), "y0")); prog.outputs["y0"] = tuple(sl)
+    prog.ops.append(ToNCHW(TV(Y2, cl, cg), "y1")); prog.outputs["y1"] = tuple(sg)
+    prog.ops.append(SplitOp())
+    DO = prog.buf("grad.dout", b, h, w, cl + cg)
+    prog.ops.append(ToNHWC("g0", TV(DO, 0, cl)))
+    prog.ops.append(ToNHWC("g1", TV(DO, cl, cg)))
+    D1 = emit_ffc_bn_act_backward(prog, blk.conv2, Y2, TV(DO), cl, cg)
+    D0 = emit_ffc_bn_act_backward(prog, blk.conv1, Y1, TV(D1), cl, cg, extra=TV(DO))
+    prog.ops.append(ToNCHW(TV(D0, 0, cl), "dx0")); prog.outputs["dx0"] = tuple(sl)
+    prog.ops.append(ToNCHW(TV(D0, cl, cg), "dx1")); prog.outputs["dx1"] = tuple(sg)
+
+
 def build_module_program(module, kind: str, shapes: Sequence[Optional[Tuple[int, ...]]], math: int) -> Program:
     """Programs for stand-alone module calls: NCHW float in -> channels-last inside -> NCHW float out."""
     prog = Program(kind=kind, math=math)
@@ -604,6 +737,8 @@ def build_module_program(module, kind: str, shapes: Sequence[Optional[Tuple[int,
             prog.ops.append(ToNCHW(TV(Y, 0, ocl), "y0")); prog.outputs["y0"] = (b, ocl, Y.H, Y.W)
         if ocg:
             prog.ops.append(ToNCHW(TV(Y, ocl, ocg), "y1")); prog.outputs["y1"] = (b, ocg, Y.H, Y.W)
+    elif kind == "resnet_block_grad":
+        build_block_grad_program(prog, module, shapes[0], shapes[1])
     elif kind == "generator":
         build_generator_program(prog, module, shapes[0])
     elif kind.startswith("generator_u8"):            # "generator_u8:<pad modulo>", shapes = (img, mask)
@@ -757,6 +892,8 @@ class CudaExecutor:
         self._keep = []          # ctypes objects / tensors that must outlive the calls
         self.calls = []          # (fn, args) with a trailing stream argument appended at run time
         self.input_slots: Dict[str, List[Tuple[int, int]]] = {}   # input name -> [(call idx, arg idx)]
+        self.split = None        # forward+backward programs: index of the first backward call (SplitOp)
+        self.generation = 0      # bumped by every forward part: a stale backward must not read newer activations
         for op in prog.ops:
             self._bind(op)
 
@@ -885,6 +1022,16 @@ class CudaExecutor:
             for i, s in enumerate(pk.segs):
                 d.seg[i] = L.KSeg(s.src, s.dy, s.dx, s.c0, s.nch)
             self.calls.append(("ffcb_conv:" + op.tag, lib.ffcb_conv, [C.byref(d)]))
+        elif isinstance(op, SplitOp):
+            self.split = len(self.calls)
+        elif isinstance(op, ReluBwdOp):
+            a, y, o = (self._ref(self.tensor(v)) for v in (op.dy, op.y, op.out))
+            self.calls.append(("ffcb_relu_bwd", lib.ffcb_relu_bwd, [C.byref(a), C.byref(y), C.byref(o)]))
+        elif isinstance(op, FoldOp):
+            g, o = self._ref(self.tensor(op.gpad)), self._ref(self.tensor(op.out))
+            adds = [(C.byref(self._ref(self.tensor(tv))), c0) for tv, c0 in op.addends] + [(None, 0)] * 2
+            self.calls.append(("ffcb_fold_reflect_border", lib.ffcb_fold_reflect_border,
+                               [C.byref(g), adds[0][0], adds[0][1], adds[1][0], adds[1][1], C.byref(o)]))
         elif isinstance(op, BorderOp):
             t = self._ref(self.tensor(op.view))
             self.calls.append(("ffcb_fill_reflect_border", lib.ffcb_fill_reflect_border, [C.byref(t)]))
@@ -898,16 +1045,32 @@ class CudaExecutor:
         else:
             raise TypeError(op)
 
-    def run(self, inputs: Dict[str, torch.Tensor], stream: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    def run(self, inputs: Dict[str, torch.Tensor], stream: Optional[int] = None,
+            part: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """Issue every call on ``stream`` (default: torch's current stream).  Outputs are the
-        executor's own tensors (overwritten by the next run)."""
+        executor's own tensors (overwritten by the next run).  ``part``: 0 / 1 run only the forward / backward half
+        of a forward+backward program (inputs of the other half may be absent)."""
         if torch.cuda.current_device() != self.dev_index:
             # the module lives on another GPU than the caller's current device (one process driving several GPUs):
             # kernels must be launched with that device current, as torch's own ops do through their device guards
             with torch.cuda.device(self.dev_index):
-                return self.run(inputs, stream)
+                return self.run(inputs, stream, part)
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
+        if part is not None:
+            assert self.split is not None, "not a forward+backward program"
+            lo, hi = (0, self.split) if part == 0 else (self.split, len(self.calls))
+            for name, slots in self.input_slots.items():
+                if name in inputs:
+                    for ci, ai in slots:
+                        self.calls[ci][2][ai] = inputs[name].data_ptr()
+            for name, fn, args in self.calls[lo:hi]:
+                rc = fn(*args, stream)
+                if rc != 0:
+                    L.check(rc, name)
+            if part == 0:
+                self.generation += 1
+            return self.outputs
         for name, slots in self.input_slots.items():
             t = inputs[name]
             dt = self.prog.dtypes.get(name, torch.float32)
@@ -1032,6 +1195,36 @@ def get_executor(module, kind: str, tensors, math: Optional[int] = None,
         cache.pop(next(iter(cache)))
     cache[key] = (sig, ex)
     return ex
+
+
+class _BlockGradFn(torch.autograd.Function):
+    """FFCResnetBlock with native forward AND native input gradients: what the reference's
+    refinement loop (evaluation/refinement.py:137-167) needs — it optimises the block inputs, the weights are frozen.
+    Forward runs the first half of a ``resnet_block_grad`` program (activations stay in the executor's buffers),
+    backward the second half.  One executor per (module, shape): a second forward before the backward of the first
+    would overwrite those activations, which raises instead of returning wrong gradients."""
+
+    @staticmethod
+    def forward(ctx, module, x_l, x_g):
+        ex = get_executor(module, "resnet_block_grad", (x_l, x_g))
+        xl, xg = x_l.detach().contiguous(), x_g.detach().contiguous()
+        outs = ex.run({"x0": xl, "x1": xg}, part=0)
+        ctx.ex, ctx.generation = ex, ex.generation
+        return xl + outs["y0"], xg + outs["y1"]
+
+    @staticmethod
+    def backward(ctx, g_l, g_g):
+        ex = ctx.ex
+        if ex.generation != ctx.generation:
+            raise RuntimeError("lama_b200: the same FFCResnetBlock ran forward again (same shape) before this backward; "
+                               "its saved activations were overwritten")
+        outs = ex.run({"g0": g_l.contiguous(), "g1": g_g.contiguous()}, part=1)
+        return None, outs["dx0"].clone(), outs["dx1"].clone()
+
+
+def block_with_input_grad(module, x_l, x_g):
+    """(out_l, out_g) of an FFCResnetBlock, differentiable w.r.t. x_l / x_g on the native path."""
+    return _BlockGradFn.apply(module, x_l, x_g)
 
 
 def run_module(module, kind: str, tensors):

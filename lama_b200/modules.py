@@ -307,6 +307,19 @@ class FFCResnetBlock(nn.Module):
         return (isinstance(self.conv1, FFC_BN_ACT) and isinstance(self.conv2, FFC_BN_ACT)
                 and self.conv1.native_supported() and self.conv2.native_supported())
 
+    def _input_grad_native(self, x_l, x_g) -> bool:
+        """Autograd is on, the weights are frozen (``model.freeze()``, bin/predict.py:59) and at least one input wants a
+        gradient: the native forward + input-gradient program applies (LAMA_B200_NATIVE_GRAD=0 disables it)."""
+        if not (torch.is_grad_enabled() and torch.is_tensor(x_l) and torch.is_tensor(x_g) and not self.training
+                and not torch.jit.is_tracing() and os.environ.get("LAMA_B200_NATIVE_GRAD", "1") == "1"):
+            return False
+        if not (x_l.is_cuda and x_g.is_cuda and x_l.dtype == torch.float32 and x_g.dtype == torch.float32
+                and (x_l.requires_grad or x_g.requires_grad)):
+            return False
+        if any(p.requires_grad for p in self.parameters()):
+            return False
+        return _engine.block_grad_supported(self) and _engine.ffc_bn_act_shapes_ok(self.conv1, x_l, x_g)
+
     def forward(self, x):
         if self.inline:
             g = self.conv1.ffc.global_in_num
@@ -316,6 +329,9 @@ class FFCResnetBlock(nn.Module):
         if (_native_ok(x_l, x_g) and self.native_supported()
                 and _engine.ffc_bn_act_shapes_ok(self.conv1, x_l, x_g)):
             out = _engine.run_module(self, "resnet_block", (x_l, x_g))
+        elif self._input_grad_native(x_l, x_g):
+            # refinement (evaluation/refinement.py:137-167): frozen weights, gradients w.r.t. the feature maps only
+            out = _engine.block_with_input_grad(self, x_l, x_g)
         else:
             _fallback("FFCResnetBlock options / mode")
             y_l, y_g = self.conv2(self.conv1((x_l, x_g)))

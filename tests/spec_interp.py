@@ -108,8 +108,23 @@ class SpecInterpreter:
                 add = self.read(op.addend).clone() if op.addend is not None else None
                 y = apply_packed_reference(op.packed, ins, op.out.hw, addend=add, addend_post=op.addend_post)
                 self.write(op.out, y)
-            elif isinstance(op, E.BorderOp):
+            elif isinstance(op, E.BorderOp) or isinstance(op, E.SplitOp):
                 pass        # the interpreter's buffers have no physical ring (taps use index math)
+            elif isinstance(op, E.ReluBwdOp):
+                self.write(op.out, self.read(op.dy) * (self.read(op.y) > 0))
+            elif isinstance(op, E.FoldOp):
+                g = self.read(op.gpad)                                  # [B, H+2, W+2, C]
+                h, w = g.shape[1] - 2, g.shape[2] - 2
+                acc = torch.zeros(g.shape[0], h, w, g.shape[3], dtype=g.dtype)
+                for yp in range(h + 2):
+                    y = abs(yp - 1); y = 2 * h - 2 - y if y >= h else y
+                    for xp in range(w + 2):
+                        x = abs(xp - 1); x = 2 * w - 2 - x if x >= w else x
+                        acc[:, y, x] += g[:, yp, xp]
+                for tv, c0 in op.addends:
+                    a = self.read(tv)
+                    acc[..., c0:c0 + a.shape[-1]] += a
+                self.write(op.out, acc)
             elif isinstance(op, E.RfftOp):
                 x = self.read(op.inp)                                            # [B,H,W,C]
                 f = torch.fft.rfftn(x, dim=(1, 2), norm="ortho")                 # [B,H,Wf,C]

@@ -545,6 +545,37 @@ def test_to_jit_trace_on_cuda_keeps_the_native_kernels(tc_math, tmp_path):
     assert torch.equal(out, eager) and torch.equal(out2, want2)
 
 
+@pytest.mark.parametrize("shape", [(2, 128, 384, 32, 32), (1, 128, 384, 64, 64), (1, 32, 96, 12, 20)])
+def test_resnet_block_input_gradients_vs_autograd_oracle(shape, math_mode):
+    """SURVEY.md row f3 groundwork: dL/dx_l, dL/dx_g through a native FFCResnetBlock (torch.autograd.Function around
+    the forward+backward program) vs autograd through the torch-CPU oracle port; rel <= 1e-4 (fp32 arm) / 5e-4
+    (split-bf16 operands in both directions).  Shapes: the verdict's (2, 128+384, 32, 32) — planar 32x32 chain —, the
+    64x64 bottleneck, and a small non-power-of-two plane on the general FFT kernels."""
+    b, cl, cg, h, w = shape
+    blk = seeded_parameters_(M.FFCResnetBlock(cl + cg, padding_type="reflect", norm_layer=torch.nn.BatchNorm2d,
+                                              activation_layer=torch.nn.ReLU, ratio_gin=0.75, ratio_gout=0.75,
+                                              enable_lfu=False).eval(), 4, gain=1.0)
+    sd = {k: v.clone() for k, v in blk.state_dict().items()}
+    for p_ in blk.parameters():
+        p_.requires_grad_(False)                              # model.freeze() (bin/predict.py:59)
+    blk = blk.to(DEV)
+    g = torch.Generator().manual_seed(2)
+    xl, xg = torch.randn(b, cl, h, w, generator=g), torch.randn(b, cg, h, w, generator=g)
+    gl, gg = torch.randn(b, cl, h, w, generator=g), torch.randn(b, cg, h, w, generator=g)
+    a_l, a_g = xl.to(DEV).requires_grad_(True), xg.to(DEV).requires_grad_(True)
+    L.get_lib().ffcb_reset_launch_count()
+    o_l, o_g = blk((a_l, a_g))
+    ((o_l * gl.to(DEV)).sum() + (o_g * gg.to(DEV)).sum()).backward()
+    assert L.get_lib().ffcb_launch_count() > 20, "the native forward+backward program did not run"
+    r_l, r_g = xl.clone().requires_grad_(True), xg.clone().requires_grad_(True)
+    q_l, q_g = otc.ffc_resnet_block(r_l, r_g, sd, "", ratio_gout=0.75)
+    ((q_l * gl).sum() + (q_g * gg).sum()).backward()
+    tol = 1e-4 if math_mode == "fp32" else 5e-4
+    assert _rel_err(o_l.detach().cpu().numpy(), q_l.detach().numpy()) < TOL[math_mode]
+    assert _rel_err(a_l.grad.cpu().numpy(), r_l.grad.numpy()) < tol
+    assert _rel_err(a_g.grad.cpu().numpy(), r_g.grad.numpy()) < tol
+
+
 def test_stage_by_stage_matches_whole_program():
     """predict_inner_features.py:84 iterates generator.model stage by stage: tuple outputs at every FFC
     stage, each stage on its own native program, same result as the fused whole-generator program."""

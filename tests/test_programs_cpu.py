@@ -253,6 +253,35 @@ def test_modules_stay_copyable_and_picklable_after_native_use():
     E.invalidate(g)
 
 
+def test_resnet_block_input_gradient_program_matches_autograd():
+    """the forward+backward program of FFCResnetBlock (gradients w.r.t. x_l, x_g; eval-mode BN, frozen
+    weights) interpreted on the CPU vs torch autograd through the oracle port in float64 — checks the transposed /
+    flipped weight packing, the zero-border gradient convolutions + reflect fold, the ReLU masks and that the FFT
+    pair is its own adjoint around the spectral GEMM."""
+    from oracle import ffc_torch_cpu as otc
+    from lama_b200.testing import seeded_parameters_
+    blk = seeded_parameters_(M.FFCResnetBlock(64, padding_type="reflect", norm_layer=torch.nn.BatchNorm2d,
+                                              activation_layer=torch.nn.ReLU, ratio_gin=0.75, ratio_gout=0.75,
+                                              enable_lfu=False).eval(), 3, gain=1.0)
+    assert E.block_grad_supported(blk)
+    b, cl, cg, h, w = 2, 16, 48, 6, 10
+    g = torch.Generator().manual_seed(1)
+    xl, xg = torch.randn(b, cl, h, w, generator=g), torch.randn(b, cg, h, w, generator=g)
+    gl, gg = torch.randn(b, cl, h, w, generator=g), torch.randn(b, cg, h, w, generator=g)
+    with torch.no_grad():
+        prog = E.build_module_program(blk, "resnet_block_grad", ((b, cl, h, w), (b, cg, h, w)), L.MATH_FP32)
+    out = SpecInterpreter(prog).run(dict(x0=xl, x1=xg, g0=gl, g1=gg))
+    sd = {k: v.double() for k, v in blk.state_dict().items()}
+    xl64, xg64 = xl.double().requires_grad_(True), xg.double().requires_grad_(True)
+    ol, og = otc.ffc_resnet_block(xl64, xg64, sd, "", ratio_gout=0.75)
+    ((ol * gl.double()).sum() + (og * gg.double()).sum()).backward()
+    _close(out["y0"], (ol.detach() - xl.double()).numpy(), 1e-6)
+    _close(out["dx0"], xl64.grad.numpy(), 1e-6)
+    _close(out["dx1"], xg64.grad.numpy(), 1e-6)
+    assert not E.block_grad_supported(M.FFCResnetBlock(64, padding_type="reflect", norm_layer=torch.nn.BatchNorm2d,
+                                                       ratio_gin=0.5, ratio_gout=0.5, enable_lfu=True).eval())
+
+
 def test_generator_u8_program_matches_reference_predict_bytes():
     """the predict-path program (uint8 image + mask in, inpainted uint8 out; decode, symmetric
     modulo padding, mask multiply / concat and blend / crop / x255 fused into the pack and gather kernels)."""
