@@ -252,32 +252,38 @@ __global__ void __launch_bounds__(kShellThreads) head_conv7_kernel(View in, cons
 // [C][W] <-> [W][C] transposes per (b, y) row through a 32x33 shared tile.
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, int H, int W, View out) {
   __shared__ float tile[32][33];
-  const int b = blockIdx.z / H, y = blockIdx.z % H;
   const int c0 = blockIdx.y * 32, x0 = blockIdx.x * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, xx = x0 + threadIdx.x;
-    tile[i][threadIdx.x] = (c < C && xx < W) ? __ldg(x + (((long long)b * C + c) * H + y) * W + xx) : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int xx = x0 + i, c = c0 + threadIdx.x;
-    if (xx < W && c < C) store1(out, pix_off(out, b, y, xx) + chan_off(out, c), tile[threadIdx.x][i]);
+  for (int z = blockIdx.z; z < out.B * H; z += gridDim.z) {      // (image, row) pairs: grid.z is capped at 65535
+    const int b = z / H, y = z % H;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, xx = x0 + threadIdx.x;
+      tile[i][threadIdx.x] = (c < C && xx < W) ? __ldg(x + (((long long)b * C + c) * H + y) * W + xx) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int xx = x0 + i, c = c0 + threadIdx.x;
+      if (xx < W && c < C) store1(out, pix_off(out, b, y, xx) + chan_off(out, c), tile[threadIdx.x][i]);
+    }
+    __syncthreads();
   }
 }
 
 __global__ void nhwc_to_nchw_kernel(View in, float* __restrict__ yo) {
   __shared__ float tile[32][33];
   const int H = in.H, W = in.W, C = in.C;
-  const int b = blockIdx.z / H, y = blockIdx.z % H;
   const int c0 = blockIdx.y * 32, x0 = blockIdx.x * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int xx = x0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (xx < W && c < C) ? load1(in, pix_off(in, b, y, xx) + chan_off(in, c)) : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, xx = x0 + threadIdx.x;
-    if (c < C && xx < W) yo[(((long long)b * C + c) * H + y) * W + xx] = tile[threadIdx.x][i];
+  for (int z = blockIdx.z; z < in.B * H; z += gridDim.z) {
+    const int b = z / H, y = z % H;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int xx = x0 + i, c = c0 + threadIdx.x;
+      tile[i][threadIdx.x] = (xx < W && c < C) ? load1(in, pix_off(in, b, y, xx) + chan_off(in, c)) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, xx = x0 + threadIdx.x;
+      if (c < C && xx < W) yo[(((long long)b * C + c) * H + y) * W + xx] = tile[threadIdx.x][i];
+    }
+    __syncthreads();
   }
 }
 
@@ -477,8 +483,8 @@ int nchw_to_nhwc(const float* x, int B, int C, int H, int W, const ffcb_tensor* 
   if ((rc = check_tensor(out, "nchw_to_nhwc.out", true))) return rc;
   FFCB_REQUIRE(out->B == B && out->C == C && out->H == H && out->W == W, "nchw_to_nhwc: shape mismatch");
   if ((long long)B * C * H * W == 0) return FFCB_OK;
-  FFCB_REQUIRE((long long)B * H <= 65535, "nchw_to_nhwc: B*H=%lld exceeds grid.z", (long long)B * H);
-  dim3 grid((W + 31) / 32, (C + 31) / 32, B * H), block(32, 8);
+  const long long rows = (long long)B * H;
+  dim3 grid((W + 31) / 32, (C + 31) / 32, (unsigned)(rows < 65535 ? rows : 65535)), block(32, 8);
   nchw_to_nhwc_kernel<<<grid, block, 0, stream>>>(x, C, H, W, make_view(*out));
   FFCB_LAUNCH_CHECK("nchw_to_nhwc_kernel");
   return FFCB_OK;
@@ -488,8 +494,8 @@ int nhwc_to_nchw(const ffcb_tensor* in, float* y, cudaStream_t stream) {
   int rc;
   if ((rc = check_tensor(in, "nhwc_to_nchw.in", true))) return rc;
   if ((long long)in->B * in->C * in->H * in->W == 0) return FFCB_OK;
-  FFCB_REQUIRE((long long)in->B * in->H <= 65535, "nhwc_to_nchw: B*H exceeds grid.z");
-  dim3 grid((in->W + 31) / 32, (in->C + 31) / 32, in->B * in->H), block(32, 8);
+  const long long rows = (long long)in->B * in->H;
+  dim3 grid((in->W + 31) / 32, (in->C + 31) / 32, (unsigned)(rows < 65535 ? rows : 65535)), block(32, 8);
   nhwc_to_nchw_kernel<<<grid, block, 0, stream>>>(make_view(*in), y);
   FFCB_LAUNCH_CHECK("nhwc_to_nchw_kernel");
   return FFCB_OK;

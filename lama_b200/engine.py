@@ -273,7 +273,21 @@ def _plain_conv(conv, k_ok=(1, 3, 7)) -> bool:
             and conv.stride[0] == conv.stride[1] and conv.stride[0] in (1, 2)
             and conv.padding[0] == conv.padding[1] and isinstance(conv.padding[0], int)
             and (conv.padding_mode == 'reflect' or conv.padding[0] == 0)
+            and conv.padding[0] <= 1          # activation buffers carry a 1-pixel reflected ring
             and conv.in_channels % 4 == 0 and conv.out_channels % 4 == 0)
+
+
+def fft_len_ok(n: int) -> bool:
+    """Lengths the shared-memory FFT kernels take (csrc/fft.cu: make_plan / kMaxSmem): powers of two up to 256 have
+    compile-time plans; any other length needs 8 * (n + 2 * n * 32) bytes of shared memory <= 227 KB, i.e. n <= 446."""
+    if n >= 4 and (n & (n - 1)) == 0:
+        return n <= 256
+    return 1 <= n and 8 * (n + 64 * n) <= 227 * 1024
+
+
+def plane_ok(h: int, w: int) -> bool:
+    """Plane sizes the native FFT pair accepts (others take the torch composition)."""
+    return w >= 2 and fft_len_ok(h) and fft_len_ok(w)
 
 
 def ffc_bn_act_supported(m) -> bool:
@@ -317,7 +331,7 @@ def ffc_bn_act_shapes_ok(m, x_l, x_g) -> bool:
         return False
     if not isinstance(f.convg2g, nn.Identity):
         st = f.convg2g
-        if st_out_hw(st, h, w)[1] < 2 or not st.native_supported((h, w)):   # LFU needs even square planes
+        if not plane_ok(*st_out_hw(st, h, w)) or not st.native_supported((h, w)):   # LFU needs even square planes
             return False
         if st.stride == 2 and (c.stride[0] != 2 or ((h + 2 * p - k) // 2 + 1, (w + 2 * p - k) // 2 + 1) != (h // 2, w // 2)):
             return False
@@ -396,7 +410,14 @@ def generator_supported(gen, x) -> bool:
     f = 2 ** len(downs)
     if h % f or w % f:                      # ConvTranspose doubles sizes: only exact multiples round-trip
         return False
+    if blocks_use_fft(gen) and not plane_ok(h // f, w // f):     # e.g. 512-wide bottleneck planes (4096 px images)
+        return False
     return h // f >= 2 and w // f >= 2      # reflect pad 1 at the bottleneck
+
+
+def blocks_use_fft(gen) -> bool:
+    lay = _generator_layout(gen)
+    return lay is not None and any(not isinstance(b.conv1.ffc.convg2g, nn.Identity) for b in lay[2])
 
 
 # -------------------------------------------------------------------------------------- builders

@@ -125,7 +125,7 @@ class FourierUnit(nn.Module):
                 and _engine.bn_foldable(self.bn))
 
     def forward(self, x):
-        if _native_ok(x) and self.native_supported() and x.dim() == 4 and x.shape[-1] >= 2:
+        if (_native_ok(x) and self.native_supported() and x.dim() == 4 and _engine.plane_ok(x.shape[-2], x.shape[-1])):
             return _engine.run_module(self, "fourier_unit", (x,))[0]
         _fallback("FourierUnit options / mode")
         return self._torch_forward(x)
@@ -187,7 +187,7 @@ class SpectralTransform(nn.Module):
 
     def forward(self, x):
         if (_native_ok(x) and x.dim() == 4 and self.native_supported(tuple(x.shape[-2:]))
-                and _engine.st_out_hw(self, *x.shape[-2:])[1] >= 2):
+                and _engine.plane_ok(*_engine.st_out_hw(self, *x.shape[-2:]))):
             return _engine.run_module(self, "spectral_transform", (x,))[0]
         _fallback("SpectralTransform options / mode")
         x = self.conv1(self.downsample(x))
