@@ -576,6 +576,28 @@ def test_resnet_block_input_gradients_vs_autograd_oracle(shape, math_mode):
     assert _rel_err(a_g.grad.cpu().numpy(), r_g.grad.numpy()) < tol
 
 
+def test_refinement_with_native_block_gradients_matches_torch_autograd(tc_math, monkeypatch):
+    """lama_b200.refine.refine_predict (evaluation/refinement.py:228-314 without kornia) on the GPU: residual blocks run
+    the native forward + input-gradient programs; the same loop with the blocks on torch autograd (cuFFT / cuDNN) must
+    give the same refined image up to the arithmetic (3 Adam steps at lr 2e-3 amplify 1e-4 gradient differences)."""
+    from lama_b200 import refine as R
+    g = seeded_parameters_(M.FFCResNetGenerator(**small_lama_kwargs(ngf=16, n_blocks=3)).eval(), 2, gain=1.0).to(DEV)
+    gen = torch.Generator().manual_seed(0)
+    img = torch.rand(1, 3, 136, 200, generator=gen)
+    mask = torch.zeros(1, 1, 136, 200); mask[..., 30:90, 50:150] = 1
+    kw = dict(modulo=8, n_iters=4, lr=0.002, min_side=64, max_scales=2, px_budget=10 ** 7)
+    lib = L.get_lib()
+    lib.ffcb_reset_launch_count()
+    native = R.refine_predict(img, mask, g, **kw)
+    assert lib.ffcb_launch_count() > 100, "native programs did not run inside the refinement loop"
+    monkeypatch.setenv("LAMA_B200_NATIVE_GRAD", "0")
+    monkeypatch.setenv("LAMA_B200_STRICT", "0")                  # blocks under autograd -> torch composition
+    ref = R.refine_predict(img, mask, g, **kw)
+    assert torch.isfinite(native).all()
+    assert float((native - ref).abs().max()) < 5e-3
+    assert float((native - ref).abs().mean()) < 2e-4
+
+
 def test_stage_by_stage_matches_whole_program():
     """predict_inner_features.py:84 iterates generator.model stage by stage: tuple outputs at every FFC
     stage, each stage on its own native program, same result as the fused whole-generator program."""
