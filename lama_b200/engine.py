@@ -61,6 +61,7 @@ class TV:
     b0: int = 0                               # batch slice [b0, b0+nb)
     nb: Optional[int] = None
     win: Optional[Tuple[int, int, int, int]] = None   # spatial sub-rectangle (y0, x0, h, w) of the buffer (LFU quadrants)
+    bcast: int = 0                            # > 0: a one-image buffer read as a batch of `bcast` images (stride 0)
 
     @property
     def channels(self) -> int:
@@ -70,9 +71,13 @@ class TV:
 
     @property
     def batch(self) -> int:
+        if self.bcast:
+            return self.bcast
         return self.buf.B - self.b0 if self.nb is None else self.nb
 
     def bslice(self, b0: int, nb: int) -> "TV":
+        if self.bcast:
+            return TV(self.buf, self.c0, self.C, self.phase, self.window, 0, None, self.win, nb)
         return TV(self.buf, self.c0, self.C, self.phase, self.window, self.b0 + b0, nb, self.win)
 
     @property
@@ -218,6 +223,7 @@ class Program:
     outputs: Dict[str, Tuple[int, ...]] = field(default_factory=dict)
     dtypes: Dict[str, torch.dtype] = field(default_factory=dict)       # inputs / outputs that are not float32
     meta: Dict[tuple, dict] = field(default_factory=dict)              # buffers a backward program needs (per module)
+    consts: Dict[str, torch.Tensor] = field(default_factory=dict)      # buffer name -> initial contents [B,H,W,C] float
 
     def buf(self, name, B, H, W, C, gemm=False, halo=False, halo_px=1, cg=0) -> Buf:
         """``gemm``: the buffer is an operand of a contraction; ``halo``: that contraction has spatial taps.
@@ -449,7 +455,7 @@ def fu_planar_ok(prog: Program, st, h: int, w: int) -> bool:
     fu = st.fu
     if st.enable_lfu and not ((h, w) == (64, 64) and c % 32 == 0):      # LFU quadrants: 32x32 planes, c/4 % 8 == 0
         return False
-    return ((h, w) in ((64, 64), (32, 32)) and c % 64 == 0 and fu.conv_layer.in_channels == 2 * c
+    return ((h, w) in ((64, 64), (32, 32)) and c % 64 == 0 and fu.conv_layer.in_channels == 2 * c + (2 if fu.spectral_pos_encoding else 0)
             and fu.conv_layer.out_channels == 2 * c)
 
 
@@ -459,19 +465,33 @@ def emit_fourier_unit(prog: Program, fu, t: TV, out: TV, residual: Optional[TV])
     b = t.batch
     h, w = t.hw
     wf = w // 2 + 1
-    cin2, cout2 = fu.conv_layer.in_channels, fu.conv_layer.out_channels
+    cout2 = fu.conv_layer.out_channels
+    cin2 = fu.conv_layer.in_channels - (2 if fu.spectral_pos_encoding else 0)       # spectrum channels (ffc.py:57)
     planar = t.buf.cg == 4      # FourierUnit chain in channel-group planar storage (emit_spectral_transform decides)
     S = prog.buf("spectrum", b, h, wf, cin2, gemm=True, cg=8 if planar else 0)
     Z = prog.buf("spectrum_out", b, h, wf, cout2, cg=8 if planar else 0)
     prog.meta[("fu", id(fu))] = dict(S=S, Z=Z)
     scale, shift = P.bn_scale_shift(fu.bn)
-    pk = P.pack_conv([(fu.conv_layer.weight, 0, 0, 0)], scale, shift, act=L.ACT_RELU,
-                     device=fu.conv_layer.weight.device)
+    wconv, pos = fu.conv_layer.weight, None
+    if fu.spectral_pos_encoding:
+        # ffc.py:91-95 prepends two coordinate channels (linspace over H and over W/2+1) to the spectrum.  They do not
+        # depend on the data: their contribution W[:, :2] . (v, h) is a per-position addend of the spectral GEMM
+        # (BN scale folded), broadcast over the batch.
+        wpos = wconv.detach().double()[:, :2, 0, 0] * scale.double()[:, None]                     # [2co, 2]
+        wconv = wconv[:, 2:]
+        vert = torch.linspace(0, 1, h, dtype=torch.float64, device=wpos.device)
+        hor = torch.linspace(0, 1, wf, dtype=torch.float64, device=wpos.device)
+        PE = prog.buf("fu.pos_addend", 1, h, wf, cout2)
+        prog.consts[PE.name] = (vert[:, None, None] * wpos[:, 0] + hor[None, :, None] * wpos[:, 1])[None].float()
+        pos = TV(PE, bcast=b)
+    cin2 = wconv.shape[1]
+    pk = P.pack_conv([(wconv, 0, 0, 0)], scale, shift, act=L.ACT_RELU, device=fu.conv_layer.weight.device)
     chunk = fu_batch_chunk(b, h, w, cin2 // 2) if prog.math == L.MATH_BF16X3 else b
     for b0 in range(0, b, chunk):
         nb = min(chunk, b - b0)
         prog.ops.append(RfftOp(t.bslice(b0, nb), TV(S).bslice(b0, nb)))
-        prog.ops.append(ConvOp(pk, [TV(S).bslice(b0, nb), None], TV(Z).bslice(b0, nb), tag="fu.conv_layer+bn+relu"))
+        prog.ops.append(ConvOp(pk, [TV(S).bslice(b0, nb), None], TV(Z).bslice(b0, nb),
+                               addend=pos.bslice(b0, nb) if pos is not None else None, tag="fu.conv_layer+bn+relu"))
         prog.ops.append(IrfftOp(TV(Z).bslice(b0, nb), residual.bslice(b0, nb) if residual is not None else None,
                                 out.bslice(b0, nb)))
 
@@ -904,6 +924,9 @@ class CudaExecutor:
                 self.storage[b.name] = torch.empty(shape, dtype=torch.float32, device=device)
             else:
                 self.storage[b.name] = torch.zeros((2,) + shape, dtype=torch.bfloat16, device=device)
+        for name, val in prog.consts.items():
+            assert self.storage[name].dtype == torch.float32 and tuple(self.storage[name].shape) == tuple(val.shape)
+            self.storage[name].copy_(val.to(device=device, dtype=torch.float32))
         ws_bytes = prog.fft_workspace_bytes()
         self.ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=device)
         self.ws_bytes = ws_bytes
@@ -957,6 +980,8 @@ class CudaExecutor:
         off += tv.b0 * sb
         t.ptr = st.data_ptr() + off * es
         t.B, t.H, t.W, t.C = tv.batch, h, w, tv.channels
+        if tv.bcast:
+            t.sb = 0                 # every image of the batch reads the same plane (position-dependent addends)
         t.fmt, t.pad, t.reflect_border = b.fmt, b.pad, b.reflect_border
         if tv.phase is not None or tv.win is not None:     # not a whole image: no ring semantics
             t.pad, t.reflect_border = 0, 0

@@ -119,9 +119,10 @@ class FourierUnit(nn.Module):
         self.fft_norm = fft_norm
 
     def native_supported(self) -> bool:
-        return (self.groups == 1 and self.spatial_scale_factor is None and not self.spectral_pos_encoding
+        spec_in = self.conv_layer.in_channels - (2 if self.spectral_pos_encoding else 0)
+        return (self.groups == 1 and self.spatial_scale_factor is None
                 and not self.use_se and not self.ffc3d and self.fft_norm == 'ortho' and not self.training
-                and self.conv_layer.in_channels % 8 == 0 and self.conv_layer.out_channels % 8 == 0
+                and spec_in % 8 == 0 and self.conv_layer.out_channels % 8 == 0
                 and _engine.bn_foldable(self.bn))
 
     def forward(self, x):

@@ -191,6 +191,14 @@ def make_f4():
                                                      enable_lfu=c["lfu"]).eval(), seed=60 + i, gain=1.0)
         x = _randn((2, c["ci"]) + c["hw"], 600 + i)
         _save(name, x=x.numpy(), y=m(x).numpy(), **_sd_np(m))
+    # FourierUnit with spectral_pos_encoding (ffc.py:91-95), alone and inside a SpectralTransform
+    m = seeded_parameters_(ffc.FourierUnit(8, 8, spectral_pos_encoding=True).eval(), seed=65, gain=1.0)
+    x = _randn((2, 8, 12, 16), 650)
+    _save("fu_c8_pos_12x16", x=x.numpy(), y=m(x).numpy(), **_sd_np(m))
+    m = seeded_parameters_(ffc.SpectralTransform(16, 32, enable_lfu=False, spectral_pos_encoding=True).eval(),
+                           seed=66, gain=1.0)
+    x = _randn((2, 16, 8, 8), 660)
+    _save("st_16to32_pos_8x8", x=x.numpy(), y=m(x).numpy(), **_sd_np(m))
     # FFC_BN_ACT with a global input AND stride 2 (the spectral branch pools, the 3x3 convs stride), LFU on
     m = seeded_parameters_(ffc.FFC_BN_ACT(in_channels=64, out_channels=64, kernel_size=3, ratio_gin=0.5, ratio_gout=0.5,
                                           stride=2, padding=1, activation_layer=relu, enable_lfu=True).eval(),

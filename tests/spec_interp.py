@@ -15,9 +15,13 @@ class SpecInterpreter:
     def __init__(self, prog: E.Program):
         self.prog = prog
         self.mem = {b.name: torch.full((b.B, b.H, b.W, b.C), float("nan"), dtype=torch.float64) for b in prog.bufs}
+        for name, val in prog.consts.items():
+            self.mem[name] = val.double().clone()
 
     def read(self, tv: E.TV) -> torch.Tensor:
         t = self.mem[tv.buf.name][tv.b0:tv.b0 + tv.batch]
+        if tv.bcast:
+            t = self.mem[tv.buf.name].expand(tv.bcast, -1, -1, -1)
         if tv.window:      # sliding-window view: pixel x exposes pixels x .. x+window-1, channel index = j*C + c
             w_out = tv.buf.W - tv.window
             return torch.cat([t[:, :, j:j + w_out] for j in range(tv.window)], dim=-1)

@@ -423,6 +423,19 @@ def test_spectral_transform_stride2_and_lfu_golden(name, ci, co, stride, lfu, ma
     assert _rel_err(y, a["y"]) < TOL[math_mode]
 
 
+def test_spectral_pos_encoding_golden(math_mode):
+    a, sd = load_golden("fu_c8_pos_12x16")
+    m = _load(M.FourierUnit(8, 8, spectral_pos_encoding=True), sd)
+    with torch.no_grad():
+        y = m(torch.from_numpy(a["x"]).to(DEV)).cpu().numpy()
+    assert _rel_err(y, a["y"]) < TOL[math_mode]
+    a, sd = load_golden("st_16to32_pos_8x8")
+    m = _load(M.SpectralTransform(16, 32, enable_lfu=False, spectral_pos_encoding=True), sd)
+    with torch.no_grad():
+        y = m(torch.from_numpy(a["x"]).to(DEV)).cpu().numpy()
+    assert _rel_err(y, a["y"]) < TOL[math_mode]
+
+
 def test_ffc_bn_act_stride2_global_lfu_and_resblock_lfu_golden(math_mode):
     a, sd = load_golden("ffcbnact_64_s2_lfu_16x16")
     m = _load(M.FFC_BN_ACT(in_channels=64, out_channels=64, kernel_size=3, ratio_gin=0.5, ratio_gout=0.5, stride=2,

@@ -69,6 +69,21 @@ def test_spectral_transform_stride2_and_lfu_programs(name, ci, co, stride, lfu):
     assert sum(isinstance(o, E.IrfftOp) for o in prog.ops) == (5 if lfu else 1)
 
 
+def test_spectral_pos_encoding_programs():
+    """ffc.py:91-95: the two coordinate channels are data independent, so they enter the spectral GEMM as a
+    per-position addend (BN scale folded) broadcast over the batch — FourierUnit alone and inside SpectralTransform."""
+    a, sd = load_golden("fu_c8_pos_12x16")
+    m = _load(M.FourierUnit(8, 8, spectral_pos_encoding=True), sd)
+    assert m.native_supported()
+    out, prog = _run(m, "fourier_unit", (torch.from_numpy(a["x"]),))
+    _close(out["y0"], a["y"])
+    assert len(prog.consts) == 1
+    a, sd = load_golden("st_16to32_pos_8x8")
+    m = _load(M.SpectralTransform(16, 32, enable_lfu=False, spectral_pos_encoding=True), sd)
+    out, _ = _run(m, "spectral_transform", (torch.from_numpy(a["x"]),))
+    _close(out["y0"], a["y"])
+
+
 def test_ffc_bn_act_stride2_global_with_lfu_program():
     a, sd = load_golden("ffcbnact_64_s2_lfu_16x16")
     m = _load(M.FFC_BN_ACT(in_channels=64, out_channels=64, kernel_size=3, ratio_gin=0.5, ratio_gout=0.5, stride=2,
@@ -136,7 +151,8 @@ def test_generator_program(name):
 
 
 def test_unsupported_options_are_not_native():
-    assert not M.FourierUnit(8, 8, spectral_pos_encoding=True).eval().native_supported()
+    assert M.FourierUnit(8, 8, spectral_pos_encoding=True).eval().native_supported()        # native since round 2
+    assert not M.FourierUnit(8, 8, use_se=True).eval().native_supported()
     assert not M.FourierUnit(8, 8, fft_norm="backward").eval().native_supported()
     assert not M.SpectralTransform(16, 16, enable_lfu=True).eval().native_supported()       # c/4 = 2 channels
     lf = M.SpectralTransform(32, 32, enable_lfu=True).eval()
