@@ -384,6 +384,11 @@ def _generator_layout(gen):
                     and ct.in_channels % 4 == 0 and ct.out_channels % 4 == 0):
                 return None
             ups.append((ct, bn)); i += 3
+        out_blk = None
+        if isinstance(mods[i], FFCResnetBlock):          # out_ffc=True (ffc.py:356-358): an inline block at full resolution
+            if not (mods[i].inline and mods[i].native_supported()):
+                return None
+            out_blk = mods[i]; i += 1
         if not (isinstance(mods[i], nn.ReflectionPad2d) and tuple(mods[i].padding) == (3, 3, 3, 3)):
             return None
         head = mods[i + 1]
@@ -400,7 +405,7 @@ def _generator_layout(gen):
             i += 1
         if i != len(mods):
             return None
-        return stem, downs, blocks, ups, head, out_act
+        return stem, downs, blocks, ups, out_blk, head, out_act
     except IndexError:
         return None
 
@@ -409,8 +414,13 @@ def generator_supported(gen, x) -> bool:
     lay = _generator_layout(gen)
     if lay is None or x.dim() != 4:
         return False
-    stem, downs, _blocks, _ups, _head, _ = lay
+    stem, downs, _blocks, _ups, out_blk, _head, _ = lay
     b, c, h, w = x.shape
+    if out_blk is not None:        # its FourierUnit transforms full-resolution planes
+        f0 = out_blk.conv1.ffc
+        if not ffc_bn_act_shapes_ok(out_blk.conv1, torch.empty(1, f0.convl2l.in_channels, h, w, device="meta"),
+                                    torch.empty(1, f0.global_in_num, h, w, device="meta")):
+            return False
     if c != stem.ffc.convl2l.in_channels or h < 4 or w < 4:
         return False
     f = 2 ** len(downs)
@@ -804,7 +814,7 @@ def build_generator_program(prog: Program, gen, shape, u8_size: Optional[Tuple[i
     ``u8_size=(H0, W0)``: the predict-path variant.  Inputs are the decoded bytes "img"
     (B,H0,W0,3) and "mask" (B,H0,W0); ``shape`` is the modulo-padded generator input (B,4,H,W); the output "y0" is
     the inpainted RGB bytes (B,H0,W0,3).  Pre/post-processing lives in the pack and gather kernels."""
-    stem, downs, blocks, ups, head, out_act = _generator_layout(gen)
+    stem, downs, blocks, ups, out_blk, head, out_act = _generator_layout(gen)
     b, cin, h, w = shape
     dev = head.weight.device
     if u8_size is None:
@@ -850,6 +860,11 @@ def build_generator_program(prog: Program, gen, shape, u8_size: Optional[Tuple[i
         for a, bb, pk in P.pack_conv_transpose_phases(ct.weight, ct.bias, sc, sh, act=L.ACT_RELU, device=dev):
             prog.ops.append(ConvOp(pk, [TV(X), None], TV(Yb, phase=(a, bb)), tag=f"convT phase {a}{bb}+bn+relu"))
         X = Yb
+    if out_blk is not None:
+        # out_ffc: FFCResnetBlock(inline=True) splits its input as x[:, :-g] | x[:, -g:] (ffc.py:278-280) — exactly the
+        # [local | global] channel order of the buffer, so it runs in place like the bottleneck blocks
+        ocg = out_blk.conv1.ffc.global_in_num
+        X = emit_resnet_block(prog, out_blk, X, X.C - ocg, ocg, in_place=True)
     if u8_size is not None and not (tc_head and ups and head.out_channels == 3):
         raise ValueError("the uint8 predict path needs the tensor-core head with 3 output channels")
     if tc_head and ups:

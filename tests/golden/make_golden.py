@@ -11,7 +11,7 @@ factory ``lama_b200.testing.seeded_parameters_``, it is run in ``eval()`` under
 The fixtures pin (a) the numpy and torch-CPU restatements in ``oracle/`` and (b), on the
 GPU box where the reference tree is absent, the CUDA path itself.
 
-Sizes are small on purpose (the whole directory stays < 2 MB).
+Sizes are small on purpose (the whole directory stays < 4 MB).
 """
 import os
 import sys
@@ -199,6 +199,13 @@ def make_f4():
                            seed=66, gain=1.0)
     x = _randn((2, 16, 8, 8), 660)
     _save("st_16to32_pos_8x8", x=x.numpy(), y=m(x).numpy(), **_sd_np(m))
+    # generator with out_ffc=True (ffc.py:356-358): an inline FFCResnetBlock at full resolution before the head
+    kw = small_lama_kwargs(ngf=16, n_blocks=1, n_downsampling=2)
+    kw.update(out_ffc=True, out_ffc_kwargs=dict(ratio_gin=0.5, ratio_gout=0.5, enable_lfu=False))
+    g = seeded_parameters_(ffc.FFCResNetGenerator(**kw).eval(), seed=67, gain=1.0)
+    img, mask = synthetic_image_mask(1, 32, seed=8)
+    x = generator_input(img, mask)
+    _save("generator_ngf16_outffc_32x32", x=x.numpy(), y=g(x).numpy(), **_sd_np(g))
     # FFC_BN_ACT with a global input AND stride 2 (the spectral branch pools, the 3x3 convs stride), LFU on
     m = seeded_parameters_(ffc.FFC_BN_ACT(in_channels=64, out_channels=64, kernel_size=3, ratio_gin=0.5, ratio_gout=0.5,
                                           stride=2, padding=1, activation_layer=relu, enable_lfu=True).eval(),

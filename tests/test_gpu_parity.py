@@ -505,6 +505,16 @@ def test_small_generator_golden(name, math_mode):
     assert float(np.abs(y - a["y"]).max()) < (5e-6 if math_mode == "fp32" else 1e-4)
 
 
+def test_generator_with_out_ffc_golden(math_mode):
+    a, sd = load_golden("generator_ngf16_outffc_32x32")
+    kw = small_lama_kwargs(ngf=16, n_blocks=1, n_downsampling=2)
+    kw.update(out_ffc=True, out_ffc_kwargs=dict(ratio_gin=0.5, ratio_gout=0.5, enable_lfu=False))
+    g = _load(M.FFCResNetGenerator(**kw), sd)
+    with torch.no_grad():
+        y = g(torch.from_numpy(a["x"]).to(DEV)).cpu().numpy()
+    assert float(np.abs(y - a["y"]).max()) < (5e-6 if math_mode == "fp32" else 1e-4)
+
+
 def test_generator_with_the_constructor_default_tanh_head(math_mode):
     """add_out_act=True (the constructor default, ffc.py:362) ends the generator with tanh: precise tanhf in the head
     epilogue (the library is built without --use_fast_math), both head implementations."""

@@ -150,6 +150,19 @@ def test_generator_program(name):
     assert not any(b.name.startswith("block.out") for b in prog.bufs)
 
 
+def test_generator_with_out_ffc_program():
+    """out_ffc=True (ffc.py:356-358): the inline FFCResnetBlock before the head joins the one generator program."""
+    a, sd = load_golden("generator_ngf16_outffc_32x32")
+    kw = small_lama_kwargs(ngf=16, n_blocks=1, n_downsampling=2)
+    kw.update(out_ffc=True, out_ffc_kwargs=dict(ratio_gin=0.5, ratio_gout=0.5, enable_lfu=False))
+    g = _load(M.FFCResNetGenerator(**kw), sd)
+    x = torch.from_numpy(a["x"])
+    assert E.generator_supported(g, x)
+    out, prog = _run(g, "generator", (x,))
+    assert float(np.abs(out["y0"].numpy() - a["y"]).max()) < 2e-6
+    assert sum(isinstance(o, E.RfftOp) for o in prog.ops) == 4          # 1 bottleneck block + the out_ffc block
+
+
 def test_unsupported_options_are_not_native():
     assert M.FourierUnit(8, 8, spectral_pos_encoding=True).eval().native_supported()        # native since round 2
     assert not M.FourierUnit(8, 8, use_se=True).eval().native_supported()
