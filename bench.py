@@ -394,8 +394,18 @@ def main():
                 "note": "fp32 CUDA-core arm (FFCB_MATH_FP32)" if math == L.MATH_FP32 else
                         "bf16x3 tcgen05 arm: 3 bf16 products per algorithmic MAC"}
         if fu_idx:
-            j = fu_idx[len(fu_idx) // 2]
-            fu_calls = [j, j + 1, j + 2]       # rfft2, fu conv, irfft2 (emit_fourier_unit order)
+            # one FourierUnit = a maximal run of {rfft2, spectral conv, irfft2} calls (3 calls, or 3 per batch chunk with
+            # LAMA_B200_FU_CHUNK): take the run in the middle of the program
+            is_fu = [n in ("ffcb_rfft2", "ffcb_irfft2") or n.startswith("ffcb_conv:fu.conv_layer") for n, _f, _a in ex.calls]
+            runs, cur = [], []
+            for i, f_ in enumerate(is_fu):
+                if f_:
+                    cur.append(i)
+                elif cur:
+                    runs.append(cur); cur = []
+            if cur:
+                runs.append(cur)
+            fu_calls = runs[len(runs) // 2]
             run_calls(fu_calls * 3)
             c = 192
             fu_bytes = 4.0 * B * h * h * (c + c) + 4.0 * (2 * c) * (2 * c) + 8.0 * (2 * c)
@@ -416,13 +426,16 @@ def main():
                 ts.sort()
                 return ts[len(ts) // 2]
             ms_cold, ms_warm = fu_time(True, fu_calls), fu_time(False, fu_calls)
-            parts = {n: {"cold_ms": fu_time(True, [k]), "warm_ms": fu_time(False, [k])}
-                     for n, k in zip(("rfft2", "spectral_gemm", "irfft2"), fu_calls)}
+            kinds = {"rfft2": [k for k in fu_calls if ex.calls[k][0] == "ffcb_rfft2"],
+                     "spectral_gemm": [k for k in fu_calls if ex.calls[k][0].startswith("ffcb_conv")],
+                     "irfft2": [k for k in fu_calls if ex.calls[k][0] == "ffcb_irfft2"]}
+            parts = {n: {"cold_ms": fu_time(True, ks), "warm_ms": fu_time(False, ks)} for n, ks in kinds.items()}
             del flush
             gbs = fu_bytes / (ms_cold * 1e-3) / 1e9
             roof["fourier_unit"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": gbs / peaks["hbm_gbs"], "ms": ms_cold, "algorithmic_bytes": fu_bytes,
-                                    "shape": [B, c, h, h], "launches": 3, "l2": "cold (512 MB flush before each run)",
+                                    "shape": [B, c, h, h], "launches": len(fu_calls),
+                                    "l2": "cold (512 MB flush before each run)",
                                     "warm": {"ms": ms_warm, "achieved": fu_bytes / (ms_warm * 1e-3) / 1e9,
                                              "frac": fu_bytes / (ms_warm * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                                     "per_kernel": parts,

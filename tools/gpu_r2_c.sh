@@ -8,7 +8,10 @@ python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1; echo "
 timeout 600 python bench.py --steps 10 > $OUT/bench_planar.json 2> $OUT/bench_planar.err; echo "bench planar rc=$?" | tee -a $OUT/summary_c.txt
 LAMA_B200_FU_LAYOUT=nhwc timeout 400 python bench.py --steps 10 --no-cpu-baseline --no-torch-cuda-baseline --no-fp32-arm --io f32 > $OUT/bench_nhwc.json 2> $OUT/bench_nhwc.err; echo "bench nhwc rc=$?" | tee -a $OUT/summary_c.txt
 FFCB_L2_HINTS=0 timeout 400 python bench.py --steps 10 --no-cpu-baseline --no-torch-cuda-baseline --no-fp32-arm --io f32 > $OUT/bench_nohints.json 2> $OUT/bench_nohints.err; echo "bench nohints rc=$?" | tee -a $OUT/summary_c.txt
-for f in bench_planar bench_nhwc bench_nohints; do python - <<PY | tee -a $OUT/summary_c.txt
+for ch in 8 16; do
+LAMA_B200_FU_CHUNK=$ch timeout 400 python bench.py --steps 10 --no-cpu-baseline --no-torch-cuda-baseline --no-fp32-arm --io f32 > $OUT/bench_chunk$ch.json 2> $OUT/bench_chunk$ch.err; echo "bench chunk $ch rc=$?" | tee -a $OUT/summary_c.txt
+done
+for f in bench_planar bench_nhwc bench_nohints bench_chunk8 bench_chunk16; do python - <<PY | tee -a $OUT/summary_c.txt
 import json
 try:
     d = json.load(open("$OUT/$f.json"))
