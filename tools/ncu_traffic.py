@@ -10,6 +10,9 @@ import sys
 WANT = {
     "dram__bytes_read.sum": "dram_read_bytes", "dram__bytes_write.sum": "dram_write_bytes",
     "gpu__time_duration.sum": "duration", "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
+    "FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_pct", "lts__t_sectors.sum": "l2_sectors",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pct",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
     "launch__registers_per_thread": "regs", "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_pct",
