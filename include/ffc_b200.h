@@ -147,10 +147,13 @@ int ffcb_stem_conv7(const float* x_nchw, int B, int Cin, int H, int W, const flo
 /*
  * Stem, tensor-core form.  ffcb_stem_pack writes the generator input as a reflect-padded (3 pixels) channels-last
  * image with 8 channels per pixel (Cin real + zeros), rows of W+8 pixels (the tail is zero), in split bf16:
- *     packed[b][yp][xp][c],  yp in [0,H+6), xp in [0,W+8),  = x[b][c][reflect(yp-3)][reflect(xp-3)]
+ *     packed[b][yp][xp][c],  yp in [0,H+6), xp in [0,W+8),  = x[b][c][reflect(yp-3)][reflect(xp-3)]      (c < Cin)
+ * and, when Cin <= 4 ("two-row" packing), packed[b][yp][xp][4+c] = packed[b][yp+1][xp][c] (zero below the last row).
  * A window view of it (C = 64, sx = 8, window = 1) exposes, at pixel x, the 8 taps x 8 channels of one kernel
- * row as ONE contiguous 128-byte K block, so ReflectionPad2d(3) + Conv2d(k7) (ffc.py:315-317) becomes an
- * ffcb_conv with seven K-segments (dy = 0..6, dx = 0) and zero-padded weights [N][7][8 taps][8 channels].
+ * row (two kernel rows with the two-row packing) as ONE contiguous 128-byte K block, so ReflectionPad2d(3) +
+ * Conv2d(k7) (ffc.py:315-317) becomes an ffcb_conv with seven K-segments (dy = 0..6, dx = 0) and zero-padded
+ * weights [N][7][8 taps][8 channels] — or four K-segments (dy = 0, 2, 4, 6) with weights
+ * [N][4][8 taps][row dy | row dy+1][4 channels] when Cin <= 4 (43 % fewer tensor-core MACs).
  */
 int ffcb_stem_pack(const float* x_nchw, int B, int Cin, int H, int W, const ffcb_tensor* packed, ffcb_stream_t stream);
 

@@ -102,9 +102,12 @@ __global__ void __launch_bounds__(kShellThreads) stem_conv7_kernel(const float* 
 // ---------------------------------------------------------------------------------------- stem pack
 // NCHW float -> reflect-padded NHWC8 (split bf16 or fp32): one thread per padded pixel, 8 channels = one
 // 16-byte (bf16) store per plane.  Feeds the tensor-core stem through a sliding-window view.
+// Cin <= 4 ("two-row" packing): channels 4..7 of padded pixel (yp, xp) hold channels 0..3 of pixel (yp+1, xp), so one
+// 64-element window (8 taps x 8 channels) covers TWO kernel rows and the 7x7 stem is four K-segments instead of seven.
 __global__ void stem_pack_kernel(const float* __restrict__ x, int Cin, int H, int W, View out) {
   const int Wp = out.W, Hp = out.H;           // W + 8, H + 6
   const long long total = (long long)out.B * Hp * Wp;
+  const bool two_rows = Cin <= 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int xp = (int)(i % Wp);
@@ -115,9 +118,13 @@ __global__ void stem_pack_kernel(const float* __restrict__ x, int Cin, int H, in
     for (int c = 0; c < 8; ++c) v[c] = 0.f;
     if (xp < W + 6) {
       const int yy = reflect_idx(yp - HALO, H), xx = reflect_idx(xp - HALO, W);
+      const int y2 = reflect_idx(yp + 1 - HALO, H);
+      const bool row2 = two_rows && yp + 1 < Hp;
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
+      for (int c = 0; c < 8; ++c) {
         if (c < Cin) v[c] = __ldg(x + (((long long)b * Cin + c) * H + yy) * W + xx);
+        else if (row2 && c >= 4 && c - 4 < Cin) v[c] = __ldg(x + (((long long)b * Cin + (c - 4)) * H + y2) * W + xx);
+      }
     }
     const long long o = pix_off(out, b, yp, xp);
     store4(out, o, make_float4(v[0], v[1], v[2], v[3]));
@@ -141,21 +148,28 @@ __global__ void stem_pack_u8_kernel(const uint8_t* __restrict__ img, const uint8
     const int xp = (int)(i % Wp);
     const int yp = (int)((i / Wp) % Hp);
     const int b = (int)(i / ((long long)Wp * Hp));
-    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (xp < W + 2 * HALO) {
-      const int ys = symmetric_idx(reflect_idx(yp - HALO, H), H0), xs = symmetric_idx(reflect_idx(xp - HALO, W), W0);
+    // decoded + masked pixel at padded coordinates (yq, xp): (img * (1 - mask), mask)
+    auto fetch = [&](int yq) {
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int ys = symmetric_idx(reflect_idx(yq - HALO, H), H0), xs = symmetric_idx(reflect_idx(xp - HALO, W), W0);
       const long long p = ((long long)b * H0 + ys) * W0 + xs;
       if (__ldg(mask + p) > 0) {
-        lo.w = 1.f;                                  // img * (1 - 1) = +0, mask channel = 1
+        r.w = 1.f;                                   // img * (1 - 1) = +0, mask channel = 1
       } else {                                       // img * (1 - 0) = img exactly
-        lo.x = __fdiv_rn((float)__ldg(img + 3 * p + 0), 255.f);
-        lo.y = __fdiv_rn((float)__ldg(img + 3 * p + 1), 255.f);
-        lo.z = __fdiv_rn((float)__ldg(img + 3 * p + 2), 255.f);
+        r.x = __fdiv_rn((float)__ldg(img + 3 * p + 0), 255.f);
+        r.y = __fdiv_rn((float)__ldg(img + 3 * p + 1), 255.f);
+        r.z = __fdiv_rn((float)__ldg(img + 3 * p + 2), 255.f);
       }
+      return r;
+    };
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;      // hi: the pixel one row below (two-row packing)
+    if (xp < W + 2 * HALO) {
+      lo = fetch(yp);
+      if (yp + 1 < Hp) hi = fetch(yp + 1);
     }
     const long long o = pix_off(out, b, yp, xp);
     store4(out, o, lo);
-    store4(out, o + 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    store4(out, o + 4, hi);
   }
 }
 

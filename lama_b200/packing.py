@@ -160,19 +160,28 @@ def pack_stem(weight: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, de
 
 
 def pack_stem_windowed(weight: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, device=None) -> PackedConv:
-    """7x7 stem (ffc.py:316) for the tensor-core arm: seven K-segments (one per kernel row, dy = 0..6 into the
-    reflect-padded packed image) of 64 = 8 taps x 8 channels; tap 7 and channels >= Cin carry zero weights.
-    K index inside a segment = kx*8 + c, matching the sliding-window view of ffcb_stem_pack's output."""
+    """7x7 stem (ffc.py:316) for the tensor-core arm over the packed NHWC8 image of ffcb_stem_pack.
+    Cin <= 4 (two-row packing: channels 4..7 of a packed pixel are the pixel one row below): FOUR K-segments
+    (dy = 0, 2, 4, 6) of 64 = 8 taps x (kernel row dy | kernel row dy+1) x 4 channels; K index inside a segment =
+    kx*8 + r*4 + c; kernel row 7, tap 7 and channels >= Cin carry zero weights.
+    Cin in 5..8: seven K-segments (one per kernel row), K index = kx*8 + c."""
     w = weight.detach().double() * scale.double()[:, None, None, None]           # [N, Cin, 7, 7]
     n, cin = w.shape[0], w.shape[1]
     assert cin <= 8 and w.shape[2] == 7 and w.shape[3] == 7
-    full = torch.zeros(n, 7, 8, 8, dtype=torch.float64, device=w.device)         # [N, ky, kx, c]
-    full[:, :, :7, :cin] = w.permute(0, 2, 3, 1)
-    w_kn = full.reshape(n, 7 * 64).t().contiguous().float()
     sh = shift.float().contiguous()
+    if cin <= 4:
+        full = torch.zeros(n, 4, 8, 2, 4, dtype=torch.float64, device=w.device)  # [N, ky pair, kx, row in pair, c]
+        for ky in range(7):
+            full[:, ky // 2, :7, ky % 2, :cin] = w[:, :, ky, :].permute(0, 2, 1)
+        w_kn = full.reshape(n, 4 * 64).t().contiguous().float()
+        segs = [Seg(0, 2 * j, 0, 0, 64) for j in range(4)]
+    else:
+        full = torch.zeros(n, 7, 8, 8, dtype=torch.float64, device=w.device)     # [N, ky, kx, c]
+        full[:, :, :7, :cin] = w.permute(0, 2, 3, 1)
+        w_kn = full.reshape(n, 7 * 64).t().contiguous().float()
+        segs = [Seg(0, ky, 0, 0, 64) for ky in range(7)]
     if device is not None:
         w_kn, sh = w_kn.to(device), sh.to(device)
-    segs = [Seg(0, ky, 0, 0, 64) for ky in range(7)]
     return PackedConv(segs=segs, n_out=n, w_kn=w_kn, shift=sh, stride=1, border=L.BORDER_ZERO, act=L.ACT_RELU)
 
 

@@ -59,6 +59,15 @@ class SpecInterpreter:
                 L.ACT_TANH: torch.tanh(y)}[act]
 
     @staticmethod
+    def _two_rows(p, cin):
+        """ffcb_stem_pack's two-row packing (Cin <= 4): channels 4..7 of a packed pixel = channels 0..3 one row below."""
+        if cin > 4:
+            return p
+        p = p.clone()
+        p[:, :-1, :, 4:4 + cin] = p[:, 1:, :, :cin]
+        return p
+
+    @staticmethod
     def _u8_front(img, mask, h, w):
         """ffcb_stem_pack_u8 up to the reflection ring: (B,H0,W0,3) u8 + (B,H0,W0) u8 -> (B,4,H,W) float32."""
         h0, w0 = mask.shape[1:]
@@ -78,12 +87,12 @@ class SpecInterpreter:
             elif isinstance(op, E.StemPackOp):
                 x = torch.nn.functional.pad(inputs[op.src].double(), (3, 3, 3, 3), mode="reflect")
                 x = torch.nn.functional.pad(x, (0, 2, 0, 0, 0, 8 - op.cin))          # W+6 -> W+8, Cin -> 8 (zeros)
-                self.write(op.out, x.permute(0, 2, 3, 1))
+                self.write(op.out, self._two_rows(x.permute(0, 2, 3, 1), op.cin))
             elif isinstance(op, E.StemPackU8Op):
                 x = self._u8_front(inputs[op.img], inputs[op.mask], op.out.buf.H - 6, op.out.buf.W - 8)
                 x = torch.nn.functional.pad(x.double(), (3, 3, 3, 3), mode="reflect")
                 x = torch.nn.functional.pad(x, (0, 2, 0, 0, 0, 4))
-                self.write(op.out, x.permute(0, 2, 3, 1))
+                self.write(op.out, self._two_rows(x.permute(0, 2, 3, 1), 4))
             elif isinstance(op, E.HeadGatherU8Op):
                 pred = self._gather(self.read(op.q), op.bias, 3, op.act).float()[:, :, :op.h0, :op.w0]
                 img = inputs[op.img].permute(0, 3, 1, 2).float() / 255

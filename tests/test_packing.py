@@ -147,9 +147,26 @@ def test_windowed_stem_packing_equals_reflect_conv7():
     sc, sh = P.bn_scale_shift(bn)
     pk = P.pack_stem_windowed(conv.weight, sc, sh)
     packed = F.pad(F.pad(x, (3, 3, 3, 3), mode="reflect"), (0, 2, 0, 0, 0, 4)).permute(0, 2, 3, 1)   # [B,H+6,W+8,8]
+    packed = packed.clone()
+    packed[:, :-1, :, 4:8] = packed[:, 1:, :, 0:4]          # two-row packing of ffcb_stem_pack (Cin <= 4)
+    assert len(pk.segs) == 4 and [s.dy for s in pk.segs] == [0, 2, 4, 6]
     wout = x.shape[3]
     window = torch.cat([packed[:, :, j:j + wout] for j in range(8)], dim=-1)                        # [B,H+6,W,64]
     got = P.apply_packed_reference(pk, [window, None], (x.shape[2], wout))
+    np.testing.assert_allclose(got.permute(0, 3, 1, 2).detach().numpy(), want.detach().numpy(), atol=2e-6)
+
+
+def test_windowed_stem_packing_with_more_than_four_input_channels():
+    """Cin in 5..8 keeps one K-segment per kernel row (no room for a second row in the 8-channel pixel)."""
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(1, 6, 8, 10, generator=g, dtype=torch.float64)
+    conv = torch.nn.Conv2d(6, 8, 7, bias=False).double()
+    want = torch.relu(conv(F.pad(x, (3, 3, 3, 3), mode="reflect")))
+    pk = P.pack_stem_windowed(conv.weight, torch.ones(8, dtype=torch.float64), torch.zeros(8, dtype=torch.float64))
+    assert len(pk.segs) == 7
+    packed = F.pad(F.pad(x, (3, 3, 3, 3), mode="reflect"), (0, 2, 0, 0, 0, 2)).permute(0, 2, 3, 1)
+    window = torch.cat([packed[:, :, j:j + 10] for j in range(8)], dim=-1)
+    got = P.apply_packed_reference(pk, [window, None], (8, 10))
     np.testing.assert_allclose(got.permute(0, 3, 1, 2).detach().numpy(), want.detach().numpy(), atol=2e-6)
 
 

@@ -196,7 +196,7 @@ def test_bf16x3_program_layout_and_semantics():
     assert isinstance(prog.ops[-1], E.HeadGatherOp) and prog.ops[-2].tag == "head 7x7 rows"
     ops = prog.ops
     assert isinstance(ops[0], E.StemPackOp) and isinstance(ops[1], E.ConvOp) and isinstance(ops[2], E.BorderOp)
-    assert ops[1].ins[0].window == 8 and len(ops[1].packed.segs) == 7
+    assert ops[1].ins[0].window == 8 and len(ops[1].packed.segs) == 4        # two-row packing: kernel rows (0,1) (2,3) (4,5) (6,-)
     # ring discipline: whenever a contraction reads a ring buffer, the last op that touched that buffer
     # before it is a BorderOp (no producer writes rings), and no BorderOp is redundant.
     last = {}
