@@ -439,7 +439,7 @@ def main():
                                     "warm": {"ms": ms_warm, "achieved": fu_bytes / (ms_warm * 1e-3) / 1e9,
                                              "frac": fu_bytes / (ms_warm * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                                     "per_kernel": parts,
-                                    "layout": os.environ.get("LAMA_B200_FU_LAYOUT", "planar"),
+                                    "layout": ("planar" if any(bf.cg for bf in ex.prog.bufs) else "nhwc"),
                                     "traffic": _ncu_traffic("FU:") if (B, S) == (32, 512) else None,
                                     "note": "SURVEY.md 8(d): algorithmic bytes = t in + u out + weights; spectrum "
                                             "intermediates not counted; graded figure = cold L2"}

@@ -461,12 +461,67 @@ def fu_planar_ok(prog: Program, st, h: int, w: int) -> bool:
     LAMA_B200_FU_LAYOUT=nhwc keeps the round-1 channels-last chain (A/B measurements)."""
     if prog.math != L.MATH_BF16X3 or os.environ.get("LAMA_B200_FU_LAYOUT", "planar") != "planar":
         return False
+    dev = st.conv2.weight.device
+    if dev.type == "cuda" and not planar_selftest(dev):
+        return False
     c = st.conv1[0].out_channels
     fu = st.fu
     if st.enable_lfu and not ((h, w) == (64, 64) and c % 32 == 0):      # LFU quadrants: 32x32 planes, c/4 % 8 == 0
         return False
     return ((h, w) in ((64, 64), (32, 32)) and c % 64 == 0 and fu.conv_layer.in_channels == 2 * c + (2 if fu.spectral_pos_encoding else 0)
             and fu.conv_layer.out_channels == 2 * c)
+
+
+_PLANAR_OK: Dict[int, bool] = {}
+
+
+def planar_selftest(device: torch.device) -> bool:
+    """Once per process and device: run the planar chain's three kernels (plane FFT pair, interleaved-operand GEMM with
+    a planar output) on a small random problem and compare with torch on the same device.  The chain depends on
+    details no compile-time check covers (tcgen05 no-swizzle descriptor fields, bulk-copy tile layout); if the check
+    fails the process keeps the channels-last chain of round 1 (still the native kernels) and says so loudly —
+    LAMA_B200_FU_LAYOUT=planar! skips the check and forces the planar chain, =nhwc forces the other."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if os.environ.get("LAMA_B200_FU_LAYOUT") == "planar!":
+        return True
+    if idx in _PLANAR_OK:
+        return _PLANAR_OK[idx]
+    ok, why = True, ""
+    try:
+        with torch.no_grad():
+            b, c, h = 2, 64, 64
+            wf = h // 2 + 1
+            g = torch.Generator().manual_seed(1234)
+            prog = Program("planar_selftest", L.MATH_BF16X3)
+            X = prog.buf("x", b, h, h, c, cg=4)
+            S = prog.buf("s", b, h, wf, 2 * c, gemm=True, cg=8)
+            Z = prog.buf("z", b, h, wf, 2 * c, cg=8)
+            U = prog.buf("u", b, h, h, c, gemm=True, cg=8)
+            wgt = torch.randn(2 * c, 2 * c, 1, 1, generator=g) * 0.1
+            pk = P.pack_conv([(wgt, 0, 0, 0)], None, None, act=L.ACT_RELU)
+            prog.inputs = {"x0": (b, c, h, h)}
+            prog.ops += [ToNHWC("x0", TV(X)), RfftOp(TV(X), TV(S)), ConvOp(pk, [TV(S), None], TV(Z)),
+                         IrfftOp(TV(Z), TV(X), TV(U)), ToNCHW(TV(U), "y0")]
+            prog.outputs = {"y0": (b, c, h, h)}
+            x = torch.randn(b, c, h, h, generator=g).to(device)
+            y = CudaExecutor(prog, device).run({"x0": x})["y0"]
+            f = torch.fft.rfftn(x.double(), dim=(-2, -1), norm="ortho")
+            f = torch.stack((f.real, f.imag), dim=2).reshape(b, 2 * c, h, wf)
+            f = torch.relu(torch.einsum("nk,bkyx->bnyx", wgt[:, :, 0, 0].double().to(device), f))
+            f = f.reshape(b, c, 2, h, wf)
+            want = x.double() + torch.fft.irfftn(torch.complex(f[:, :, 0], f[:, :, 1]), s=(h, h), dim=(-2, -1), norm="ortho")
+            err = float((y.double() - want).abs().max()) / float(want.abs().max())
+            ok, why = err < 1e-3, f"relative error {err:.2e}"
+    except Exception as e:  # noqa: BLE001  (a launch failure is an answer too)
+        ok, why = False, f"{type(e).__name__}: {e}"
+    _PLANAR_OK[idx] = ok
+    if not ok:
+        import warnings
+        msg = (f"lama_b200: the channel-group planar FourierUnit chain failed its start-up check on cuda:{idx} ({why}); "
+               f"using the channels-last chain (native round-1 kernels) instead")
+        warnings.warn(msg, RuntimeWarning)
+        print(msg, file=__import__("sys").stderr, flush=True)
+    return ok
 
 
 def emit_fourier_unit(prog: Program, fu, t: TV, out: TV, residual: Optional[TV]):

@@ -332,6 +332,13 @@ def test_plane_fft_pair_channel_group_planar(b, c, h, residual):
         assert _rel_err(out["y1"].numpy(), want_y) < 2e-5
 
 
+def test_planar_chain_startup_check_passes():
+    """engine.planar_selftest gates the default layout of the SpectralTransform chain; a failure there silently costs
+    the round-2 speed-up (the process keeps the channels-last chain), so it must be a visible test failure."""
+    E._PLANAR_OK.clear()
+    assert E.planar_selftest(torch.device(DEV)) is True
+
+
 @pytest.mark.parametrize("case", ["flat_interleaved_to_planar8", "nhwc_to_planar4", "spatial_taps_plus_interleaved",
                                   "flat_ragged_m"])
 def test_conv_tc_channel_group_planar_operands(case):
