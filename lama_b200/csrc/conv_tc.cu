@@ -58,6 +58,7 @@ struct TcParams {
   long long a_sg[2], a_sb[2], a_sy[2], a_lo[2];
   int a_H[2], a_W[2];
   long long m_total;         // flat mode: B*H*W
+  int bulk_lanes;            // lanes of the producer warp issuing the bulk copies of interleaved tiles (32; 1 = bring-up)
   int hints;                 // L2 residency hints for the planar (FourierUnit chain) outputs
   int desc_swap;             // bring-up: exchange LBO / SBO of the no-swizzle descriptor (FFCB_TC_DESC_SWAP)
   int debug;                 // bring-up knobs (FFCB_TC_DEBUG): 1 no global ld/st in epilogue, 2 no epilogue work,
@@ -301,10 +302,15 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   const long long num_tiles = p.num_m_tiles * p.num_n_tiles;
 
   if (warp == 0) {
-    // ================================================================ TMA producer (one lane)
-    if (lane == 0) {
+    // ================================================================ TMA producer
+    // The whole warp walks the K blocks (warp-uniform control flow); lane 0 owns the mbarrier waits, the expect-tx and
+    // the tensor-map loads.  The 16 (flat) or 16*TH (spatial) 1-D bulk copies of an interleaved operand tile are
+    // spread over the lanes: issued by one lane they cost ~16 x the issue latency of a copy per K block and starve the
+    // MMA pipe (measured: spectral GEMM 102 us vs 65 us with two tensor-map boxes per stage).
+    {
       int stage = 0;
       uint32_t phase = 0;
+      const int bulk_lanes = p.bulk_lanes;
       for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         // tile order: N tiles of one pixel tile are adjacent, so the CTAs working on them run
         // concurrently and share the activation tile through L2 (one DRAM read instead of num_n_tiles)
@@ -317,54 +323,57 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           const int nblk = (g.nch + BK - 1) / BK;
           const int cx = tc.x0 * p.stride + g.dx + p.coord_off[g.src];
           const int cy = tc.y0 * p.stride + g.dy + p.coord_off[g.src];
+          const int il = p.a_il[g.src];
           for (int j = 0; j < nblk; ++j, ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1);
+            if (lane == 0) mbar_wait(&empty[stage], phase ^ 1);
+            if (il) __syncwarp();
             uint8_t* st = smem + (size_t)stage * stage_bytes;
             const bool skip_a = (p.debug & 8) != 0;
-            if (skip_a || !p.a_il[g.src]) mbar_expect_tx(&full[stage], (uint32_t)(skip_a ? 2 * w_bytes : stage_bytes));
             const int cc = g.c0 + j * BK;
-            if (skip_a) {
-            } else if (p.a_il[g.src]) {
+            if (il && !skip_a) {
               // eight channel-group slabs per plane; rows of the tile are contiguous pixels of the group image
-              const int s = g.src;
-              uint32_t a_bytes = 0;
+              const int src_i = g.src;
               if (p.flat) {
                 const long long left = p.m_total - tc.m0;
                 const uint32_t bytes = (uint32_t)(left < BM ? left : BM) * 16u;
-                a_bytes = 16u * bytes;
-                mbar_expect_tx(&full[stage], a_bytes + 2u * (uint32_t)w_bytes);
-                const unsigned short* src = p.a_ptr[s] + (long long)(cc >> 3) * p.a_sg[s] + tc.m0 * 8;
-#pragma unroll 1
-                for (int kg = 0; kg < 8; ++kg) {
-                  bulk_load(st + kg * 2048, src + kg * p.a_sg[s], bytes, &full[stage]);
-                  bulk_load(st + kTileABytes + kg * 2048, src + kg * p.a_sg[s] + p.a_lo[s], bytes, &full[stage]);
+                if (lane == 0) mbar_expect_tx(&full[stage], 16u * bytes + 2u * (uint32_t)w_bytes);
+                __syncwarp();
+                const unsigned short* src = p.a_ptr[src_i] + (long long)(cc >> 3) * p.a_sg[src_i] + tc.m0 * 8;
+                for (int i = lane < bulk_lanes ? lane : 16; i < 16; i += bulk_lanes) {          // i = plane * 8 + slab
+                  const int kg = i & 7, pl = i >> 3;
+                  bulk_load(st + pl * kTileABytes + kg * 2048, src + kg * p.a_sg[src_i] + pl * p.a_lo[src_i], bytes,
+                            &full[stage]);
                 }
               } else {
-                const int x0 = tc.x0, nx = (p.a_W[s] - x0 < p.TW ? p.a_W[s] - x0 : p.TW);
-                int rows = p.a_H[s] - tc.y0;
+                const int x0 = tc.x0, nx = (p.a_W[src_i] - x0 < p.TW ? p.a_W[src_i] - x0 : p.TW);
+                int rows = p.a_H[src_i] - tc.y0;
                 rows = rows < p.TH ? rows : p.TH;
                 const uint32_t bytes = (uint32_t)nx * 16u;
-                a_bytes = 16u * bytes * (uint32_t)rows;
-                mbar_expect_tx(&full[stage], a_bytes + 2u * (uint32_t)w_bytes);
-                const unsigned short* src = p.a_ptr[s] + (long long)(cc >> 3) * p.a_sg[s] + (long long)tc.b * p.a_sb[s] +
-                                            (long long)tc.y0 * p.a_sy[s] + x0 * 8;
-#pragma unroll 1
-                for (int kg = 0; kg < 8; ++kg)
-                  for (int r = 0; r < rows; ++r) {
-                    const unsigned short* q = src + kg * p.a_sg[s] + r * p.a_sy[s];
-                    bulk_load(st + kg * 2048 + r * p.TW * 16, q, bytes, &full[stage]);
-                    bulk_load(st + kTileABytes + kg * 2048 + r * p.TW * 16, q + p.a_lo[s], bytes, &full[stage]);
-                  }
+                if (lane == 0) mbar_expect_tx(&full[stage], 16u * bytes * (uint32_t)rows + 2u * (uint32_t)w_bytes);
+                __syncwarp();
+                const unsigned short* src = p.a_ptr[src_i] + (long long)(cc >> 3) * p.a_sg[src_i] +
+                                            (long long)tc.b * p.a_sb[src_i] + (long long)tc.y0 * p.a_sy[src_i] + x0 * 8;
+                for (int i = lane < bulk_lanes ? lane : 16 * rows; i < 16 * rows; i += bulk_lanes) {    // i = (plane * 8 + slab) * rows + r
+                  const int r = i % rows, ks = i / rows, kg = ks & 7, pl = ks >> 3;
+                  bulk_load(st + pl * kTileABytes + kg * 2048 + r * p.TW * 16,
+                            src + kg * p.a_sg[src_i] + r * p.a_sy[src_i] + pl * p.a_lo[src_i], bytes, &full[stage]);
+                }
               }
-            } else if (p.flat) {
-              tma_load_3d(st, map, &full[stage], cc, (int)tc.m0, 0);
-              tma_load_3d(st + kTileABytes, map, &full[stage], cc, (int)tc.m0, 1);
-            } else {
-              tma_load_5d(st, map, &full[stage], cc, cx, cy, tc.b, 0);
-              tma_load_5d(st + kTileABytes, map, &full[stage], cc, cx, cy, tc.b, 1);
+            } else if (lane == 0) {
+              mbar_expect_tx(&full[stage], (uint32_t)(skip_a ? 2 * w_bytes : stage_bytes));
+              if (skip_a) {
+              } else if (p.flat) {
+                tma_load_3d(st, map, &full[stage], cc, (int)tc.m0, 0);
+                tma_load_3d(st + kTileABytes, map, &full[stage], cc, (int)tc.m0, 1);
+              } else {
+                tma_load_5d(st, map, &full[stage], cc, cx, cy, tc.b, 0);
+                tma_load_5d(st + kTileABytes, map, &full[stage], cc, cx, cy, tc.b, 1);
+              }
             }
-            tma_load_3d(st + 2 * kTileABytes, &map_w, &full[stage], kb * BK, n_tile * p.BN, 0);
-            tma_load_3d(st + 2 * kTileABytes + w_bytes, &map_w, &full[stage], kb * BK, n_tile * p.BN, 1);
+            if (lane == 0) {
+              tma_load_3d(st + 2 * kTileABytes, &map_w, &full[stage], kb * BK, n_tile * p.BN, 0);
+              tma_load_3d(st + 2 * kTileABytes + w_bytes, &map_w, &full[stage], kb * BK, n_tile * p.BN, 1);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -663,6 +672,8 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     const char* sw = getenv("FFCB_TC_DESC_SWAP");
     p.desc_swap = sw ? atoi(sw) : 0;
     p.hints = l2_hints_enabled() ? 1 : 0;
+    const char* bl = getenv("FFCB_TC_BULK_LANES");
+    p.bulk_lanes = (bl && atoi(bl) == 1) ? 1 : 32;
   }
   p.addend = d->addend.ptr ? make_view(d->addend) : null_view();
   p.shift = d->shift;
