@@ -5,6 +5,8 @@ mkdir -p gpurun_out
 OUT=gpurun_out
 export PYTHONUNBUFFERED=1
 python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1; echo "build rc=$?" | tee $OUT/summary_c.txt
+timeout 300 python tools/fft_microbench.py --gemm-knobs > $OUT/gemm_knobs.jsonl 2> $OUT/gemm_knobs.err; echo "gemm knobs rc=$?" | tee -a $OUT/summary_c.txt
+cat $OUT/gemm_knobs.jsonl | tee -a $OUT/summary_c.txt
 timeout 600 python bench.py --steps 10 > $OUT/bench_planar.json 2> $OUT/bench_planar.err; echo "bench planar rc=$?" | tee -a $OUT/summary_c.txt
 LAMA_B200_FU_LAYOUT=nhwc timeout 400 python bench.py --steps 10 --no-cpu-baseline --no-torch-cuda-baseline --no-fp32-arm --io f32 > $OUT/bench_nhwc.json 2> $OUT/bench_nhwc.err; echo "bench nhwc rc=$?" | tee -a $OUT/summary_c.txt
 FFCB_L2_HINTS=0 timeout 400 python bench.py --steps 10 --no-cpu-baseline --no-torch-cuda-baseline --no-fp32-arm --io f32 > $OUT/bench_nohints.json 2> $OUT/bench_nohints.err; echo "bench nohints rc=$?" | tee -a $OUT/summary_c.txt
