@@ -48,9 +48,15 @@ __device__ __forceinline__ void split_pair(float a, float b, unsigned& hi, unsig
 }
 
 // grid: (C/4/sets, B).  A plane set = 4-channel group of the real input = 8-channel (4 complex) group of the spectrum.
-template <int N>
+// DENSE: every tensor is the engine's dense [group][image][y][x][cg] allocation, so in-plane offsets are compile-time
+// constants (one base pointer per thread + immediates instead of 64-bit address arithmetic per access — the kernels
+// are issue-bound: 5.2 K instructions per thread before, a quarter of them integer).
+template <int N, bool DENSE>
 __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) rfft2_plane_cg_kernel(CgArgs a) {
   using Cfg = CgCfg<N>;
+  constexpr unsigned WF = N / 2 + 1;
+  const unsigned in_sy = DENSE ? 4u * N : a.in_sy, in_sx = DENSE ? 4u : a.in_sx;
+  const unsigned sp_sy = DENSE ? 8u * WF : a.sp_sy, sp_sx = DENSE ? 8u : a.sp_sx;
   extern __shared__ __align__(16) float smem_all[];
   const int set = threadIdx.x / Cfg::set_threads, tid = threadIdx.x % Cfg::set_threads;
   const int group = blockIdx.x * Cfg::sets + set;
@@ -64,7 +70,7 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) rfft2_plane
     for (int i = 0; i < Cfg::px_iters; ++i) {
       int y, x;
       cg_pixel_slot<N>(tid, i, y, x);
-      cp_async16(base + 4u * (unsigned)cg_real_idx<N>(y, x, 0), src + ((unsigned)y * a.in_sy + (unsigned)x * a.in_sx),
+      cp_async16(base + 4u * (unsigned)cg_real_idx<N>(y, x, 0), src + ((unsigned)y * in_sy + (unsigned)x * in_sx),
                  pol_in);
     }
     cp_async_wait_all();
@@ -80,23 +86,28 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) rfft2_plane
     unsigned short* lo = hi + a.sp_lo;
     const float scale = a.scale;
     const uint64_t pol_sp = l2_policy(a.hints ? 2 : 0);       // the spectrum is the next kernel's GEMM operand: keep it in L2
-    cg_fwd_cols<N>(
-        tid, [&](int i2) { return S[i2]; },
-        [&](int ky, int kx, int c, float2 z) {
-          const unsigned o = (unsigned)ky * a.sp_sy + (unsigned)kx * a.sp_sx + 2u * (unsigned)c;
-          unsigned h, l;
-          const float2 zs = cscale(z, scale);
-          split_pair(zs.x, zs.y, h, l);
-          st_hint_b32(hi + o, h, pol_sp);
-          st_hint_b32(lo + o, l, pol_sp);
-        });
+    auto emit = [&](int ky, int kx, int c, float2 z) {
+      const unsigned o = (unsigned)ky * sp_sy + (unsigned)kx * sp_sx + 2u * (unsigned)c;
+      unsigned h, l;
+      const float2 zs = cscale(z, scale);
+      split_pair(zs.x, zs.y, h, l);
+      st_hint_b32(hi + o, h, pol_sp);
+      st_hint_b32(lo + o, l, pol_sp);
+    };
+    // the packed DC / Nyquist task (kx == 0) lives in the first warp of a plane set only: warp-uniform branch
+    if (tid < 32) cg_fwd_cols<N, true>(tid, [&](int i2) { return S[i2]; }, emit);
+    else cg_fwd_cols<N, false>(tid, [&](int i2) { return S[i2]; }, emit);
   }
 }
 
 // grid: (C/4/sets, B) over the REAL output's 4-channel groups; spectrum group = the same index (4 complex = 8 floats).
-template <int N, bool HAS_RES, bool OUT_SPLIT>
+template <int N, bool HAS_RES, bool OUT_SPLIT, bool DENSE>
 __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) irfft2_plane_cg_kernel(CgArgs a) {
   using Cfg = CgCfg<N>;
+  constexpr unsigned WF = N / 2 + 1;
+  const unsigned in_sy = DENSE ? 4u * N : a.in_sy, in_sx = DENSE ? 4u : a.in_sx;
+  const unsigned sp_sy = DENSE ? 8u * WF : a.sp_sy, sp_sx = DENSE ? 8u : a.sp_sx;
+  const unsigned out_sy = DENSE ? (OUT_SPLIT ? 8u : 4u) * N : a.out_sy, out_sx = DENSE ? (OUT_SPLIT ? 8u : 4u) : a.out_sx;
   extern __shared__ __align__(16) float smem_all[];
   const int set = threadIdx.x / Cfg::set_threads, tid = threadIdx.x % Cfg::set_threads;
   const int group = blockIdx.x * Cfg::sets + set;
@@ -106,10 +117,10 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) irfft2_plan
     const float* sp = reinterpret_cast<const float*>(a.spec) + (long long)group * a.sp_sg +
                       (long long)blockIdx.y * a.sp_sb + 2 * (tid & 3);
     const uint64_t pol_sp = l2_policy(a.hints ? 1 : 0);       // last use of the post-GEMM spectrum
-    cg_inv_cols<N>(
-        tid,
-        [&](int ky, int kx) { return ld_hint_f2(sp + ((unsigned)ky * a.sp_sy + (unsigned)kx * a.sp_sx), pol_sp); },
-        [&](int i2, float2 z) { S[i2] = z; });
+    auto ldz = [&](int ky, int kx) { return ld_hint_f2(sp + ((unsigned)ky * sp_sy + (unsigned)kx * sp_sx), pol_sp); };
+    auto sts = [&](int i2, float2 z) { S[i2] = z; };
+    if (tid < 32) cg_inv_cols<N, true>(tid, ldz, sts);
+    else cg_inv_cols<N, false>(tid, ldz, sts);
   }
   __syncthreads();
   cg_inv_rows<N>(
@@ -127,7 +138,7 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) irfft2_plan
       for (int j = 0; j < 8; ++j) {
         int y, x;
         cg_pixel_slot<N>(tid, i0 + j, y, x);
-        q[j] = HAS_RES ? ld_hint_f4(res + ((unsigned)y * a.in_sy + (unsigned)x * a.in_sx), pol_res)
+        q[j] = HAS_RES ? ld_hint_f4(res + ((unsigned)y * in_sy + (unsigned)x * in_sx), pol_res)
                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
@@ -141,7 +152,7 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) irfft2_plan
           // out is cg = 8: this plane set's four channels are one half (8 bytes per plane) of the 16-byte pixel granule
           unsigned short* hi = reinterpret_cast<unsigned short*>(a.out) + (long long)(group >> 1) * a.out_sg +
                                (long long)blockIdx.y * a.out_sb + 4 * (group & 1);
-          const unsigned o = (unsigned)y * a.out_sy + (unsigned)x * a.out_sx;
+          const unsigned o = (unsigned)y * out_sy + (unsigned)x * out_sx;
           unsigned h0, l0, h1, l1;
           split_pair(r0, r1, h0, l0);
           split_pair(r2, r3, h1, l1);
@@ -149,7 +160,7 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) irfft2_plan
           st_hint_v2(hi + a.out_lo + o, make_uint2(l0, l1), pol_out);
         } else {
           float* op = reinterpret_cast<float*>(a.out) + (long long)group * a.out_sg +
-                      (long long)blockIdx.y * a.out_sb + ((unsigned)y * a.out_sy + (unsigned)x * a.out_sx);
+                      (long long)blockIdx.y * a.out_sb + ((unsigned)y * out_sy + (unsigned)x * out_sx);
           st_hint_f4(op, make_float4(r0, r1, r2, r3), pol_out);
         }
       }
@@ -188,15 +199,18 @@ bool plane64_cg_inv_eligible(const ffcb_tensor* spec, const ffcb_tensor* residua
   return real_cg4(out);
 }
 
-template <int N>
+template <int N, bool DENSE>
 static int launch_fwd_cg(const CgArgs& a, int groups, int batch, cudaStream_t stream) {
   using Cfg = CgCfg<N>;
-  FFCB_CUDA(cudaFuncSetAttribute(rfft2_plane_cg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes));
+  FFCB_CUDA(cudaFuncSetAttribute(rfft2_plane_cg_kernel<N, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::smem_bytes));
   dim3 grid(groups / Cfg::sets, batch);
-  rfft2_plane_cg_kernel<N><<<grid, kCgThreads, Cfg::smem_bytes, stream>>>(a);
+  rfft2_plane_cg_kernel<N, DENSE><<<grid, kCgThreads, Cfg::smem_bytes, stream>>>(a);
   FFCB_LAUNCH_CHECK("rfft2_plane_cg_kernel");
   return FFCB_OK;
 }
+
+static bool dense_real(const ffcb_tensor* t, int cg) { return t->sx == cg && t->sy == (int64_t)t->W * cg; }
 
 int rfft2_plane64_cg(const ffcb_tensor* in, const ffcb_tensor* spec, cudaStream_t stream) {
   CgArgs a{};
@@ -206,27 +220,30 @@ int rfft2_plane64_cg(const ffcb_tensor* in, const ffcb_tensor* spec, cudaStream_
   a.sp_lo = spec->lo_off;
   a.scale = 1.0f / (float)in->H;
   a.hints = l2_hints_enabled() ? 1 : 0;
-  return in->H == 64 ? launch_fwd_cg<64>(a, in->C / 4, in->B, stream) : launch_fwd_cg<32>(a, in->C / 4, in->B, stream);
+  const bool dense = dense_real(in, 4) && dense_real(spec, 8);
+  if (in->H == 64)
+    return dense ? launch_fwd_cg<64, true>(a, in->C / 4, in->B, stream) : launch_fwd_cg<64, false>(a, in->C / 4, in->B, stream);
+  return dense ? launch_fwd_cg<32, true>(a, in->C / 4, in->B, stream) : launch_fwd_cg<32, false>(a, in->C / 4, in->B, stream);
 }
 
-template <int N, bool HAS_RES, bool OUT_SPLIT>
+template <int N, bool HAS_RES, bool OUT_SPLIT, bool DENSE>
 static int launch_inv_cg(const CgArgs& a, int groups, int batch, cudaStream_t stream) {
   using Cfg = CgCfg<N>;
-  FFCB_CUDA(cudaFuncSetAttribute(irfft2_plane_cg_kernel<N, HAS_RES, OUT_SPLIT>,
+  FFCB_CUDA(cudaFuncSetAttribute(irfft2_plane_cg_kernel<N, HAS_RES, OUT_SPLIT, DENSE>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes));
   dim3 grid(groups / Cfg::sets, batch);
-  irfft2_plane_cg_kernel<N, HAS_RES, OUT_SPLIT><<<grid, kCgThreads, Cfg::smem_bytes, stream>>>(a);
+  irfft2_plane_cg_kernel<N, HAS_RES, OUT_SPLIT, DENSE><<<grid, kCgThreads, Cfg::smem_bytes, stream>>>(a);
   FFCB_LAUNCH_CHECK("irfft2_plane_cg_kernel");
   return FFCB_OK;
 }
 
-template <int N>
+template <int N, bool DENSE>
 static int dispatch_inv_cg(const CgArgs& a, int groups, int batch, bool has_res, bool split, cudaStream_t stream) {
   if (has_res)
-    return split ? launch_inv_cg<N, true, true>(a, groups, batch, stream)
-                 : launch_inv_cg<N, true, false>(a, groups, batch, stream);
-  return split ? launch_inv_cg<N, false, true>(a, groups, batch, stream)
-               : launch_inv_cg<N, false, false>(a, groups, batch, stream);
+    return split ? launch_inv_cg<N, true, true, DENSE>(a, groups, batch, stream)
+                 : launch_inv_cg<N, true, false, DENSE>(a, groups, batch, stream);
+  return split ? launch_inv_cg<N, false, true, DENSE>(a, groups, batch, stream)
+               : launch_inv_cg<N, false, false, DENSE>(a, groups, batch, stream);
 }
 
 int irfft2_plane64_cg(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out,
@@ -243,8 +260,12 @@ int irfft2_plane64_cg(const ffcb_tensor* spec, const ffcb_tensor* residual, cons
   a.scale = 1.0f / (float)out->H;
   a.hints = l2_hints_enabled() ? 1 : 0;
   const bool split = out->fmt == FFCB_BF16X2;
-  return out->H == 64 ? dispatch_inv_cg<64>(a, out->C / 4, out->B, has_res, split, stream)
-                      : dispatch_inv_cg<32>(a, out->C / 4, out->B, has_res, split, stream);
+  const bool dense = dense_real(spec, 8) && dense_real(out, split ? 8 : 4) && (!has_res || dense_real(residual, 4));
+  if (out->H == 64)
+    return dense ? dispatch_inv_cg<64, true>(a, out->C / 4, out->B, has_res, split, stream)
+                 : dispatch_inv_cg<64, false>(a, out->C / 4, out->B, has_res, split, stream);
+  return dense ? dispatch_inv_cg<32, true>(a, out->C / 4, out->B, has_res, split, stream)
+               : dispatch_inv_cg<32, false>(a, out->C / 4, out->B, has_res, split, stream);
 }
 
 }  // namespace ffcb

@@ -67,24 +67,31 @@ FFCB_HD void cg_fwd_rows(int tid, Load&& ld2, Sync&& sync, Store&& st4) {
 
 // ---- forward, column pass: Sx column (kx, c) -> spectrum values (ky, kx) [and (ky, 32) for the packed task kx = 0]
 // `emit(ky, kx, value)`: the caller scales and stores
-template <int N, class Load, class Emit>
+// MAYBE_PACKED = false: the caller guarantees kx != 0 for every thread of the warp (warps 1.. of a plane set), so the
+// Hermitian-split arithmetic and the predicated Nyquist stores of the packed task are not even compiled in.
+template <int N, bool MAYBE_PACKED, class Load, class Emit>
 FFCB_HD void cg_fwd_cols(int tid, Load&& ld, Emit&& emit) {
   using F = RegFft<N>;
   const int c = tid & 3, kx = tid >> 2;
-  const bool packed = kx == 0;
+  const bool packed = MAYBE_PACKED && kx == 0;
   float2 v[N];
 #pragma unroll
   for (int y = 0; y < N; ++y) v[y] = ld(cg_cplx_idx<N>(y, kx, c));
   F::template run<false>(v);
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    const float2 wk = v[F::at(k)], wm = v[F::at((N - k) & (N - 1))];
-    // packed: v = X0 + i X32 with both columns real -> Hermitian split
-    const float2 cm = make_float2(wm.x, -wm.y), df = csub(wk, cm);
-    const float2 x0 = cscale(cadd(wk, cm), 0.5f);
-    const float2 x32 = cscale(make_float2(df.y, -df.x), 0.5f);
-    emit(k, kx, c, packed ? x0 : wk);
-    if (packed) emit(k, N / 2, c, x32);
+    const float2 wk = v[F::at(k)];
+    if constexpr (MAYBE_PACKED) {
+      const float2 wm = v[F::at((N - k) & (N - 1))];
+      // packed: v = X0 + i X32 with both columns real -> Hermitian split
+      const float2 cm = make_float2(wm.x, -wm.y), df = csub(wk, cm);
+      const float2 x0 = cscale(cadd(wk, cm), 0.5f);
+      const float2 x32 = cscale(make_float2(df.y, -df.x), 0.5f);
+      emit(k, kx, c, packed ? x0 : wk);
+      if (packed) emit(k, N / 2, c, x32);
+    } else {
+      emit(k, kx, c, wk);
+    }
   }
 }
 
@@ -92,29 +99,31 @@ FFCB_HD void cg_fwd_cols(int tid, Load&& ld, Emit&& emit) {
 // The packed task (kx = 0) transforms Herm(Z[.,0]) + i Herm(Z[.,32]) whose inverse is Re(ifft Z0) + i Re(ifft Z32):
 // exactly the packed slot the row pass wants (C2R: imaginary parts of bins 0 and 32 are ignored after the H inverse).
 // `ld(ky, kx)`: spectrum value of this task's channel; `st(float2 index, value)`
-template <int N, class Load, class Store>
+template <int N, bool MAYBE_PACKED, class Load, class Store>
 FFCB_HD void cg_inv_cols(int tid, Load&& ld, Store&& st) {
   using F = RegFft<N>;
   const int c = tid & 3, kx = tid >> 2;
-  const bool packed = kx == 0;
+  const bool packed = MAYBE_PACKED && kx == 0;
   float2 v[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) v[k] = ld(k, kx);
+  if constexpr (MAYBE_PACKED) {
 #pragma unroll
-  for (int k = 0; k <= N / 2; ++k) {
-    const int m = (N - k) & (N - 1);
-    const float2 a = v[k], b = v[m];
-    float2 cc = make_float2(0.f, 0.f), d = make_float2(0.f, 0.f);
-    if (packed) {
-      cc = ld(k, N / 2);
-      d = (m != k) ? ld(m, N / 2) : cc;
+    for (int k = 0; k <= N / 2; ++k) {
+      const int m = (N - k) & (N - 1);
+      const float2 a = v[k], b = v[m];
+      float2 cc = make_float2(0.f, 0.f), d = make_float2(0.f, 0.f);
+      if (packed) {
+        cc = ld(k, N / 2);
+        d = (m != k) ? ld(m, N / 2) : cc;
+      }
+      const float2 h0 = cscale(cadd(a, make_float2(b.x, -b.y)), 0.5f);          // Hermitian parts of the two columns
+      const float2 h32 = cscale(cadd(cc, make_float2(d.x, -d.y)), 0.5f);
+      const float2 ih = make_float2(-h32.y, h32.x);                            // i * h32
+      const float2 lo = cadd(h0, ih), hi = csub(h0, ih);                       // h0 + i h32,  h0 - i h32
+      v[k] = packed ? lo : a;
+      if (m != k) v[m] = packed ? make_float2(hi.x, -hi.y) : b;                // conj(h0) + i conj(h32) = conj(h0 - i h32)
     }
-    const float2 h0 = cscale(cadd(a, make_float2(b.x, -b.y)), 0.5f);          // Hermitian parts of the two columns
-    const float2 h32 = cscale(cadd(cc, make_float2(d.x, -d.y)), 0.5f);
-    const float2 ih = make_float2(-h32.y, h32.x);                            // i * h32
-    const float2 lo = cadd(h0, ih), hi = csub(h0, ih);                       // h0 + i h32,  h0 - i h32
-    v[k] = packed ? lo : a;
-    if (m != k) v[m] = packed ? make_float2(hi.x, -hi.y) : b;                // conj(h0) + i conj(h32) = conj(h0 - i h32)
   }
   F::template run<true>(v);
 #pragma unroll
