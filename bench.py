@@ -193,6 +193,37 @@ def torch_cuda_baseline(dev, B, S, steps=5, warmup=3):
                 torch.cuda.empty_cache()
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = keep
+    # the same sub-path inputs through the drop-in modules (native programs), for the ours-vs-eager table
+    try:
+        blk_m = M.FFCResnetBlock(512, padding_type="reflect", norm_layer=torch.nn.BatchNorm2d,
+                                 activation_layer=torch.nn.ReLU, ratio_gin=0.75, ratio_gout=0.75, enable_lfu=False)
+        blk_m.load_state_dict({k[len(blk):]: v for k, v in sd.items() if k.startswith(blk)})
+        blk_m = blk_m.eval().to(dev)
+        fu_m = M.FourierUnit(192, 192)
+        fu_m.load_state_dict({k[len(fu):]: v for k, v in sd.items() if k.startswith(fu)})
+        fu_m = fu_m.eval().to(dev)
+        fu0_m = M.FourierUnit(64, 64)
+        fu0_m.load_state_dict(sd0)
+        fu0_m = fu0_m.eval().to(dev)
+        ours = {"resblock_bs8_%d" % S: lambda: blk_m((xl, xg)),
+                "fourier_unit_B%d_C192_%dx%d" % (B, h, h): lambda: fu_m(t),
+                "fourier_unit_1x64x256x256": lambda: fu0_m(x0)}
+        for name, fn in ours.items():
+            with torch.no_grad():
+                for _ in range(warmup):
+                    fn()
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize(dev)
+            out[name]["ours_module_call_ms"] = e0.elapsed_time(e1) / steps
+        out["note_ours"] = ("ours_module_call_ms = the drop-in module called like the reference module (NCHW float in / out, "
+                            "layout conversion + weight checksum inside the call)")
+    except Exception as ex_o:  # noqa: BLE001
+        out["ours_error"] = f"{type(ex_o).__name__}: {ex_o}"[:300]
     return out
 
 
