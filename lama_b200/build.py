@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC", "-shared",
-]
+] + os.environ.get("LAMA_B200_NVCC_EXTRA", "").split()      # experiments only (e.g. --use_fast_math A/B)
 
 
 def _nvcc():
