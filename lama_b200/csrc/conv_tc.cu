@@ -12,6 +12,8 @@
 //                tap (dy,dx) is the same box shifted by (dx,dy); stride-2 convs use elementStrides=2;
 //                zero-border convs map the interior only and let TMA zero-fill out-of-bounds;
 //                dense 1x1 inputs (spectra, W/2+1 columns) use a flat 3-D map (C, B*H*W, plane);
+//                channel-group planar inputs ([C/8][B][H][W][8], the FourierUnit chain) use a no-swizzle map
+//                (8, pixels..., groups): the box is the "interleaved" K-major operand tile [K/8][pixel][8];
 //   weights    : 3-D map (Kpad, N, plane), K-major.
 // Warp roles (256 threads, persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = MMA issuer
 // (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> shift /
@@ -51,15 +53,12 @@ struct TcParams {
   int obw, obh;              // epilogue store box of one warp: obw x obh pixels (obw*obh == 32)
   int nseg;
   // channel-group planar ("interleaved") A operands: in[src] stored [C/8][B][H][W][8] per plane (ffcb_tensor.cg == 8).
-  // Their K block is loaded as eight [128 pixels][16 B] slabs with 1-D bulk copies and multiplied through a
-  // no-swizzle K-major descriptor (core matrix = 8 pixels x 16 B; SBO 128 B, LBO 2048 B).
+  // Their K block is ONE tensor-map box per plane — (8 elements, 128 pixels, 8 groups), no swizzle — which lands in
+  // shared memory as eight [128 pixels][16 B] slabs: exactly the no-swizzle K-major operand tile (core matrix = 8
+  // pixels x 16 B; SBO 128 B, LBO 2048 B).  The lo plane is addressed as groups a_lg .. of the same map.
   int a_il[2];
-  const unsigned short* a_ptr[2];
-  long long a_sg[2], a_sb[2], a_sy[2], a_lo[2];
-  int a_H[2], a_W[2];
-  long long m_total;         // flat mode: B*H*W
-  int bulk_lanes;            // lanes of the producer warp issuing the bulk copies of interleaved tiles (32; 1 = bring-up)
-  int hints;                 // L2 residency hints for the planar (FourierUnit chain) outputs
+  int a_lg[2];               // group index of the lo plane's first group (lo_off / sg)
+  int out_planar;            // out is channel-group planar float32: stored through a (cg, group, pixel...) tensor map
   int desc_swap;             // bring-up: exchange LBO / SBO of the no-swizzle descriptor (FFCB_TC_DESC_SWAP)
   int debug;                 // bring-up knobs (FFCB_TC_DEBUG): 1 no global ld/st in epilogue, 2 no epilogue work,
                              // 4 no MMA issue, 8 no activation loads
@@ -117,12 +116,6 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// 1-D bulk copy global -> shared, completion on an mbarrier (bytes: multiple of 16, both addresses 16-byte aligned)
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -255,6 +248,9 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, long long m_t
   return t;
 }
 
+// IL: some K segment reads a channel-group planar ("interleaved") operand.  The instantiation without them is the
+// round-1 kernel instruction for instruction (one descriptor kind, no per-segment walk in the MMA issuer).
+template <bool IL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap map_in0,
                const __grid_constant__ CUtensorMap map_in1, const __grid_constant__ CUtensorMap map_w,
@@ -302,15 +298,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   const long long num_tiles = p.num_m_tiles * p.num_n_tiles;
 
   if (warp == 0) {
-    // ================================================================ TMA producer
-    // The whole warp walks the K blocks (warp-uniform control flow); lane 0 owns the mbarrier waits, the expect-tx and
-    // the tensor-map loads.  The 16 (flat) or 16*TH (spatial) 1-D bulk copies of an interleaved operand tile are
-    // spread over the lanes: issued by one lane they cost ~16 x the issue latency of a copy per K block and starve the
-    // MMA pipe (measured: spectral GEMM 102 us vs 65 us with two tensor-map boxes per stage).
-    {
+    // ================================================================ TMA producer (one lane)
+    if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int bulk_lanes = p.bulk_lanes;
       for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         // tile order: N tiles of one pixel tile are adjacent, so the CTAs working on them run
         // concurrently and share the activation tile through L2 (one DRAM read instead of num_n_tiles)
@@ -323,57 +314,32 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           const int nblk = (g.nch + BK - 1) / BK;
           const int cx = tc.x0 * p.stride + g.dx + p.coord_off[g.src];
           const int cy = tc.y0 * p.stride + g.dy + p.coord_off[g.src];
-          const int il = p.a_il[g.src];
+          const int il = IL ? p.a_il[g.src] : 0, lg = IL ? p.a_lg[g.src] : 0;
           for (int j = 0; j < nblk; ++j, ++kb) {
-            if (lane == 0) mbar_wait(&empty[stage], phase ^ 1);
-            if (il) __syncwarp();
+            mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* st = smem + (size_t)stage * stage_bytes;
             const bool skip_a = (p.debug & 8) != 0;
+            mbar_expect_tx(&full[stage], (uint32_t)(skip_a ? 2 * w_bytes : stage_bytes));
             const int cc = g.c0 + j * BK;
-            if (il && !skip_a) {
-              // eight channel-group slabs per plane; rows of the tile are contiguous pixels of the group image
-              const int src_i = g.src;
+            if (skip_a) {
+            } else if (IL && il) {
+              // (8 elements, pixels, 8 channel groups): hi plane groups cc/8 .., lo plane groups lg + cc/8 ..
               if (p.flat) {
-                const long long left = p.m_total - tc.m0;
-                const uint32_t bytes = (uint32_t)(left < BM ? left : BM) * 16u;
-                if (lane == 0) mbar_expect_tx(&full[stage], 16u * bytes + 2u * (uint32_t)w_bytes);
-                __syncwarp();
-                const unsigned short* src = p.a_ptr[src_i] + (long long)(cc >> 3) * p.a_sg[src_i] + tc.m0 * 8;
-                for (int i = lane < bulk_lanes ? lane : 16; i < 16; i += bulk_lanes) {          // i = plane * 8 + slab
-                  const int kg = i & 7, pl = i >> 3;
-                  bulk_load(st + pl * kTileABytes + kg * 2048, src + kg * p.a_sg[src_i] + pl * p.a_lo[src_i], bytes,
-                            &full[stage]);
-                }
+                tma_load_3d(st, map, &full[stage], 0, (int)tc.m0, cc >> 3);
+                tma_load_3d(st + kTileABytes, map, &full[stage], 0, (int)tc.m0, lg + (cc >> 3));
               } else {
-                const int x0 = tc.x0, nx = (p.a_W[src_i] - x0 < p.TW ? p.a_W[src_i] - x0 : p.TW);
-                int rows = p.a_H[src_i] - tc.y0;
-                rows = rows < p.TH ? rows : p.TH;
-                const uint32_t bytes = (uint32_t)nx * 16u;
-                if (lane == 0) mbar_expect_tx(&full[stage], 16u * bytes * (uint32_t)rows + 2u * (uint32_t)w_bytes);
-                __syncwarp();
-                const unsigned short* src = p.a_ptr[src_i] + (long long)(cc >> 3) * p.a_sg[src_i] +
-                                            (long long)tc.b * p.a_sb[src_i] + (long long)tc.y0 * p.a_sy[src_i] + x0 * 8;
-                for (int i = lane < bulk_lanes ? lane : 16 * rows; i < 16 * rows; i += bulk_lanes) {    // i = (plane * 8 + slab) * rows + r
-                  const int r = i % rows, ks = i / rows, kg = ks & 7, pl = ks >> 3;
-                  bulk_load(st + pl * kTileABytes + kg * 2048 + r * p.TW * 16,
-                            src + kg * p.a_sg[src_i] + r * p.a_sy[src_i] + pl * p.a_lo[src_i], bytes, &full[stage]);
-                }
+                tma_load_5d(st, map, &full[stage], 0, tc.x0, tc.y0, tc.b, cc >> 3);
+                tma_load_5d(st + kTileABytes, map, &full[stage], 0, tc.x0, tc.y0, tc.b, lg + (cc >> 3));
               }
-            } else if (lane == 0) {
-              mbar_expect_tx(&full[stage], (uint32_t)(skip_a ? 2 * w_bytes : stage_bytes));
-              if (skip_a) {
-              } else if (p.flat) {
-                tma_load_3d(st, map, &full[stage], cc, (int)tc.m0, 0);
-                tma_load_3d(st + kTileABytes, map, &full[stage], cc, (int)tc.m0, 1);
-              } else {
-                tma_load_5d(st, map, &full[stage], cc, cx, cy, tc.b, 0);
-                tma_load_5d(st + kTileABytes, map, &full[stage], cc, cx, cy, tc.b, 1);
-              }
+            } else if (p.flat) {
+              tma_load_3d(st, map, &full[stage], cc, (int)tc.m0, 0);
+              tma_load_3d(st + kTileABytes, map, &full[stage], cc, (int)tc.m0, 1);
+            } else {
+              tma_load_5d(st, map, &full[stage], cc, cx, cy, tc.b, 0);
+              tma_load_5d(st + kTileABytes, map, &full[stage], cc, cx, cy, tc.b, 1);
             }
-            if (lane == 0) {
-              tma_load_3d(st + 2 * kTileABytes, &map_w, &full[stage], kb * BK, n_tile * p.BN, 0);
-              tma_load_3d(st + 2 * kTileABytes + w_bytes, &map_w, &full[stage], kb * BK, n_tile * p.BN, 1);
-            }
+            tma_load_3d(st + 2 * kTileABytes, &map_w, &full[stage], kb * BK, n_tile * p.BN, 0);
+            tma_load_3d(st + 2 * kTileABytes + w_bytes, &map_w, &full[stage], kb * BK, n_tile * p.BN, 1);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -391,31 +357,53 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
-        int kb = 0;
-        for (int sgi = 0; sgi < p.nseg; ++sgi) {
-          const int il = p.a_il[p.seg[sgi].src];
-          const int nblk = (p.seg[sgi].nch + BK - 1) / BK;
-          for (int j = 0; j < nblk; ++j, ++kb) {
+        if constexpr (!IL) {
+          for (int kb = 0; kb < total_kblocks; ++kb) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint64_t a_hi = il ? make_smem_desc_nosw(st, p.desc_swap) : make_smem_desc(st);
-            const uint64_t a_lo = il ? make_smem_desc_nosw(st + kTileABytes, p.desc_swap) : make_smem_desc(st + kTileABytes);
+            const uint64_t a_hi = make_smem_desc(st);
+            const uint64_t a_lo = make_smem_desc(st + kTileABytes);
             const uint64_t w_hi = make_smem_desc(st + 2 * kTileABytes);
             const uint64_t w_lo = make_smem_desc(st + 2 * kTileABytes + w_bytes);
-            // per UMMA_K = 16 step: +32 B inside the swizzle row, or two 2048-byte slabs of the interleaved tile
-            const uint64_t a_step = il ? (uint64_t)(4096 >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
 #pragma unroll
             for (int k = 0; k < ((p.debug & 4) ? 0 : BK / UMMA_K); ++k) {
-              const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-              const uint64_t aadv = (uint64_t)k * a_step;
-              umma_bf16(d_tmem, a_hi + aadv, w_hi + adv, idesc, (kb | k) != 0);
-              umma_bf16(d_tmem, a_lo + aadv, w_hi + adv, idesc, 1);
-              umma_bf16(d_tmem, a_hi + aadv, w_lo + adv, idesc, 1);
+              const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per UMMA_K inside the swizzle row
+              umma_bf16(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+              umma_bf16(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
+              umma_bf16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
             }
             umma_commit(&empty[stage]);                 // smem stage reusable once these MMAs retire
             if (kb == total_kblocks - 1) umma_commit(&acc_full[acc]);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        } else {
+          int kb = 0;
+          for (int sgi = 0; sgi < p.nseg; ++sgi) {
+            const int il = p.a_il[p.seg[sgi].src];
+            const int nblk = (p.seg[sgi].nch + BK - 1) / BK;
+            for (int j = 0; j < nblk; ++j, ++kb) {
+              mbar_wait(&full[stage], phase);
+              tc_fence_after();
+              const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+              const uint64_t a_hi = il ? make_smem_desc_nosw(st, p.desc_swap) : make_smem_desc(st);
+              const uint64_t a_lo = il ? make_smem_desc_nosw(st + kTileABytes, p.desc_swap) : make_smem_desc(st + kTileABytes);
+              const uint64_t w_hi = make_smem_desc(st + 2 * kTileABytes);
+              const uint64_t w_lo = make_smem_desc(st + 2 * kTileABytes + w_bytes);
+              // per UMMA_K = 16 step: +32 B inside the swizzle row, or two 2048-byte slabs of the interleaved tile
+              const uint64_t a_step = il ? (uint64_t)(4096 >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
+#pragma unroll
+              for (int k = 0; k < ((p.debug & 4) ? 0 : BK / UMMA_K); ++k) {
+                const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                const uint64_t aadv = (uint64_t)k * a_step;
+                umma_bf16(d_tmem, a_hi + aadv, w_hi + adv, idesc, (kb | k) != 0);
+                umma_bf16(d_tmem, a_lo + aadv, w_hi + adv, idesc, 1);
+                umma_bf16(d_tmem, a_hi + aadv, w_lo + adv, idesc, 1);
+              }
+              umma_commit(&empty[stage]);                 // smem stage reusable once these MMAs retire
+              if (kb == total_kblocks - 1) umma_commit(&acc_full[acc]);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
           }
         }
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -503,22 +491,6 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += ad[j];
         }
-        if (p.out.cg != 0) {
-          // channel-group planar float32 output (FourierUnit chain): the lane's pixel is contiguous with its
-          // neighbours' inside every channel group, so plain 16-byte stores are whole lines — no staging tile
-          if (valid && !(p.debug & 1)) {
-            float* ob = reinterpret_cast<float*>(p.out.ptr) + pix_off(p.out, b, y, x);
-            const uint64_t pol = l2_policy(p.hints ? 2 : 0);       // consumed by the next kernel of the chain
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int n = n0 + 4 * q;
-              if (n < p.N)
-                st_hint_f4(ob + (long long)(n / p.out.cg) * p.out.sg + (n % p.out.cg),
-                           make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), pol);
-            }
-          }
-          continue;
-        }
         // the previous TMA store of this warp must have finished reading the staging tile
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
@@ -551,8 +523,17 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         fence_async_smem();
         __syncwarp();
         if (lane == 0 && !(p.debug & 1)) {
-          if (p.flat) tma_store_3d(&map_out, stg, n0, (int)tc.m0 + wq * 32, 0);
-          else tma_store_5d(&map_out, stg, n0, box_x, box_y, tc.b, 0);
+          if (p.out_planar) {
+            // channel-group planar float32 output: the same staging tile ([pixel][32 channels] = [pixel][group][cg])
+            // leaves through a (cg, group, pixel ...) tensor map — one store per warp and chunk, like channels-last
+            const int grp = n0 / p.out.cg;
+            if (p.flat) tma_store_3d(&map_out, stg, 0, grp, (int)tc.m0 + wq * 32);
+            else tma_store_5d(&map_out, stg, 0, grp, box_x, box_y, tc.b);
+          } else if (p.flat) {
+            tma_store_3d(&map_out, stg, n0, (int)tc.m0 + wq * 32, 0);
+          } else {
+            tma_store_5d(&map_out, stg, n0, box_x, box_y, tc.b, 0);
+          }
           tma_store_commit();
         }
       }
@@ -665,15 +646,13 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
 
   TcParams p;
   p.out = make_view(d->out);
+  p.out_planar = d->out.cg != 0 ? 1 : 0;
   if (d->out.cg != 0)
     FFCB_REQUIRE(d->out.fmt == FFCB_F32 && d->out.sx % 4 == 0 && d->out.sy % 4 == 0 && d->out.sb % 4 == 0,
                  "conv(tc): channel-group planar outputs are float32");
   {
     const char* sw = getenv("FFCB_TC_DESC_SWAP");
     p.desc_swap = sw ? atoi(sw) : 0;
-    p.hints = l2_hints_enabled() ? 1 : 0;
-    const char* bl = getenv("FFCB_TC_BULK_LANES");
-    p.bulk_lanes = (bl && atoi(bl) == 1) ? 1 : 32;
   }
   p.addend = d->addend.ptr ? make_view(d->addend) : null_view();
   p.shift = d->shift;
@@ -701,17 +680,15 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     flat = t.H == H && t.W == W && t.sy == (int64_t)W * t.sx && t.sb == (int64_t)H * t.sy;
   }
   for (int s = 0; s < 2; ++s) {
-    p.a_il[s] = 0; p.a_ptr[s] = nullptr; p.a_sg[s] = p.a_sb[s] = p.a_sy[s] = p.a_lo[s] = 0; p.a_H[s] = p.a_W[s] = 0;
+    p.a_il[s] = 0; p.a_lg[s] = 0;
     if (!used[s] || d->in[s].cg == 0) continue;
     const ffcb_tensor& t = d->in[s];
     p.a_il[s] = 1;
-    p.a_ptr[s] = reinterpret_cast<const unsigned short*>(t.ptr);
-    p.a_sg[s] = t.sg; p.a_sb[s] = t.sb; p.a_sy[s] = t.sy; p.a_lo[s] = t.lo_off;
-    p.a_H[s] = t.H; p.a_W[s] = t.W;
-    FFCB_REQUIRE(t.sg % 8 == 0 && t.sb % 8 == 0 && t.sy % 8 == 0 && t.lo_off % 8 == 0,
-                 "conv(tc): channel-group planar in[%d] strides not 16-byte aligned", s);
+    FFCB_REQUIRE(t.sg % 8 == 0 && t.sb % 8 == 0 && t.sy % 8 == 0 && t.lo_off % t.sg == 0,
+                 "conv(tc): channel-group planar in[%d]: strides not 16-byte aligned or lo plane not a whole number of "
+                 "groups away", s);
+    p.a_lg[s] = (int)(t.lo_off / t.sg);
   }
-  p.m_total = (long long)d->out.B * H * W;
   // the epilogue stores 32-pixel boxes through a tensor map: a flattened pixel axis needs a dense output too
   flat = flat && (d->out.cg != 0 || (d->out.sy == (int64_t)W * d->out.sx && d->out.sb == (int64_t)H * d->out.sy));
   p.flat = flat ? 1 : 0;
@@ -735,9 +712,30 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   alignas(64) CUtensorMap maps[4];
   int rc;
   for (int s = 0; s < 2; ++s) {
-    if (!used[s] || p.a_il[s]) { p.coord_off[s] = 0; continue; }     // no tensor map: patched with a valid one below
+    if (!used[s]) { p.coord_off[s] = 0; continue; }     // no tensor map: patched with a valid one below
     const ffcb_tensor& t = d->in[s];
     const cuuint64_t esz = 2;
+    if (p.a_il[s]) {
+      // [group][B][H][W][8]: (8 elements, pixels ..., groups of both planes); no swizzle — the box IS the operand tile
+      p.coord_off[s] = 0;
+      const cuuint64_t groups = (cuuint64_t)p.a_lg[s] + (cuuint64_t)(t.C / 8);
+      if (flat) {
+        cuuint64_t dims[3] = {8, (cuuint64_t)t.B * t.H * t.W, groups};
+        cuuint64_t str[2] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.sg * esz};
+        cuuint32_t box[3] = {8, BM, 8}, es[3] = {1, 1, 1};
+        if ((rc = encode_typed(&maps[s], t.ptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_NONE, 3, dims, str,
+                               box, es, "flat interleaved activations")))
+          return rc;
+      } else {
+        cuuint64_t dims[5] = {8, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)t.B, groups};
+        cuuint64_t str[4] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.sy * esz, (cuuint64_t)t.sb * esz, (cuuint64_t)t.sg * esz};
+        cuuint32_t box[5] = {8, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1, 8}, es[5] = {1, 1, 1, 1, 1};
+        if ((rc = encode_typed(&maps[s], t.ptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_NONE, 5, dims, str,
+                               box, es, "spatial interleaved activations")))
+          return rc;
+      }
+      continue;
+    }
     if (flat) {
       cuuint64_t dims[3] = {(cuuint64_t)t.C, (cuuint64_t)t.B * t.H * t.W, 2};
       cuuint64_t str[2] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.lo_off * esz};
@@ -767,9 +765,32 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   }
 
   for (int s = 0; s < 2; ++s)
-    if (!used[s] || p.a_il[s]) maps[s] = maps[2];      // never dereferenced by the kernel, but prefetched
+    if (!used[s]) maps[s] = maps[2];      // never dereferenced by the kernel, but prefetched
   if (d->out.cg != 0) {
-    maps[3] = maps[2];                                   // planar outputs are stored with plain vector stores
+    // channel-group planar float32 output [group][B][H][W][cg]: (cg, group, pixel ...) — the staging tile's 128-byte
+    // rows are [32/cg groups][cg channels], so the box (cg, 32/cg, 32 pixels) reads them in order (SWIZZLE_128B)
+    const ffcb_tensor& t = d->out;
+    const cuuint64_t esz = 4, cg = (cuuint64_t)t.cg;
+    FFCB_REQUIRE(((uintptr_t)t.ptr % 16) == 0 && (t.sg * esz) % 16 == 0 && (t.sb * esz) % 16 == 0 && (t.sy * esz) % 16 == 0,
+                 "conv(tc): planar out strides / pointer not 16-byte aligned");
+    if (flat) {
+      FFCB_REQUIRE(t.sx == t.cg && t.sy == (int64_t)W * t.sx && t.sb == (int64_t)H * t.sy,
+                   "conv(tc): a flat contraction needs a dense planar output");
+      cuuint64_t dims[3] = {cg, (cuuint64_t)t.C / cg, (cuuint64_t)t.B * t.H * t.W};
+      cuuint64_t str[2] = {(cuuint64_t)t.sg * esz, (cuuint64_t)t.sx * esz};
+      cuuint32_t box[3] = {(cuuint32_t)cg, (cuuint32_t)(32 / cg), 32}, es[3] = {1, 1, 1};
+      if ((rc = encode_typed(&maps[3], t.ptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B, 3, dims, str,
+                             box, es, "flat planar output")))
+        return rc;
+    } else {
+      cuuint64_t dims[5] = {cg, (cuuint64_t)t.C / cg, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)t.B};
+      cuuint64_t str[4] = {(cuuint64_t)t.sg * esz, (cuuint64_t)t.sx * esz, (cuuint64_t)t.sy * esz, (cuuint64_t)t.sb * esz};
+      cuuint32_t box[5] = {(cuuint32_t)cg, (cuuint32_t)(32 / cg), (cuuint32_t)p.obw, (cuuint32_t)p.obh, 1};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      if ((rc = encode_typed(&maps[3], t.ptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B, 5, dims, str,
+                             box, es, "spatial planar output")))
+        return rc;
+    }
   } else {
     // output: fp32 rows of 128 B (SWIZZLE_128B) or split bf16 rows of 64 B per plane (SWIZZLE_64B)
     const ffcb_tensor& t = d->out;
@@ -803,13 +824,16 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   FFCB_REQUIRE(stages >= 2, "conv(tc): BN=%d leaves fewer than 2 pipeline stages", p.BN);
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + bar_bytes + 1024;
-  FFCB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const bool any_il = p.a_il[0] || p.a_il[1];
+  FFCB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FFCB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   int dev = 0, sms = 148;
   FFCB_CUDA(cudaGetDevice(&dev));
   FFCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  conv_tc_kernel<<<grid, kThreads, smem, stream>>>(p, maps[0], maps[1], maps[2], maps[3]);
+  if (any_il) conv_tc_kernel<true><<<grid, kThreads, smem, stream>>>(p, maps[0], maps[1], maps[2], maps[3]);
+  else conv_tc_kernel<false><<<grid, kThreads, smem, stream>>>(p, maps[0], maps[1], maps[2], maps[3]);
   FFCB_LAUNCH_CHECK("conv_tc_kernel");
   return FFCB_OK;
 }
