@@ -163,6 +163,10 @@ __device__ __forceinline__ void st_hint_b32(void* p, unsigned v, uint64_t pol) {
 __device__ __forceinline__ void st_hint_v2(void* p, uint2 v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void st_hint_u4(void* p, uint4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void st_hint_f4(void* p, float4 v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w), "l"(pol) : "memory");

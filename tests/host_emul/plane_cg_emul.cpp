@@ -44,14 +44,33 @@ static bool run_size() {
   snap = smem;
   const float2* Sn = reinterpret_cast<const float2*>(snap.data());
   std::vector<float> spec(N * WF * 8, 1e30f);     // [ky][kx][8]: (re, im) x 4 channels
-  auto emit = [&](int ky, int kx, int c, float2 z) {
-    spec[(ky * WF + kx) * 8 + 2 * c] = z.x / (float)N;
-    spec[(ky * WF + kx) * 8 + 2 * c + 1] = z.y / (float)N;
+  // column results go back in place (Nyquist column of the packed task into a side buffer), then a position loop
+  std::vector<float2> NQ(N * 4, make_float2(1e30f, 1e30f));
+  auto put = [&](int ky, int kx, int c, float2 z) {
+    if (kx == N / 2) NQ[ky * 4 + c] = z;
+    else S[cg_cplx_idx<N>(ky, kx, c)] = z;
   };
   for (int tid = 0; tid < T; ++tid) {       // the kernels compile the packed arithmetic into the first warp only
-    if (tid < 32) cg_fwd_cols<N, true>(tid, [&](int i2) { return Sn[i2]; }, emit);
-    else cg_fwd_cols<N, false>(tid, [&](int i2) { return Sn[i2]; }, emit);
+    if (tid < 32) cg_fwd_cols<N, true>(tid, [&](int i2) { return Sn[i2]; }, put);
+    else cg_fwd_cols<N, false>(tid, [&](int i2) { return Sn[i2]; }, put);
   }
+  int covered = 0;
+  for (int tid = 0; tid < T; ++tid) {
+    int ky, kx;
+    cg_spec_pos0<N>(tid, ky, kx);
+    for (int i = 0; i < CgCfg<N>::pos_iters; ++i) {
+      if (ky < N) {
+        const float2* src = kx == N / 2 ? &NQ[ky * 4] : &S[cg_cplx_idx<N>(ky, kx, 0)];
+        for (int c = 0; c < 4; ++c) {
+          spec[(ky * WF + kx) * 8 + 2 * c] = src[c].x / (float)N;
+          spec[(ky * WF + kx) * 8 + 2 * c + 1] = src[c].y / (float)N;
+        }
+        ++covered;
+      }
+      cg_spec_pos_next<N>(ky, kx);
+    }
+  }
+  if (covered != N * WF) { printf("position loop covered %d of %d\n", covered, N * WF); return false; }
   double err_f = 0;
   for (int c = 0; c < 4; ++c)
     for (int ky = 0; ky < N; ++ky)
