@@ -513,6 +513,18 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
             hi[c ^ sw] = make_uint4(h[0], h[1], h[2], h[3]);
             lo[c ^ sw] = make_uint4(l[0], l[1], l[2], l[3]);
           }
+        } else if (p.out_planar) {
+          // channel-group planar float32 output: staging tile [32/cg groups][32 pixels][cg floats] (dense, no swizzle) —
+          // the image of a (cg, pixels, groups) box whose global strides grow with the dimension (a box with the
+          // group dimension before the pixels faults in the TMA unit)
+          float* stf = reinterpret_cast<float*>(stg);
+          const int cgo = p.out.cg;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int j = (4 * c) / cgo, w = (4 * c) % cgo;
+            *reinterpret_cast<float4*>(stf + (j * 32 + lane) * cgo + w) =
+                make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
         } else {
           // [32 rows][32 floats] = 128-byte rows, TMA SWIZZLE_128B: chunk c of row r lives at c ^ (r & 7)
           float4* dst = reinterpret_cast<float4*>(stg) + lane * 8;
@@ -524,11 +536,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         __syncwarp();
         if (lane == 0 && !(p.debug & 1)) {
           if (p.out_planar) {
-            // channel-group planar float32 output: the same staging tile ([pixel][32 channels] = [pixel][group][cg])
-            // leaves through a (cg, group, pixel ...) tensor map — one store per warp and chunk, like channels-last
+            // channel-group planar float32 output: one (cg, pixels ..., groups) box per warp and chunk
             const int grp = n0 / p.out.cg;
-            if (p.flat) tma_store_3d(&map_out, stg, 0, grp, (int)tc.m0 + wq * 32);
-            else tma_store_5d(&map_out, stg, 0, grp, box_x, box_y, tc.b);
+            if (p.flat) tma_store_3d(&map_out, stg, 0, (int)tc.m0 + wq * 32, grp);
+            else tma_store_5d(&map_out, stg, 0, box_x, box_y, tc.b, grp);
           } else if (p.flat) {
             tma_store_3d(&map_out, stg, n0, (int)tc.m0 + wq * 32, 0);
           } else {
@@ -767,8 +778,8 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   for (int s = 0; s < 2; ++s)
     if (!used[s]) maps[s] = maps[2];      // never dereferenced by the kernel, but prefetched
   if (d->out.cg != 0) {
-    // channel-group planar float32 output [group][B][H][W][cg]: (cg, group, pixel ...) — the staging tile's 128-byte
-    // rows are [32/cg groups][cg channels], so the box (cg, 32/cg, 32 pixels) reads them in order (SWIZZLE_128B)
+    // channel-group planar float32 output [group][B][H][W][cg]: (cg, pixels ..., groups), strides growing with the
+    // dimension; the staging tile is the dense box image [32/cg groups][32 pixels][cg]
     const ffcb_tensor& t = d->out;
     const cuuint64_t esz = 4, cg = (cuuint64_t)t.cg;
     FFCB_REQUIRE(((uintptr_t)t.ptr % 16) == 0 && (t.sg * esz) % 16 == 0 && (t.sb * esz) % 16 == 0 && (t.sy * esz) % 16 == 0,
@@ -776,18 +787,18 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     if (flat) {
       FFCB_REQUIRE(t.sx == t.cg && t.sy == (int64_t)W * t.sx && t.sb == (int64_t)H * t.sy,
                    "conv(tc): a flat contraction needs a dense planar output");
-      cuuint64_t dims[3] = {cg, (cuuint64_t)t.C / cg, (cuuint64_t)t.B * t.H * t.W};
-      cuuint64_t str[2] = {(cuuint64_t)t.sg * esz, (cuuint64_t)t.sx * esz};
-      cuuint32_t box[3] = {(cuuint32_t)cg, (cuuint32_t)(32 / cg), 32}, es[3] = {1, 1, 1};
-      if ((rc = encode_typed(&maps[3], t.ptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B, 3, dims, str,
+      cuuint64_t dims[3] = {cg, (cuuint64_t)t.B * t.H * t.W, (cuuint64_t)t.C / cg};
+      cuuint64_t str[2] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.sg * esz};
+      cuuint32_t box[3] = {(cuuint32_t)cg, 32, (cuuint32_t)(32 / cg)}, es[3] = {1, 1, 1};
+      if ((rc = encode_typed(&maps[3], t.ptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE, 3, dims, str,
                              box, es, "flat planar output")))
         return rc;
     } else {
-      cuuint64_t dims[5] = {cg, (cuuint64_t)t.C / cg, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)t.B};
-      cuuint64_t str[4] = {(cuuint64_t)t.sg * esz, (cuuint64_t)t.sx * esz, (cuuint64_t)t.sy * esz, (cuuint64_t)t.sb * esz};
-      cuuint32_t box[5] = {(cuuint32_t)cg, (cuuint32_t)(32 / cg), (cuuint32_t)p.obw, (cuuint32_t)p.obh, 1};
+      cuuint64_t dims[5] = {cg, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)t.B, (cuuint64_t)t.C / cg};
+      cuuint64_t str[4] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.sy * esz, (cuuint64_t)t.sb * esz, (cuuint64_t)t.sg * esz};
+      cuuint32_t box[5] = {(cuuint32_t)cg, (cuuint32_t)p.obw, (cuuint32_t)p.obh, 1, (cuuint32_t)(32 / cg)};
       cuuint32_t es[5] = {1, 1, 1, 1, 1};
-      if ((rc = encode_typed(&maps[3], t.ptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B, 5, dims, str,
+      if ((rc = encode_typed(&maps[3], t.ptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE, 5, dims, str,
                              box, es, "spatial planar output")))
         return rc;
     }

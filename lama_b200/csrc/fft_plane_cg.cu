@@ -75,28 +75,61 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) rfft2_plane
     }
     cp_async_wait_all();
   }
-  __syncthreads();
-  cg_fwd_rows<N>(
-      tid, [&](int i) { return *reinterpret_cast<const float2*>(smem + i); }, [&]() { __syncwarp(); },
-      [&](int i2, float4 v) { *reinterpret_cast<float4*>(S + i2) = v; });
+  // Two passes (rows, columns) as ONE rolled loop around a single copy of the register transform: the unrolled
+  // transform is most of the kernel's code, and one copy keeps the kernel close to the instruction-cache size.
+  // Column results go back to shared memory in place (the Nyquist column of the packed task into a 2 KB side buffer) and
+  // leave in a rolled loop over spectrum positions: 16-byte stores, the whole plane set is one contiguous stream.
+  float2* NQ = reinterpret_cast<float2*>(smem_all + Cfg::sets * Cfg::set_floats) + set * (N * 4);
+  float2 v[N];
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();                     // pass 0: the cp.async data of all threads; pass 1: the row results
+    if (pass == 0) {
+      cg_fwd_rows_load<N>(tid, v, [&](int i) { return *reinterpret_cast<const float2*>(smem + i); });
+      __syncwarp();                      // a row's two tasks are neighbouring lanes: reads before the in-place writes
+    } else {
+      cg_fwd_cols_load<N>(tid, v, [&](int i2) { return S[i2]; });
+    }
+    RegFft<N>::template run<false>(v);
+    if (pass == 0) {
+      cg_fwd_rows_post<N>(tid, v, [&](int i2, float4 q) { *reinterpret_cast<float4*>(S + i2) = q; });
+    } else {
+      // a column is read and written by its own task only: in place, no barrier between the loads above and these stores
+      auto put = [&](int ky, int kx, int c, float2 z) {
+        if (kx == N / 2) NQ[ky * 4 + c] = z;
+        else S[cg_cplx_idx<N>(ky, kx, c)] = z;
+      };
+      if (tid < 32) cg_fwd_cols_post<N, true>(tid, v, put);     // the packed DC / Nyquist task lives in the first warp
+      else cg_fwd_cols_post<N, false>(tid, v, put);
+    }
+  }
   __syncthreads();
   {
     unsigned short* hi = reinterpret_cast<unsigned short*>(a.spec) + (long long)group * a.sp_sg +
                          (long long)blockIdx.y * a.sp_sb;
-    unsigned short* lo = hi + a.sp_lo;
     const float scale = a.scale;
-    const uint64_t pol_sp = l2_policy(a.hints ? 2 : 0);       // the spectrum is the next kernel's GEMM operand: keep it in L2
-    auto emit = [&](int ky, int kx, int c, float2 z) {
-      const unsigned o = (unsigned)ky * sp_sy + (unsigned)kx * sp_sx + 2u * (unsigned)c;
-      unsigned h, l;
-      const float2 zs = cscale(z, scale);
-      split_pair(zs.x, zs.y, h, l);
-      st_hint_b32(hi + o, h, pol_sp);
-      st_hint_b32(lo + o, l, pol_sp);
-    };
-    // the packed DC / Nyquist task (kx == 0) lives in the first warp of a plane set only: warp-uniform branch
-    if (tid < 32) cg_fwd_cols<N, true>(tid, [&](int i2) { return S[i2]; }, emit);
-    else cg_fwd_cols<N, false>(tid, [&](int i2) { return S[i2]; }, emit);
+    const uint64_t pol_sp = l2_policy(a.hints ? 2 : 0);     // the spectrum is the next kernel's GEMM operand: keep it in L2
+    int ky, kx;
+    cg_spec_pos0<N>(tid, ky, kx);
+#pragma unroll 1
+    for (int i = 0; i < Cfg::pos_iters; ++i) {
+      if (ky < N) {
+        const float4* src = kx == N / 2 ? reinterpret_cast<const float4*>(NQ + ky * 4)
+                                        : reinterpret_cast<const float4*>(S + cg_cplx_idx<N>(ky, kx, 0));
+        const float4 q0 = src[0], q1 = src[1];               // (re, im) of channels 0,1 | 2,3
+        uint4 h, l;
+        const float2 z0 = cscale(make_float2(q0.x, q0.y), scale), z1 = cscale(make_float2(q0.z, q0.w), scale);
+        const float2 z2 = cscale(make_float2(q1.x, q1.y), scale), z3 = cscale(make_float2(q1.z, q1.w), scale);
+        split_pair(z0.x, z0.y, h.x, l.x);
+        split_pair(z1.x, z1.y, h.y, l.y);
+        split_pair(z2.x, z2.y, h.z, l.z);
+        split_pair(z3.x, z3.y, h.w, l.w);
+        unsigned short* dst = hi + ((unsigned)ky * sp_sy + (unsigned)kx * sp_sx);
+        st_hint_u4(dst, h, pol_sp);
+        st_hint_u4(dst + a.sp_lo, l, pol_sp);
+      }
+      cg_spec_pos_next<N>(ky, kx);
+    }
   }
 }
 
@@ -118,20 +151,29 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) irfft2_plan
                       (long long)blockIdx.y * a.sp_sb + 2 * (tid & 3);
     const uint64_t pol_sp = l2_policy(a.hints ? 1 : 0);       // last use of the post-GEMM spectrum
     auto ldz = [&](int ky, int kx) { return ld_hint_f2(sp + ((unsigned)ky * sp_sy + (unsigned)kx * sp_sx), pol_sp); };
-    auto sts = [&](int i2, float2 z) { S[i2] = z; };
-    if (tid < 32) cg_inv_cols<N, true>(tid, ldz, sts);
-    else cg_inv_cols<N, false>(tid, ldz, sts);
+    // columns, then rows: one rolled loop around a single copy of the inverse register transform (see the forward kernel)
+    float2 v[N];
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 0) {
+        if (tid < 32) cg_inv_cols_load<N, true>(tid, v, ldz);
+        else cg_inv_cols_load<N, false>(tid, v, ldz);
+      } else {
+        __syncthreads();
+        cg_inv_rows_load<N>(tid, v, [&](int i2) { return *reinterpret_cast<const float4*>(S + i2); });
+        __syncwarp();
+      }
+      RegFft<N>::template run<true>(v);
+      if (pass == 0) cg_inv_cols_post<N>(tid, v, [&](int i2, float2 z) { S[i2] = z; });
+      else cg_inv_rows_post<N>(tid, v, [&](int i, float2 z) { *reinterpret_cast<float2*>(smem + i) = z; });
+    }
   }
-  __syncthreads();
-  cg_inv_rows<N>(
-      tid, [&](int i2) { return *reinterpret_cast<const float4*>(S + i2); }, [&]() { __syncwarp(); },
-      [&](int i, float2 z) { *reinterpret_cast<float2*>(smem + i) = z; });
   __syncthreads();
   {   // epilogue: whole pixels (4 channels), lanes along x: + residual, scale, convert, store
     const float* res = HAS_RES ? a.in + (long long)group * a.in_sg + (long long)blockIdx.y * a.in_sb : nullptr;
     const float scale = a.scale;
     const uint64_t pol_res = l2_policy(a.hints ? 1 : 0), pol_out = l2_policy(a.hints ? 2 : 0);   // u feeds the next contraction
-#pragma unroll 2
+#pragma unroll 1
     for (int i0 = 0; i0 < Cfg::px_iters; i0 += 8) {
       float4 q[8];
 #pragma unroll
@@ -203,9 +245,9 @@ template <int N, bool DENSE>
 static int launch_fwd_cg(const CgArgs& a, int groups, int batch, cudaStream_t stream) {
   using Cfg = CgCfg<N>;
   FFCB_CUDA(cudaFuncSetAttribute(rfft2_plane_cg_kernel<N, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::smem_bytes));
+                                 Cfg::fwd_smem_bytes));
   dim3 grid(groups / Cfg::sets, batch);
-  rfft2_plane_cg_kernel<N, DENSE><<<grid, kCgThreads, Cfg::smem_bytes, stream>>>(a);
+  rfft2_plane_cg_kernel<N, DENSE><<<grid, kCgThreads, Cfg::fwd_smem_bytes, stream>>>(a);
   FFCB_LAUNCH_CHECK("rfft2_plane_cg_kernel");
   return FFCB_OK;
 }
