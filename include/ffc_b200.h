@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define FFCB_VERSION 110 /* 0.1.1: ffcb_tensor gained the channel-group fields sg / cg */
+#define FFCB_VERSION 111 /* 0.1.1: ffcb_tensor gained the channel-group fields cg / tile / sg */
 
 enum {
   FFCB_OK = 0,
@@ -79,7 +79,14 @@ typedef struct {
                       FourierUnit chain (SpectralTransform.conv1 -> rfft2 -> spectral conv -> irfft2 -> conv2,
                       ffc.py:145-161): one (image, group) plane set is ONE contiguous block for the plane FFT kernels
                       and the [K/8][pixel][8] "interleaved" (no-swizzle, K-major) operand tile of tcgen05.mma. */
-  int64_t sg;      /* stride between channel groups (elements); ignored when cg == 0 */
+  int32_t tile;    /* 0, or 128 with cg == 8: "tile-blocked" variant for tcgen05 operands — pixels are flattened
+                      (m = (b*H + y)*W + x over the view) and stored in blocks of 128:
+                        element (m, c) at ptr + (m/128)*sg + (c/8)*1024 + (m%128)*8 + c%8
+                      so the [8 groups][128 pixels][8] operand tile of one 64-channel K block of one 128-pixel M tile is
+                      ONE contiguous 16 KB run (a single cp.async.bulk per plane); sg = elements per 128-pixel block
+                      (all groups of the allocation), sb / sy / sx are ignored.  Written by the plane FFT kernels,
+                      read by ffcb_conv (tcgen05 arm; 1x1 taps; M tiles that coincide with the blocks). */
+  int64_t sg;      /* cg > 0: stride between channel groups (elements), or between 128-pixel blocks when tile != 0 */
 } ffcb_tensor;
 
 /* One K-segment of an implicit-GEMM convolution: `nch` input channels starting at channel

@@ -17,7 +17,7 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
 BORDER_ZERO, BORDER_REFLECT = 0, 1
 MATH_FP32, MATH_BF16X3 = 0, 1
 MAX_KSEG = 64
-VERSION = 110
+VERSION = 111
 
 
 class Tensor(C.Structure):
@@ -25,7 +25,7 @@ class Tensor(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("sb", C.c_int64), ("sy", C.c_int64), ("sx", C.c_int64),
                 ("lo_off", C.c_int64), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
                 ("fmt", C.c_int32), ("pad", C.c_int32), ("reflect_border", C.c_int32), ("window", C.c_int32),
-                ("cg", C.c_int32), ("sg", C.c_int64)]
+                ("cg", C.c_int32), ("tile", C.c_int32), ("sg", C.c_int64)]
 
 
 class KSeg(C.Structure):

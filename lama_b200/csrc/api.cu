@@ -54,6 +54,10 @@ int check_tensor(const ffcb_tensor* t, const char* name, bool allow_cg) {
                  t->cg, t->C);
     FFCB_REQUIRE(t->sx >= t->cg && t->sg % 4 == 0 && t->sg > 0 && !t->window && t->pad == 0,
                  "%s: bad channel-group strides (sx=%lld, sg=%lld)", name, (long long)t->sx, (long long)t->sg);
+    FFCB_REQUIRE(t->tile == 0 || (t->tile == 128 && t->cg == 8 && t->sg % 1024 == 0 && t->sg >= (long long)(t->C / 8) * 1024),
+                 "%s: tile-blocked views need tile=128, cg=8 and sg = a whole number of 1024-element group slabs", name);
+  } else {
+    FFCB_REQUIRE(t->tile == 0, "%s: tile != 0 needs cg == 8", name);
   }
   (void)esz;
   return FFCB_OK;

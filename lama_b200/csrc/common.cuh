@@ -40,7 +40,7 @@ struct View {
   char* ptr;
   long long sb, sy, sx, lo_off, sg;
   int B, H, W, C;
-  int fmt, pad, reflect_border, cg;
+  int fmt, pad, reflect_border, cg, tile;
 };
 
 inline View make_view(const ffcb_tensor& t) {
@@ -50,6 +50,7 @@ inline View make_view(const ffcb_tensor& t) {
   v.B = t.B; v.H = t.H; v.W = t.W; v.C = t.C;
   v.fmt = t.fmt; v.pad = t.pad; v.reflect_border = t.reflect_border;
   v.cg = t.cg; v.sg = t.cg ? t.sg : 0;
+  v.tile = t.cg ? t.tile : 0;
   return v;
 }
 
@@ -70,6 +71,15 @@ __host__ __device__ __forceinline__ long long pix_off(const View& v, int b, int 
 // element offset of channel c inside a pixel: c for channels-last views, (c / cg) * sg + c % cg for channel-group planar
 __host__ __device__ __forceinline__ long long chan_off(const View& v, int c) {
   return v.cg ? (long long)(c / v.cg) * v.sg + (c % v.cg) : (long long)c;
+}
+
+// element offset of (b, y, x, c) for every layout: channels-last, channel-group planar, tile-blocked
+__host__ __device__ __forceinline__ long long elem_off(const View& v, int b, int y, int x, int c) {
+  if (v.tile) {
+    const long long m = ((long long)b * v.H + y) * v.W + x;
+    return (m >> 7) * v.sg + (long long)(c >> 3) * 1024 + (m & 127) * 8 + (c & 7);
+  }
+  return pix_off(v, b, y, x) + chan_off(v, c);
 }
 
 // reflect without edge repeat: -1 -> 1, n -> n-2 (valid for |overshoot| < n)

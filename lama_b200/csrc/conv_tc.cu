@@ -12,8 +12,8 @@
 //                tap (dy,dx) is the same box shifted by (dx,dy); stride-2 convs use elementStrides=2;
 //                zero-border convs map the interior only and let TMA zero-fill out-of-bounds;
 //                dense 1x1 inputs (spectra, W/2+1 columns) use a flat 3-D map (C, B*H*W, plane);
-//                channel-group planar inputs ([C/8][B][H][W][8], the FourierUnit chain) use a no-swizzle map
-//                (8, pixels..., groups): the box is the "interleaved" K-major operand tile [K/8][pixel][8];
+//                tile-blocked inputs (ffcb_tensor.tile, the FourierUnit chain) need no map: the "interleaved"
+//                K-major operand tile [K/8][pixel][8] is one contiguous 16 KB run, fetched with a 1-D bulk copy;
 //   weights    : 3-D map (Kpad, N, plane), K-major.
 // Warp roles (256 threads, persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = MMA issuer
 // (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> shift /
@@ -52,13 +52,17 @@ struct TcParams {
   int coord_off[2];          // +1 when in[src] is mapped with its border ring
   int obw, obh;              // epilogue store box of one warp: obw x obh pixels (obw*obh == 32)
   int nseg;
-  // channel-group planar ("interleaved") A operands: in[src] stored [C/8][B][H][W][8] per plane (ffcb_tensor.cg == 8).
-  // Their K block is ONE tensor-map box per plane — (8 elements, 128 pixels, 8 groups), no swizzle — which lands in
-  // shared memory as eight [128 pixels][16 B] slabs: exactly the no-swizzle K-major operand tile (core matrix = 8
-  // pixels x 16 B; SBO 128 B, LBO 2048 B).  The lo plane is addressed as groups a_lg .. of the same map.
+  // Tile-blocked "interleaved" A operands (ffcb_tensor.tile == 128, cg == 8; the FourierUnit chain): the operand tile
+  // [8 groups][128 pixels][8 channels] of one 64-channel K block of one M tile is ONE contiguous 16 KB run per plane,
+  // fetched with a single 1-D bulk copy and multiplied through a no-swizzle K-major descriptor (core matrix = 8
+  // pixels x 16 B; SBO 128 B, LBO 2048 B).  (Measured alternatives: sixteen 2 KB bulk copies of a plain group-planar
+  // tensor: +24 us on the spectral GEMM; a (8, 128, 8) tensor-map box with its 16-byte rows: +65 us.)
   int a_il[2];
-  int a_lg[2];               // group index of the lo plane's first group (lo_off / sg)
-  int out_planar;            // out is channel-group planar float32: stored through a (cg, group, pixel...) tensor map
+  const unsigned short* a_ptr[2];
+  long long a_sg[2], a_lo[2];     // elements per 128-pixel block, hi -> lo plane offset
+  int a_tiles_per_image[2];       // spatial mode: 128-pixel blocks per image (H * W / 128)
+  int out_planar;                 // out is channel-group planar float32: stored straight from registers
+  int hints;                      // L2 residency hints for the planar (FourierUnit chain) outputs
   int desc_swap;             // bring-up: exchange LBO / SBO of the no-swizzle descriptor (FFCB_TC_DESC_SWAP)
   int debug;                 // bring-up knobs (FFCB_TC_DEBUG): 1 no global ld/st in epilogue, 2 no epilogue work,
                              // 4 no MMA issue, 8 no activation loads
@@ -116,6 +120,12 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes: multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -250,7 +260,8 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, long long m_t
 
 // IL: some K segment reads a channel-group planar ("interleaved") operand.  The instantiation without them is the
 // round-1 kernel instruction for instruction (one descriptor kind, no per-segment walk in the MMA issuer).
-template <bool IL>
+// PO: the output is channel-group planar float32 (stored from registers instead of through the staging tile).
+template <bool IL, bool PO>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap map_in0,
                const __grid_constant__ CUtensorMap map_in1, const __grid_constant__ CUtensorMap map_w,
@@ -314,7 +325,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           const int nblk = (g.nch + BK - 1) / BK;
           const int cx = tc.x0 * p.stride + g.dx + p.coord_off[g.src];
           const int cy = tc.y0 * p.stride + g.dy + p.coord_off[g.src];
-          const int il = IL ? p.a_il[g.src] : 0, lg = IL ? p.a_lg[g.src] : 0;
+          const int il = IL ? p.a_il[g.src] : 0;
           for (int j = 0; j < nblk; ++j, ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* st = smem + (size_t)stage * stage_bytes;
@@ -323,14 +334,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
             const int cc = g.c0 + j * BK;
             if (skip_a) {
             } else if (IL && il) {
-              // (8 elements, pixels, 8 channel groups): hi plane groups cc/8 .., lo plane groups lg + cc/8 ..
-              if (p.flat) {
-                tma_load_3d(st, map, &full[stage], 0, (int)tc.m0, cc >> 3);
-                tma_load_3d(st + kTileABytes, map, &full[stage], 0, (int)tc.m0, lg + (cc >> 3));
-              } else {
-                tma_load_5d(st, map, &full[stage], 0, tc.x0, tc.y0, tc.b, cc >> 3);
-                tma_load_5d(st + kTileABytes, map, &full[stage], 0, tc.x0, tc.y0, tc.b, lg + (cc >> 3));
-              }
+              // one contiguous 16 KB run per plane: block of this M tile, groups cc/8 .. cc/8+7
+              const long long blk = p.flat ? (tc.m0 >> 7)
+                                           : (long long)tc.b * p.a_tiles_per_image[g.src] + ((tc.y0 * p.out.W) >> 7);
+              const unsigned short* src = p.a_ptr[g.src] + blk * p.a_sg[g.src] + (long long)(cc >> 3) * 1024;
+              bulk_load(st, src, kTileABytes, &full[stage]);
+              bulk_load(st + kTileABytes, src + p.a_lo[g.src], kTileABytes, &full[stage]);
             } else if (p.flat) {
               tma_load_3d(st, map, &full[stage], cc, (int)tc.m0, 0);
               tma_load_3d(st + kTileABytes, map, &full[stage], cc, (int)tc.m0, 1);
@@ -491,6 +500,23 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += ad[j];
         }
+        if constexpr (PO) {
+          // channel-group planar float32 output (FourierUnit chain): the lane's pixel is contiguous with its
+          // neighbours' inside every channel group, so plain 16-byte stores are whole lines — no staging tile.
+          // (A tensor-map store with 16 / 32-byte boxes was measured 2.5x slower than these stores.)
+          if (valid && !(p.debug & 1)) {
+            float* ob = reinterpret_cast<float*>(p.out.ptr) + pix_off(p.out, b, y, x);
+            const uint64_t pol = l2_policy(p.hints ? 2 : 0);       // consumed by the next kernel of the chain
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int n = n0 + 4 * q;
+              if (n < p.N)
+                st_hint_f4(ob + (long long)(n / p.out.cg) * p.out.sg + (n % p.out.cg),
+                           make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), pol);
+            }
+          }
+          continue;
+        }
         // the previous TMA store of this warp must have finished reading the staging tile
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
@@ -513,18 +539,6 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
             hi[c ^ sw] = make_uint4(h[0], h[1], h[2], h[3]);
             lo[c ^ sw] = make_uint4(l[0], l[1], l[2], l[3]);
           }
-        } else if (p.out_planar) {
-          // channel-group planar float32 output: staging tile [32/cg groups][32 pixels][cg floats] (dense, no swizzle) —
-          // the image of a (cg, pixels, groups) box whose global strides grow with the dimension (a box with the
-          // group dimension before the pixels faults in the TMA unit)
-          float* stf = reinterpret_cast<float*>(stg);
-          const int cgo = p.out.cg;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int j = (4 * c) / cgo, w = (4 * c) % cgo;
-            *reinterpret_cast<float4*>(stf + (j * 32 + lane) * cgo + w) =
-                make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          }
         } else {
           // [32 rows][32 floats] = 128-byte rows, TMA SWIZZLE_128B: chunk c of row r lives at c ^ (r & 7)
           float4* dst = reinterpret_cast<float4*>(stg) + lane * 8;
@@ -535,16 +549,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         fence_async_smem();
         __syncwarp();
         if (lane == 0 && !(p.debug & 1)) {
-          if (p.out_planar) {
-            // channel-group planar float32 output: one (cg, pixels ..., groups) box per warp and chunk
-            const int grp = n0 / p.out.cg;
-            if (p.flat) tma_store_3d(&map_out, stg, 0, (int)tc.m0 + wq * 32, grp);
-            else tma_store_5d(&map_out, stg, 0, box_x, box_y, tc.b, grp);
-          } else if (p.flat) {
-            tma_store_3d(&map_out, stg, n0, (int)tc.m0 + wq * 32, 0);
-          } else {
-            tma_store_5d(&map_out, stg, n0, box_x, box_y, tc.b, 0);
-          }
+          if (p.flat) tma_store_3d(&map_out, stg, n0, (int)tc.m0 + wq * 32, 0);
+          else tma_store_5d(&map_out, stg, n0, box_x, box_y, tc.b, 0);
           tma_store_commit();
         }
       }
@@ -641,8 +647,9 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     FFCB_REQUIRE(t.fmt == FFCB_BF16X2, "conv(tc): in[%d] must be split bf16 (FFCB_BF16X2)", s);
     if (t.cg != 0) {
       // interleaved operand: 1x1 taps at unit stride only, whole 64-channel K blocks, dense group images
-      FFCB_REQUIRE(t.cg == 8 && !taps[s] && d->stride == 1 && t.sx == 8 && t.H == d->out.H && t.W == d->out.W,
-                   "conv(tc): channel-group planar in[%d] needs cg=8, dense pixels, 1x1 taps and stride 1", s);
+      FFCB_REQUIRE(t.cg == 8 && t.tile == 128 && !taps[s] && d->stride == 1 && t.H == d->out.H && t.W == d->out.W,
+                   "conv(tc): a channel-group planar in[%d] must be tile-blocked (tile=128, cg=8) with 1x1 taps, stride 1",
+                   s);
       for (int i = 0; i < d->nseg; ++i)
         if (d->seg[i].src == s)
           FFCB_REQUIRE(d->seg[i].nch % 64 == 0 && d->seg[i].c0 % 8 == 0,
@@ -664,6 +671,7 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   {
     const char* sw = getenv("FFCB_TC_DESC_SWAP");
     p.desc_swap = sw ? atoi(sw) : 0;
+    p.hints = l2_hints_enabled() ? 1 : 0;
   }
   p.addend = d->addend.ptr ? make_view(d->addend) : null_view();
   p.shift = d->shift;
@@ -688,17 +696,17 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   for (int s = 0; s < 2 && flat; ++s) {
     if (!used[s]) continue;
     const ffcb_tensor& t = d->in[s];
-    flat = t.H == H && t.W == W && t.sy == (int64_t)W * t.sx && t.sb == (int64_t)H * t.sy;
+    flat = t.H == H && t.W == W && (t.tile != 0 || (t.sy == (int64_t)W * t.sx && t.sb == (int64_t)H * t.sy));
   }
   for (int s = 0; s < 2; ++s) {
-    p.a_il[s] = 0; p.a_lg[s] = 0;
+    p.a_il[s] = 0; p.a_ptr[s] = nullptr; p.a_sg[s] = p.a_lo[s] = 0; p.a_tiles_per_image[s] = 0;
     if (!used[s] || d->in[s].cg == 0) continue;
     const ffcb_tensor& t = d->in[s];
     p.a_il[s] = 1;
-    FFCB_REQUIRE(t.sg % 8 == 0 && t.sb % 8 == 0 && t.sy % 8 == 0 && t.lo_off % t.sg == 0,
-                 "conv(tc): channel-group planar in[%d]: strides not 16-byte aligned or lo plane not a whole number of "
-                 "groups away", s);
-    p.a_lg[s] = (int)(t.lo_off / t.sg);
+    p.a_ptr[s] = reinterpret_cast<const unsigned short*>(t.ptr);
+    p.a_sg[s] = t.sg; p.a_lo[s] = t.lo_off;
+    p.a_tiles_per_image[s] = (t.H * t.W) >> 7;
+    FFCB_REQUIRE(t.lo_off % 8 == 0, "conv(tc): tile-blocked in[%d]: lo plane not 16-byte aligned", s);
   }
   // the epilogue stores 32-pixel boxes through a tensor map: a flattened pixel axis needs a dense output too
   flat = flat && (d->out.cg != 0 || (d->out.sy == (int64_t)W * d->out.sx && d->out.sb == (int64_t)H * d->out.sy));
@@ -716,6 +724,11 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     FFCB_REQUIRE(p.TW * d->stride <= 256 && p.TH * d->stride <= 256, "conv(tc): tile exceeds the TMA box limit");
   }
 
+  for (int s = 0; s < 2; ++s)
+    if (p.a_il[s] && !flat)
+      FFCB_REQUIRE(p.TW == W && p.TW * p.TH == BM && H % p.TH == 0 && (H * W) % BM == 0,
+                   "conv(tc): tile-blocked in[%d] in a spatial contraction needs M tiles of whole rows (W a power of two "
+                   "<= 128 dividing 128, H*W a multiple of 128); got %dx%d", s, H, W);
   p.obw = p.TW < 32 ? p.TW : 32;
   p.obh = 32 / p.obw;
 
@@ -726,27 +739,7 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     if (!used[s]) { p.coord_off[s] = 0; continue; }     // no tensor map: patched with a valid one below
     const ffcb_tensor& t = d->in[s];
     const cuuint64_t esz = 2;
-    if (p.a_il[s]) {
-      // [group][B][H][W][8]: (8 elements, pixels ..., groups of both planes); no swizzle — the box IS the operand tile
-      p.coord_off[s] = 0;
-      const cuuint64_t groups = (cuuint64_t)p.a_lg[s] + (cuuint64_t)(t.C / 8);
-      if (flat) {
-        cuuint64_t dims[3] = {8, (cuuint64_t)t.B * t.H * t.W, groups};
-        cuuint64_t str[2] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.sg * esz};
-        cuuint32_t box[3] = {8, BM, 8}, es[3] = {1, 1, 1};
-        if ((rc = encode_typed(&maps[s], t.ptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_NONE, 3, dims, str,
-                               box, es, "flat interleaved activations")))
-          return rc;
-      } else {
-        cuuint64_t dims[5] = {8, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)t.B, groups};
-        cuuint64_t str[4] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.sy * esz, (cuuint64_t)t.sb * esz, (cuuint64_t)t.sg * esz};
-        cuuint32_t box[5] = {8, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1, 8}, es[5] = {1, 1, 1, 1, 1};
-        if ((rc = encode_typed(&maps[s], t.ptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_NONE, 5, dims, str,
-                               box, es, "spatial interleaved activations")))
-          return rc;
-      }
-      continue;
-    }
+    if (p.a_il[s]) { p.coord_off[s] = 0; continue; }       // bulk copies: no tensor map (patched with a valid one below)
     if (flat) {
       cuuint64_t dims[3] = {(cuuint64_t)t.C, (cuuint64_t)t.B * t.H * t.W, 2};
       cuuint64_t str[2] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.lo_off * esz};
@@ -776,32 +769,9 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   }
 
   for (int s = 0; s < 2; ++s)
-    if (!used[s]) maps[s] = maps[2];      // never dereferenced by the kernel, but prefetched
+    if (!used[s] || p.a_il[s]) maps[s] = maps[2];      // never dereferenced by the kernel, but prefetched
   if (d->out.cg != 0) {
-    // channel-group planar float32 output [group][B][H][W][cg]: (cg, pixels ..., groups), strides growing with the
-    // dimension; the staging tile is the dense box image [32/cg groups][32 pixels][cg]
-    const ffcb_tensor& t = d->out;
-    const cuuint64_t esz = 4, cg = (cuuint64_t)t.cg;
-    FFCB_REQUIRE(((uintptr_t)t.ptr % 16) == 0 && (t.sg * esz) % 16 == 0 && (t.sb * esz) % 16 == 0 && (t.sy * esz) % 16 == 0,
-                 "conv(tc): planar out strides / pointer not 16-byte aligned");
-    if (flat) {
-      FFCB_REQUIRE(t.sx == t.cg && t.sy == (int64_t)W * t.sx && t.sb == (int64_t)H * t.sy,
-                   "conv(tc): a flat contraction needs a dense planar output");
-      cuuint64_t dims[3] = {cg, (cuuint64_t)t.B * t.H * t.W, (cuuint64_t)t.C / cg};
-      cuuint64_t str[2] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.sg * esz};
-      cuuint32_t box[3] = {(cuuint32_t)cg, 32, (cuuint32_t)(32 / cg)}, es[3] = {1, 1, 1};
-      if ((rc = encode_typed(&maps[3], t.ptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE, 3, dims, str,
-                             box, es, "flat planar output")))
-        return rc;
-    } else {
-      cuuint64_t dims[5] = {cg, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)t.B, (cuuint64_t)t.C / cg};
-      cuuint64_t str[4] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.sy * esz, (cuuint64_t)t.sb * esz, (cuuint64_t)t.sg * esz};
-      cuuint32_t box[5] = {(cuuint32_t)cg, (cuuint32_t)p.obw, (cuuint32_t)p.obh, 1, (cuuint32_t)(32 / cg)};
-      cuuint32_t es[5] = {1, 1, 1, 1, 1};
-      if ((rc = encode_typed(&maps[3], t.ptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE, 5, dims, str,
-                             box, es, "spatial planar output")))
-        return rc;
-    }
+    maps[3] = maps[2];                                   // planar outputs are stored with plain vector stores
   } else {
     // output: fp32 rows of 128 B (SWIZZLE_128B) or split bf16 rows of 64 B per plane (SWIZZLE_64B)
     const ffcb_tensor& t = d->out;
@@ -835,16 +805,20 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   FFCB_REQUIRE(stages >= 2, "conv(tc): BN=%d leaves fewer than 2 pipeline stages", p.BN);
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + bar_bytes + 1024;
-  const bool any_il = p.a_il[0] || p.a_il[1];
-  FFCB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  FFCB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   int dev = 0, sms = 148;
   FFCB_CUDA(cudaGetDevice(&dev));
   FFCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  if (any_il) conv_tc_kernel<true><<<grid, kThreads, smem, stream>>>(p, maps[0], maps[1], maps[2], maps[3]);
-  else conv_tc_kernel<false><<<grid, kThreads, smem, stream>>>(p, maps[0], maps[1], maps[2], maps[3]);
+  const bool any_il = p.a_il[0] || p.a_il[1];
+  auto launch = [&](auto kernel) -> int {
+    FFCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    kernel<<<grid, kThreads, smem, stream>>>(p, maps[0], maps[1], maps[2], maps[3]);
+    return FFCB_OK;
+  };
+  if (any_il) rc = p.out_planar ? launch(conv_tc_kernel<true, true>) : launch(conv_tc_kernel<true, false>);
+  else rc = p.out_planar ? launch(conv_tc_kernel<false, true>) : launch(conv_tc_kernel<false, false>);
+  if (rc) return rc;
   FFCB_LAUNCH_CHECK("conv_tc_kernel");
   return FFCB_OK;
 }

@@ -29,6 +29,8 @@ struct CgArgs {
   void* out;        long long out_sg, out_sb; unsigned out_sy, out_sx; long long out_lo;
   float scale;
   int hints;      // L2 residency hints on (common.cuh: l2_policy)
+  int sp_tiled;   // forward: the spectrum is tile-blocked (ffcb_tensor.tile = 128): sp_sg = elements per 128-position block
+  int out_tiled;  // inverse: the split-bf16 output is tile-blocked: out_sg = elements per 128-pixel block
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,6 +113,10 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) rfft2_plane
     const uint64_t pol_sp = l2_policy(a.hints ? 2 : 0);     // the spectrum is the next kernel's GEMM operand: keep it in L2
     int ky, kx;
     cg_spec_pos0<N>(tid, ky, kx);
+    // tile-blocked spectrum (the GEMM operand layout): position m = b * N*WF + p of the flattened batch lives at
+    // (m / 128) * sp_sg + group * 1024 + (m % 128) * 8 — consecutive positions stay consecutive inside a block
+    unsigned short* tbase = reinterpret_cast<unsigned short*>(a.spec) + (long long)group * 1024;
+    long long m = (long long)blockIdx.y * Cfg::positions + tid;
 #pragma unroll 1
     for (int i = 0; i < Cfg::pos_iters; ++i) {
       if (ky < N) {
@@ -124,11 +130,13 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) rfft2_plane
         split_pair(z1.x, z1.y, h.y, l.y);
         split_pair(z2.x, z2.y, h.z, l.z);
         split_pair(z3.x, z3.y, h.w, l.w);
-        unsigned short* dst = hi + ((unsigned)ky * sp_sy + (unsigned)kx * sp_sx);
+        unsigned short* dst = a.sp_tiled ? tbase + ((m >> 7) * a.sp_sg + (m & 127) * 8)
+                                         : hi + ((unsigned)ky * sp_sy + (unsigned)kx * sp_sx);
         st_hint_u4(dst, h, pol_sp);
         st_hint_u4(dst + a.sp_lo, l, pol_sp);
       }
       cg_spec_pos_next<N>(ky, kx);
+      m += Cfg::set_threads;
     }
   }
 }
@@ -192,14 +200,20 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) irfft2_plan
         const float r2 = fmaf(v.z, scale, q[j].z), r3 = fmaf(v.w, scale, q[j].w);
         if constexpr (OUT_SPLIT) {
           // out is cg = 8: this plane set's four channels are one half (8 bytes per plane) of the 16-byte pixel granule
-          unsigned short* hi = reinterpret_cast<unsigned short*>(a.out) + (long long)(group >> 1) * a.out_sg +
-                               (long long)blockIdx.y * a.out_sb + 4 * (group & 1);
-          const unsigned o = (unsigned)y * out_sy + (unsigned)x * out_sx;
+          unsigned short* hi;
+          if (a.out_tiled) {     // pixel m of the flattened batch: (m / 128) * out_sg + (group / 2) * 1024 + (m % 128) * 8
+            const long long m = ((long long)blockIdx.y * N + y) * N + x;
+            hi = reinterpret_cast<unsigned short*>(a.out) + ((m >> 7) * a.out_sg + (long long)(group >> 1) * 1024 +
+                                                               (m & 127) * 8 + 4 * (group & 1));
+          } else {
+            hi = reinterpret_cast<unsigned short*>(a.out) + (long long)(group >> 1) * a.out_sg +
+                 (long long)blockIdx.y * a.out_sb + 4 * (group & 1) + ((unsigned)y * out_sy + (unsigned)x * out_sx);
+          }
           unsigned h0, l0, h1, l1;
           split_pair(r0, r1, h0, l0);
           split_pair(r2, r3, h1, l1);
-          st_hint_v2(hi + o, make_uint2(h0, h1), pol_out);
-          st_hint_v2(hi + a.out_lo + o, make_uint2(l0, l1), pol_out);
+          st_hint_v2(hi, make_uint2(h0, h1), pol_out);
+          st_hint_v2(hi + a.out_lo, make_uint2(l0, l1), pol_out);
         } else {
           float* op = reinterpret_cast<float*>(a.out) + (long long)group * a.out_sg +
                       (long long)blockIdx.y * a.out_sb + ((unsigned)y * out_sy + (unsigned)x * out_sx);
@@ -224,9 +238,11 @@ bool real_cg4(const ffcb_tensor* t) {
 
 // Do these views take the channel-group planar plane kernels?  (Anything with cg != 0 must: there is no other path.)
 bool plane64_cg_fwd_eligible(const ffcb_tensor* in, const ffcb_tensor* spec) {
-  return real_cg4(in) && spec->cg == 8 && spec->fmt == FFCB_BF16X2 && spec->sx % 2 == 0 && spec->sy % 2 == 0 &&
-         spec->sb % 2 == 0 && spec->sg % 2 == 0 && spec->lo_off % 2 == 0 && ((uintptr_t)spec->ptr % 4) == 0 &&
-         offsets_fit(spec);
+  if (!(real_cg4(in) && spec->cg == 8 && spec->fmt == FFCB_BF16X2 && spec->lo_off % 8 == 0 &&
+        ((uintptr_t)spec->ptr % 16) == 0))
+    return false;
+  if (spec->tile) return spec->tile == 128 && spec->sg % 8 == 0;
+  return spec->sx % 8 == 0 && spec->sy % 8 == 0 && spec->sb % 8 == 0 && spec->sg % 8 == 0 && offsets_fit(spec);
 }
 
 bool plane64_cg_inv_eligible(const ffcb_tensor* spec, const ffcb_tensor* residual, const ffcb_tensor* out) {
@@ -235,9 +251,11 @@ bool plane64_cg_inv_eligible(const ffcb_tensor* spec, const ffcb_tensor* residua
         out->B <= 65535))
     return false;
   if (residual && residual->ptr && !real_cg4(residual)) return false;
-  if (out->fmt == FFCB_BF16X2)
-    return out->cg == 8 && out->sx % 4 == 0 && out->sy % 4 == 0 && out->sb % 4 == 0 && out->sg % 4 == 0 &&
-           out->lo_off % 4 == 0 && ((uintptr_t)out->ptr % 8) == 0 && offsets_fit(out) && out->C % 8 == 0;
+  if (out->fmt == FFCB_BF16X2) {
+    if (!(out->cg == 8 && out->lo_off % 4 == 0 && ((uintptr_t)out->ptr % 8) == 0 && out->C % 8 == 0)) return false;
+    if (out->tile) return out->tile == 128 && out->sg % 4 == 0;
+    return out->sx % 4 == 0 && out->sy % 4 == 0 && out->sb % 4 == 0 && out->sg % 4 == 0 && offsets_fit(out);
+  }
   return real_cg4(out);
 }
 
@@ -260,9 +278,10 @@ int rfft2_plane64_cg(const ffcb_tensor* in, const ffcb_tensor* spec, cudaStream_
   a.in_sg = in->sg; a.in_sb = in->sb; a.in_sy = (unsigned)in->sy; a.in_sx = (unsigned)in->sx;
   a.spec = spec->ptr; a.sp_sg = spec->sg; a.sp_sb = spec->sb; a.sp_sy = (unsigned)spec->sy; a.sp_sx = (unsigned)spec->sx;
   a.sp_lo = spec->lo_off;
+  a.sp_tiled = spec->tile != 0;
   a.scale = 1.0f / (float)in->H;
   a.hints = l2_hints_enabled() ? 1 : 0;
-  const bool dense = dense_real(in, 4) && dense_real(spec, 8);
+  const bool dense = dense_real(in, 4) && (spec->tile != 0 || dense_real(spec, 8));
   if (in->H == 64)
     return dense ? launch_fwd_cg<64, true>(a, in->C / 4, in->B, stream) : launch_fwd_cg<64, false>(a, in->C / 4, in->B, stream);
   return dense ? launch_fwd_cg<32, true>(a, in->C / 4, in->B, stream) : launch_fwd_cg<32, false>(a, in->C / 4, in->B, stream);
@@ -299,10 +318,12 @@ int irfft2_plane64_cg(const ffcb_tensor* spec, const ffcb_tensor* residual, cons
   a.spec = spec->ptr; a.sp_sg = spec->sg; a.sp_sb = spec->sb; a.sp_sy = (unsigned)spec->sy; a.sp_sx = (unsigned)spec->sx;
   a.out = out->ptr; a.out_sg = out->sg; a.out_sb = out->sb; a.out_sy = (unsigned)out->sy; a.out_sx = (unsigned)out->sx;
   a.out_lo = out->lo_off;
+  a.out_tiled = out->tile != 0;
   a.scale = 1.0f / (float)out->H;
   a.hints = l2_hints_enabled() ? 1 : 0;
   const bool split = out->fmt == FFCB_BF16X2;
-  const bool dense = dense_real(spec, 8) && dense_real(out, split ? 8 : 4) && (!has_res || dense_real(residual, 4));
+  const bool dense = dense_real(spec, 8) && (out->tile != 0 || dense_real(out, split ? 8 : 4)) &&
+                     (!has_res || dense_real(residual, 4));
   if (out->H == 64)
     return dense ? dispatch_inv_cg<64, true>(a, out->C / 4, out->B, has_res, split, stream)
                  : dispatch_inv_cg<64, false>(a, out->C / 4, out->B, has_res, split, stream);

@@ -19,10 +19,10 @@ namespace {
 
 // generic 4-channel access that also understands channel-group planar views
 __device__ __forceinline__ float4 load4g(const View& v, int b, int y, int x, int c) {
-  return load4(v, pix_off(v, b, y, x) + chan_off(v, c));
+  return load4(v, elem_off(v, b, y, x, c));
 }
 __device__ __forceinline__ void store4g(const View& v, int b, int y, int x, int c, float4 r) {
-  store4(v, pix_off(v, b, y, x) + chan_off(v, c), r);
+  store4(v, elem_off(v, b, y, x, c), r);
 }
 
 __global__ void relu_bwd_kernel(View dy, View y, View out) {

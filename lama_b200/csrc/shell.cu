@@ -276,7 +276,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, int H, i
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
       const int xx = x0 + i, c = c0 + threadIdx.x;
-      if (xx < W && c < C) store1(out, pix_off(out, b, y, xx) + chan_off(out, c), tile[threadIdx.x][i]);
+      if (xx < W && c < C) store1(out, elem_off(out, b, y, xx, c), tile[threadIdx.x][i]);
     }
     __syncthreads();
   }
@@ -290,7 +290,7 @@ __global__ void nhwc_to_nchw_kernel(View in, float* __restrict__ yo) {
     const int b = z / H, y = z % H;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
       const int xx = x0 + i, c = c0 + threadIdx.x;
-      tile[i][threadIdx.x] = (xx < W && c < C) ? load1(in, pix_off(in, b, y, xx) + chan_off(in, c)) : 0.f;
+      tile[i][threadIdx.x] = (xx < W && c < C) ? load1(in, elem_off(in, b, y, xx, c)) : 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {

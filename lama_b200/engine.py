@@ -48,6 +48,7 @@ class Buf:
     fmt: int = L.F32
     reflect_border: int = 0
     cg: int = 0        # > 0: channel-group planar storage [C/cg][B][H][W][cg] (FourierUnit chain, include/ffc_b200.h)
+    tile: int = 0      # 128 (with cg == 8, split bf16): tile-blocked [pixel block of 128][C/8][128][8] — tcgen05 operand tiles
 
 
 @dataclass
@@ -233,8 +234,10 @@ class Program:
         tc = self.math == L.MATH_BF16X3 and gemm
         ring = halo_px if (tc and halo) else 0
         assert not (cg and ring) and (cg == 0 or C % cg == 0)
+        # channel-group planar contraction operands are tile-blocked: one contiguous 16 KB run per (M tile, K block, plane)
+        tile = 128 if (cg == 8 and tc) else 0
         b = Buf(f"{name}#{len(self.bufs)}", B, H, W, C, pad=ring, fmt=L.BF16X2 if tc else L.F32,
-                reflect_border=1 if ring else 0, cg=cg)
+                reflect_border=1 if ring else 0, cg=cg, tile=tile)
         self.bufs.append(b)
         return b
 
@@ -552,6 +555,8 @@ def emit_fourier_unit(prog: Program, fu, t: TV, out: TV, residual: Optional[TV])
     cin2 = wconv.shape[1]
     pk = P.pack_conv([(wconv, 0, 0, 0)], scale, shift, act=L.ACT_RELU, device=fu.conv_layer.weight.device)
     chunk = fu_batch_chunk(b, h, w, cin2 // 2) if prog.math == L.MATH_BF16X3 else b
+    if planar and ((chunk * h * wf) % 128 or (chunk * h * w) % 128):
+        chunk = b          # tile-blocked buffers can only be sliced on 128-pixel blocks
     for b0 in range(0, b, chunk):
         nb = min(chunk, b - b0)
         prog.ops.append(RfftOp(t.bslice(b0, nb), TV(S).bslice(b0, nb)))
@@ -990,6 +995,8 @@ class CudaExecutor:
             shape = (b.B, b.H + 2 * b.pad, b.W + 2 * b.pad, b.C)
             if b.cg:
                 shape = (b.C // b.cg, b.B, b.H, b.W, b.cg)
+            if b.tile:
+                shape = (-(-(b.B * b.H * b.W) // 128), b.C // 8, 128, 8)      # zero-initialised: the tail block stays finite
             if b.fmt == L.F32:
                 self.storage[b.name] = torch.empty(shape, dtype=torch.float32, device=device)
             else:
@@ -1016,6 +1023,21 @@ class CudaExecutor:
         b = tv.buf
         st = self.storage[b.name]
         es = 4 if b.fmt == L.F32 else 2
+        if b.tile:
+            assert (tv.phase is None and not tv.window and tv.win is None and b.pad == 0 and tv.c0 % 8 == 0
+                    and tv.channels % 8 == 0)
+            m0 = tv.b0 * b.H * b.W
+            if m0 % 128:
+                raise ValueError("a batch slice of a tile-blocked buffer must start on a 128-pixel block")
+            t = L.Tensor()
+            nblk, groups = -(-(b.B * b.H * b.W) // 128), b.C // 8
+            t.cg, t.tile, t.sg = 8, 128, groups * 1024
+            t.sx, t.sy, t.sb = 8, b.W * 8, b.H * b.W * 8
+            t.lo_off = nblk * groups * 1024
+            t.ptr = st.data_ptr() + ((tv.c0 // 8) * 1024 + (m0 // 128) * t.sg) * es
+            t.B, t.H, t.W, t.C = tv.batch, b.H, b.W, tv.channels
+            t.fmt, t.pad, t.reflect_border = b.fmt, 0, 0
+            return t
         if b.cg:
             assert tv.phase is None and not tv.window and b.pad == 0 and tv.c0 % b.cg == 0 and tv.channels % b.cg == 0
             t = L.Tensor()
