@@ -47,14 +47,19 @@ def _peaks():
 
 def _ncu_traffic(prefix):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-    (profiles/r01_traffic.json, bs32 512x512); None if the capture is not there."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if not os.path.isfile(p):
-        return None
-    with open(p) as fh:
-        for k, v in json.load(fh).items():
-            if k.startswith(prefix):
-                return v
+    (profiles/r02_traffic.json, bs32 512x512, written by tools/ncu_traffic.py; kernels that did not change since
+    round 1 fall back to profiles/r01_traffic.json); None if neither capture holds the kernel."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if not os.path.isfile(p):
+            continue
+        with open(p) as fh:
+            for k, v in json.load(fh).items():
+                if k.startswith(prefix):
+                    if isinstance(v, list):                       # ncu_traffic.py: one record per captured launch
+                        vals = [e["dram_bytes"] for e in v if "dram_bytes" in e]
+                        return sum(vals) / len(vals) if vals else None
+                    return v
     return None
 
 

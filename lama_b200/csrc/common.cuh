@@ -181,6 +181,11 @@ __device__ __forceinline__ void st_hint_f4(void* p, float4 v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w), "l"(pol) : "memory");
 }
+// 32-byte store (sm_100: STG.256): one whole sector per lane
+__device__ __forceinline__ void st_hint_f8(void* p, const float* v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(p), "f"(v[0]),
+               "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(pol) : "memory");
+}
 __device__ __forceinline__ float2 ld_hint_f2(const void* p, uint64_t pol) {
   float2 v;
   asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));

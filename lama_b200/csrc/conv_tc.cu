@@ -507,12 +507,20 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           if (valid && !(p.debug & 1)) {
             float* ob = reinterpret_cast<float*>(p.out.ptr) + pix_off(p.out, b, y, x);
             const uint64_t pol = l2_policy(p.hints ? 2 : 0);       // consumed by the next kernel of the chain
+            if (p.out.cg == 8) {                                     // 32 B per lane and group: whole sectors
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int n = n0 + 4 * q;
-              if (n < p.N)
-                st_hint_f4(ob + (long long)(n / p.out.cg) * p.out.sg + (n % p.out.cg),
-                           make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), pol);
+              for (int q = 0; q < 4; ++q) {
+                const int n = n0 + 8 * q;
+                if (n < p.N) st_hint_f8(ob + (long long)(n >> 3) * p.out.sg, v + 8 * q, pol);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int n = n0 + 4 * q;
+                if (n < p.N)
+                  st_hint_f4(ob + (long long)(n >> 2) * p.out.sg,
+                             make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), pol);
+              }
             }
           }
           continue;
@@ -668,6 +676,10 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   if (d->out.cg != 0)
     FFCB_REQUIRE(d->out.fmt == FFCB_F32 && d->out.sx % 4 == 0 && d->out.sy % 4 == 0 && d->out.sb % 4 == 0,
                  "conv(tc): channel-group planar outputs are float32");
+  if (d->out.cg == 8)     // 32-byte stores
+    FFCB_REQUIRE(d->out.sx % 8 == 0 && d->out.sy % 8 == 0 && d->out.sb % 8 == 0 && d->out.sg % 8 == 0 &&
+                     (reinterpret_cast<uintptr_t>(d->out.ptr) & 31) == 0,
+                 "conv(tc): cg = 8 planar output needs 32-byte aligned pixels");
   {
     const char* sw = getenv("FFCB_TC_DESC_SWAP");
     p.desc_swap = sw ? atoi(sw) : 0;

@@ -46,6 +46,17 @@ def time_call(i, reps=20):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
+if os.environ.get("ONCE"):
+    # one launch of each op inside a cudaProfilerStart/Stop range: `ncu --profile-from-start off --set full ...`
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    for w in want:
+        n, fn, a = ex.calls[idx[w]]
+        assert fn(*a, stream) == 0
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    print("once:", [names[idx[w]] for w in want])
+    sys.exit(0)
 if os.environ.get("SWEEP_BN"):
     print("N-tile sweep (FFCB_TC_BN), us per launch")
     for w in want[:4]:
