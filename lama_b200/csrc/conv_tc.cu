@@ -159,6 +159,24 @@ __device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t saddr, int swap
   return d;
 }
 
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN.
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -309,8 +327,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   const long long num_tiles = p.num_m_tiles * p.num_n_tiles;
 
   if (warp == 0) {
-    // ================================================================ TMA producer (one lane)
-    if (lane == 0) {
+    // ================================================================ TMA producer (uniform control flow, one elected lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -328,6 +346,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           const int il = IL ? p.a_il[g.src] : 0;
           for (int j = 0; j < nblk; ++j, ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one()) {
             uint8_t* st = smem + (size_t)stage * stage_bytes;
             const bool skip_a = (p.debug & 8) != 0;
             mbar_expect_tx(&full[stage], (uint32_t)(skip_a ? 2 * w_bytes : stage_bytes));
@@ -349,15 +368,26 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
             }
             tma_load_3d(st + 2 * kTileABytes, &map_w, &full[stage], kb * BK, n_tile * p.BN, 0);
             tma_load_3d(st + 2 * kTileABytes + w_bytes, &map_w, &full[stage], kb * BK, n_tile * p.BN, 1);
+            }
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (one lane)
-    if (lane == 0) {
+    // ================================================================ MMA issuer
+    // All 32 lanes walk the pipeline (uniform control flow, every lane polls the barriers); ONE lane chosen by
+    // `elect.sync` issues the MMAs and commits.  Under a plain `if (lane == 0)` the compiler treats the block as
+    // divergent and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (9 instructions and two
+    // branches per 64-cycle MMA: the issuer, not the tensor pipe, set the pace); here each MMA is one uniform add
+    // plus the UTCHMMA.  Descriptors are (lo, hi) 32-bit pairs: advancing along K only touches the 14-bit
+    // start-address field of the low word.
+    {
       const uint32_t idesc = make_idesc(p.BN);
+      constexpr uint32_t kHiSw = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);          // SBO 1024, v1, SWIZZLE_128B
+      const uint32_t hi_il = (uint32_t)((p.desc_swap ? 2048 : 128) >> 4) | (1u << 14);     // SBO, v1, no swizzle
+      const uint32_t lbo_il = (uint32_t)((p.desc_swap ? 128 : 2048) >> 4) << 16;           // LBO (low word)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -366,53 +396,36 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
-        if constexpr (!IL) {
-          for (int kb = 0; kb < total_kblocks; ++kb) {
+        int kb = 0;
+        for (int sgi = 0; sgi < (IL ? p.nseg : 1); ++sgi) {
+          const bool il = IL && p.a_il[p.seg[sgi].src] != 0;
+          const int nblk = IL ? (p.seg[sgi].nch + BK - 1) / BK : total_kblocks;
+          const uint32_t a_hiword = il ? hi_il : kHiSw;
+          const uint32_t a_lbo = il ? lbo_il : 0u;
+          const uint32_t a_step = il ? (uint32_t)(4096 >> 4) : (uint32_t)((UMMA_K * 2) >> 4);
+          for (int j = 0; j < nblk; ++j, ++kb) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
-            const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint64_t a_hi = make_smem_desc(st);
-            const uint64_t a_lo = make_smem_desc(st + kTileABytes);
-            const uint64_t w_hi = make_smem_desc(st + 2 * kTileABytes);
-            const uint64_t w_lo = make_smem_desc(st + 2 * kTileABytes + w_bytes);
-#pragma unroll
-            for (int k = 0; k < ((p.debug & 4) ? 0 : BK / UMMA_K); ++k) {
-              const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per UMMA_K inside the swizzle row
-              umma_bf16(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
-              umma_bf16(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
-              umma_bf16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
-            }
-            umma_commit(&empty[stage]);                 // smem stage reusable once these MMAs retire
-            if (kb == total_kblocks - 1) umma_commit(&acc_full[acc]);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          }
-        } else {
-          int kb = 0;
-          for (int sgi = 0; sgi < p.nseg; ++sgi) {
-            const int il = p.a_il[p.seg[sgi].src];
-            const int nblk = (p.seg[sgi].nch + BK - 1) / BK;
-            for (int j = 0; j < nblk; ++j, ++kb) {
-              mbar_wait(&full[stage], phase);
-              tc_fence_after();
+            if (elect_one()) {
               const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
-              const uint64_t a_hi = il ? make_smem_desc_nosw(st, p.desc_swap) : make_smem_desc(st);
-              const uint64_t a_lo = il ? make_smem_desc_nosw(st + kTileABytes, p.desc_swap) : make_smem_desc(st + kTileABytes);
-              const uint64_t w_hi = make_smem_desc(st + 2 * kTileABytes);
-              const uint64_t w_lo = make_smem_desc(st + 2 * kTileABytes + w_bytes);
-              // per UMMA_K = 16 step: +32 B inside the swizzle row, or two 2048-byte slabs of the interleaved tile
-              const uint64_t a_step = il ? (uint64_t)(4096 >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
+              const uint32_t a_hi = ((st & 0x3FFFF) >> 4) | a_lbo;
+              const uint32_t a_lo = (((st + kTileABytes) & 0x3FFFF) >> 4) | a_lbo;
+              const uint32_t w_hi = ((st + 2 * kTileABytes) & 0x3FFFF) >> 4;
+              const uint32_t w_lo = ((st + 2 * kTileABytes + w_bytes) & 0x3FFFF) >> 4;
 #pragma unroll
-              for (int k = 0; k < ((p.debug & 4) ? 0 : BK / UMMA_K); ++k) {
-                const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-                const uint64_t aadv = (uint64_t)k * a_step;
-                umma_bf16(d_tmem, a_hi + aadv, w_hi + adv, idesc, (kb | k) != 0);
-                umma_bf16(d_tmem, a_lo + aadv, w_hi + adv, idesc, 1);
-                umma_bf16(d_tmem, a_hi + aadv, w_lo + adv, idesc, 1);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                if (p.debug & 4) break;
+                const uint32_t wadv = (uint32_t)((k * UMMA_K * 2) >> 4);     // +32 B per UMMA_K inside the swizzle row
+                const uint32_t aadv = (uint32_t)k * a_step;                  // same, or two 2048-byte slabs (interleaved)
+                umma_bf16(d_tmem, desc64(a_hi + aadv, a_hiword), desc64(w_hi + wadv, kHiSw), idesc, (kb | k) != 0);
+                umma_bf16(d_tmem, desc64(a_lo + aadv, a_hiword), desc64(w_hi + wadv, kHiSw), idesc, 1);
+                umma_bf16(d_tmem, desc64(a_hi + aadv, a_hiword), desc64(w_lo + wadv, kHiSw), idesc, 1);
               }
               umma_commit(&empty[stage]);                 // smem stage reusable once these MMAs retire
               if (kb == total_kblocks - 1) umma_commit(&acc_full[acc]);
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
