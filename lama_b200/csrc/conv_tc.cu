@@ -539,7 +539,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           continue;
         }
         // the previous TMA store of this warp must have finished reading the staging tile
-        if (lane == 0) tma_store_wait_read();
+        if (elect_one()) tma_store_wait_read();     // (elect.sync is deterministic: always the lane that committed)
         __syncwarp();
         if (out_split) {
           // [plane][32 rows][32 bf16] = 64-byte rows, TMA SWIZZLE_64B: 16-byte chunk c of row r lives at c ^ ((r>>1)&3)
@@ -569,7 +569,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0 && !(p.debug & 1)) {
+        if (!(p.debug & 1) && elect_one()) {
           if (p.flat) tma_store_3d(&map_out, stg, n0, (int)tc.m0 + wq * 32, 0);
           else tma_store_5d(&map_out, stg, n0, box_x, box_y, tc.b, 0);
           tma_store_commit();
@@ -579,7 +579,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       mbar_arrive(&acc_empty[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
-    if (lane == 0) tma_store_wait_all();
+    if (elect_one()) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -835,7 +835,7 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   FFCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  const bool any_il = p.a_il[0] || p.a_il[1];
+  const bool any_il = p.a_il[0] || p.a_il[1] || getenv("FFCB_TC_FORCE_IL") != nullptr;   // (knob: A/B of the two instantiations)
   auto launch = [&](auto kernel) -> int {
     FFCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     kernel<<<grid, kThreads, smem, stream>>>(p, maps[0], maps[1], maps[2], maps[3]);
