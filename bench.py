@@ -225,8 +225,25 @@ def torch_cuda_baseline(dev, B, S, steps=5, warmup=3):
                 e1.record()
                 torch.cuda.synchronize(dev)
             out[name]["ours_module_call_ms"] = e0.elapsed_time(e1) / steps
+            # same call in a serving loop that never touches the weights (LAMA_B200_TRUST_WEIGHTS=1: no per-call content
+            # checksum of the weights, i.e. no host<->device round trip inside the call)
+            os.environ["LAMA_B200_TRUST_WEIGHTS"] = "1"
+            try:
+                with torch.no_grad():
+                    for _ in range(warmup):
+                        fn()
+                    torch.cuda.synchronize(dev)
+                    e0.record()
+                    for _ in range(steps):
+                        fn()
+                    e1.record()
+                    torch.cuda.synchronize(dev)
+                out[name]["ours_module_call_trusted_weights_ms"] = e0.elapsed_time(e1) / steps
+            finally:
+                os.environ.pop("LAMA_B200_TRUST_WEIGHTS", None)
         out["note_ours"] = ("ours_module_call_ms = the drop-in module called like the reference module (NCHW float in / out, "
-                            "layout conversion + weight checksum inside the call)")
+                            "layout conversion + weight content checksum — one device->host scalar read — inside the "
+                            "call); ..._trusted_weights_ms = same with LAMA_B200_TRUST_WEIGHTS=1")
     except Exception as ex_o:  # noqa: BLE001
         out["ours_error"] = f"{type(ex_o).__name__}: {ex_o}"[:300]
     return out

@@ -31,19 +31,7 @@ struct CgArgs {
   int hints;      // L2 residency hints on (common.cuh: l2_policy)
   int sp_tiled;   // forward: the spectrum is tile-blocked (ffcb_tensor.tile = 128): sp_sg = elements per 128-position block
   int out_tiled;  // inverse: the split-bf16 output is tile-blocked: out_sg = elements per 128-pixel block
-  int lookahead;  // > 0 (dense tensors): prefetch the streamed input of the CTA `lookahead` blocks ahead into L2
 };
-
-__device__ __forceinline__ void l2_prefetch_block(const void* p, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-// block that will take this CTA's slot about one wave later (launch order is x-major)
-__device__ __forceinline__ bool lookahead_block(int lookahead, unsigned& bx, unsigned& by) {
-  const unsigned next = blockIdx.y * gridDim.x + blockIdx.x + (unsigned)lookahead;
-  bx = next % gridDim.x;
-  by = next / gridDim.x;
-  return lookahead > 0 && by < gridDim.y;
-}
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -76,12 +64,6 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) rfft2_plane
   const int group = blockIdx.x * Cfg::sets + set;
   float* smem = smem_all + set * Cfg::set_floats;
   float2* S = reinterpret_cast<float2*>(smem);
-  if constexpr (DENSE) {
-    // the kernel is latency-bound (12 warps per SM): warm L2 with the plane set of the CTA one wave ahead
-    unsigned nbx, nby;
-    if (tid == 0 && lookahead_block(a.lookahead, nbx, nby))
-      l2_prefetch_block(a.in + (long long)(nbx * Cfg::sets + set) * a.in_sg + (long long)nby * a.in_sb, 4u * N * N * 4u);
-  }
   {   // plane set -> shared memory (real layout), 16 bytes per pixel, lanes along x
     const float* src = a.in + (long long)group * a.in_sg + (long long)blockIdx.y * a.in_sb;
     const uint32_t base = smem_addr(smem);
@@ -172,17 +154,6 @@ __global__ void __launch_bounds__(kCgThreads, CgCfg<N>::ctas_per_sm) irfft2_plan
   const int group = blockIdx.x * Cfg::sets + set;
   float* smem = smem_all + set * Cfg::set_floats;
   float2* S = reinterpret_cast<float2*>(smem);
-  if constexpr (HAS_RES && DENSE) {
-    // the residual plane set (one dense block) is only needed by the epilogue: pull it into L2 now, so that the
-    // epilogue's eight load batches see L2 latency instead of DRAM latency (the kernel is latency-bound at 12 warps/SM)
-    if (tid == 0) l2_prefetch_block(a.in + (long long)group * a.in_sg + (long long)blockIdx.y * a.in_sb, 4u * N * N * 4u);
-  }
-  if constexpr (DENSE) {     // ... and the spectrum of the CTA one wave ahead
-    unsigned nbx, nby;
-    if (tid == 0 && lookahead_block(a.lookahead, nbx, nby))
-      l2_prefetch_block(reinterpret_cast<const float*>(a.spec) + (long long)(nbx * Cfg::sets + set) * a.sp_sg +
-                            (long long)nby * a.sp_sb, 8u * WF * N * 4u);
-  }
   {
     const float* sp = reinterpret_cast<const float*>(a.spec) + (long long)group * a.sp_sg +
                       (long long)blockIdx.y * a.sp_sb + 2 * (tid & 3);
@@ -288,30 +259,13 @@ bool plane64_cg_inv_eligible(const ffcb_tensor* spec, const ffcb_tensor* residua
   return real_cg4(out);
 }
 
-// CTAs resident on the device at once = distance (in launch order) to the block that inherits this CTA's slot.
-// FFCB_FFT_PREFETCH=0 switches the L2 look-ahead off (A/B measurements).
-static int cg_lookahead(int ctas_per_sm) {
-  static int sms = -1;
-  if (sms < 0) {
-    const char* e = getenv("FFCB_FFT_PREFETCH");
-    int dev = 0, n = 0;
-    if ((e && atoi(e) == 0) || cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      n = 0;
-    sms = n;
-  }
-  return sms * ctas_per_sm;
-}
-
 template <int N, bool DENSE>
 static int launch_fwd_cg(const CgArgs& a, int groups, int batch, cudaStream_t stream) {
   using Cfg = CgCfg<N>;
   FFCB_CUDA(cudaFuncSetAttribute(rfft2_plane_cg_kernel<N, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::fwd_smem_bytes));
   dim3 grid(groups / Cfg::sets, batch);
-  CgArgs b = a;
-  b.lookahead = cg_lookahead(Cfg::ctas_per_sm);
-  rfft2_plane_cg_kernel<N, DENSE><<<grid, kCgThreads, Cfg::fwd_smem_bytes, stream>>>(b);
+  rfft2_plane_cg_kernel<N, DENSE><<<grid, kCgThreads, Cfg::fwd_smem_bytes, stream>>>(a);
   FFCB_LAUNCH_CHECK("rfft2_plane_cg_kernel");
   return FFCB_OK;
 }
@@ -339,9 +293,7 @@ static int launch_inv_cg(const CgArgs& a, int groups, int batch, cudaStream_t st
   FFCB_CUDA(cudaFuncSetAttribute(irfft2_plane_cg_kernel<N, HAS_RES, OUT_SPLIT, DENSE>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes));
   dim3 grid(groups / Cfg::sets, batch);
-  CgArgs b = a;
-  b.lookahead = cg_lookahead(Cfg::ctas_per_sm);
-  irfft2_plane_cg_kernel<N, HAS_RES, OUT_SPLIT, DENSE><<<grid, kCgThreads, Cfg::smem_bytes, stream>>>(b);
+  irfft2_plane_cg_kernel<N, HAS_RES, OUT_SPLIT, DENSE><<<grid, kCgThreads, Cfg::smem_bytes, stream>>>(a);
   FFCB_LAUNCH_CHECK("irfft2_plane_cg_kernel");
   return FFCB_OK;
 }

@@ -981,6 +981,71 @@ def insert_border_ops(prog: Program):
 
 
 # ------------------------------------------------------------------------------------- executor
+def op_views(op) -> Tuple[List[TV], List[TV]]:
+    """(views read, views written) by one op of a program — the basis of the buffer liveness analysis."""
+    if isinstance(op, (ToNHWC, StemOp, StemPackOp, StemPackU8Op)):
+        return [], [op.out]
+    if isinstance(op, (ToNCHW, HeadOp)):
+        return [op.inp], []
+    if isinstance(op, (HeadGatherOp, HeadGatherU8Op)):
+        return [op.q], []
+    if isinstance(op, ConvOp):
+        return [t for t in op.ins if t is not None] + ([op.addend] if op.addend is not None else []), [op.out]
+    if isinstance(op, RfftOp):
+        return [op.inp], [op.spec]
+    if isinstance(op, IrfftOp):
+        return [op.spec] + ([op.residual] if op.residual is not None else []), [op.out]
+    if isinstance(op, BorderOp):
+        return [op.view], [op.view]
+    if isinstance(op, ReluBwdOp):
+        return [op.dy, op.y], [op.out]
+    if isinstance(op, FoldOp):
+        return [op.gpad] + [tv for tv, _c0 in op.addends], [op.out]
+    if isinstance(op, SplitOp):
+        return [], []
+    raise TypeError(op)
+
+
+def storage_key(b: Buf) -> tuple:
+    """Buffers with equal keys have byte-identical storage (dtype, shape, ring, layout)."""
+    return (b.fmt, b.B, b.H, b.W, b.C, b.pad, b.reflect_border, b.cg, b.tile)
+
+
+def assign_storage_slots(prog: Program) -> Dict[str, int]:
+    """Buffer name -> storage slot.  A program is a straight-line op list on one stream, so a buffer is dead after
+    the last op that touches it and its storage can back a later buffer.  Only buffers with IDENTICAL storage
+    (``storage_key``) share a slot: whatever a kernel leaves unwritten (zero-initialised pixel / channel padding, the
+    reflected ring before its producer ran) then holds what the same kind of buffer held there before, never foreign
+    bits.  For big-lama this folds the 18 residual blocks' ~150 buffers onto two blocks' worth: 28 GB -> 10 GB at bs32
+    512x512, and bs64 1024x1024 (BASELINE config 4 on one GPU) fits a 180 GB B200 at all.  Constant buffers
+    (``prog.consts``) keep their own storage; ``LAMA_B200_POOL=0`` gives every buffer its own."""
+    first: Dict[str, int] = {}
+    last: Dict[str, int] = {}
+    for i, op in enumerate(prog.ops):
+        reads, writes = op_views(op)
+        for tv in reads + writes:
+            first.setdefault(tv.buf.name, i)
+            last[tv.buf.name] = i
+    pooling = os.environ.get("LAMA_B200_POOL", "1") != "0"
+    slots: Dict[str, int] = {}
+    free_at: List[Tuple[tuple, int]] = []          # per slot: (storage key, index of the last op that touches it)
+    for b in sorted(prog.bufs, key=lambda bb: first.get(bb.name, -1)):
+        key = storage_key(b)
+        reuse = None
+        if pooling and b.name in first and b.name not in prog.consts:
+            for si, (k, until) in enumerate(free_at):
+                if k == key and until is not None and until < first[b.name]:
+                    reuse = si
+                    break
+        if reuse is None:
+            reuse = len(free_at)
+            free_at.append((key, None))
+        # constants and never-touched buffers hold their slot for good
+        free_at[reuse] = (key, last[b.name] if (b.name in last and b.name not in prog.consts) else None)
+        slots[b.name] = reuse
+    return slots
+
+
 class CudaExecutor:
     """Binds a Program to device buffers and pre-built C-ABI calls."""
 
@@ -991,16 +1056,24 @@ class CudaExecutor:
         self.dev_index = device.index if device.index is not None else torch.cuda.current_device()
         L.check(self.lib.ffcb_check_device(self.dev_index), "ffcb_check_device")
         self.storage: Dict[str, torch.Tensor] = {}
+        self.slots = assign_storage_slots(prog)          # buffers whose lifetimes do not overlap share storage
+        slot_tensor: Dict[int, torch.Tensor] = {}
         for b in prog.bufs:
+            si = self.slots[b.name]
+            if si in slot_tensor:
+                self.storage[b.name] = slot_tensor[si]
+                continue
             shape = (b.B, b.H + 2 * b.pad, b.W + 2 * b.pad, b.C)
             if b.cg:
                 shape = (b.C // b.cg, b.B, b.H, b.W, b.cg)
             if b.tile:
                 shape = (-(-(b.B * b.H * b.W) // 128), b.C // 8, 128, 8)      # zero-initialised: the tail block stays finite
             if b.fmt == L.F32:
-                self.storage[b.name] = torch.empty(shape, dtype=torch.float32, device=device)
+                slot_tensor[si] = torch.empty(shape, dtype=torch.float32, device=device)
             else:
-                self.storage[b.name] = torch.zeros((2,) + shape, dtype=torch.bfloat16, device=device)
+                slot_tensor[si] = torch.zeros((2,) + shape, dtype=torch.bfloat16, device=device)
+            self.storage[b.name] = slot_tensor[si]
+        self.storage_bytes = sum(t.numel() * t.element_size() for t in slot_tensor.values())
         for name, val in prog.consts.items():
             assert self.storage[name].dtype == torch.float32 and tuple(self.storage[name].shape) == tuple(val.shape)
             self.storage[name].copy_(val.to(device=device, dtype=torch.float32))

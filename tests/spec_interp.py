@@ -14,7 +14,17 @@ from lama_b200.packing import apply_packed_reference
 class SpecInterpreter:
     def __init__(self, prog: E.Program):
         self.prog = prog
-        self.mem = {b.name: torch.full((b.B, b.H, b.W, b.C), float("nan"), dtype=torch.float64) for b in prog.bufs}
+        # buffers share storage exactly as in the product's executor (engine.assign_storage_slots): a buffer whose
+        # slot is reused too early would be read back corrupted here too, on the CPU
+        slots = E.assign_storage_slots(prog)
+        by_slot = {}
+        self.mem = {}
+        for b in prog.bufs:
+            if slots[b.name] not in by_slot:
+                by_slot[slots[b.name]] = torch.full((b.B, b.H, b.W, b.C), float("nan"), dtype=torch.float64)
+            self.mem[b.name] = by_slot[slots[b.name]]
+            assert tuple(self.mem[b.name].shape) == (b.B, b.H, b.W, b.C)
+        self.n_slots = len(by_slot)
         for name, val in prog.consts.items():
             self.mem[name] = val.double().clone()
 

@@ -211,8 +211,13 @@ def test_fft_round_trip_full_size():
 
 
 # ------------------------------------------------------------------------------------ conv kernel
-@pytest.mark.parametrize("math", MATHS)
-@pytest.mark.parametrize("case", ["k3_reflect", "k3_s2", "k1_two_src", "k7_nopad", "zero_border_phase", "ragged"])
+_CONV_CASES = ["k3_reflect", "k3_s2", "k1_two_src", "k7_nopad", "zero_border_phase", "ragged"]
+# (the tcgen05 arm requires 64-channel K segments: "k7_nopad" and "ragged" exist for the CUDA-core arm only)
+_CONV_PARAMS = [(c, m) for m in MATHS for c in _CONV_CASES
+                if not (m == L.MATH_BF16X3 and c in ("k7_nopad", "ragged"))]
+
+
+@pytest.mark.parametrize("case,math", _CONV_PARAMS)
 def test_conv_contract(case, math):
     """ffcb_conv vs the torch restatement of its contract (packing.apply_packed_reference), covering
     reflect / zero borders, stride 2, two sources, addend before/after the activation, sub-pixel
@@ -261,8 +266,6 @@ def test_conv_contract(case, math):
         b, h, w, cin, n = 3, 7, 9, 20, 24
         pk = P.pack_conv([(rn(n, cin, 3, 3) * 0.1, 0, 0, 1)], None, rn(n), act=L.ACT_RELU)
         ins, out_hw, add = [rn(b, h, w, cin), None], (h, w), None
-    if math == L.MATH_BF16X3 and case in ("k7_nopad", "ragged"):
-        pytest.skip("tcgen05 arm needs 64-channel K segments")
     prog = E.Program("conv", math)
     bufs, tvs = [], []
     feed = {}
@@ -398,11 +401,13 @@ def _finish_borders(prog):
 # ------------------------------------------------------------------------------------ modules vs goldens
 @pytest.mark.parametrize("name,ci,co", [("fu_c8_16x16", 8, 8), ("fu_c4to6_8x32", 4, 6), ("fu_c16_32x32", 16, 16),
                                         ("fu_c4_15x15", 4, 4), ("fu_c4_6x9", 4, 4)])
-def test_fourier_unit_golden(name, ci, co, math_mode):
+def test_fourier_unit_golden(name, ci, co, math_mode, monkeypatch):
     a, sd = load_golden(name)
     m = _load(M.FourierUnit(ci, co), sd)
     if not m.native_supported():
-        pytest.skip("channel count outside the native path")
+        # channel count outside the kernels' granularity (multiples of 4): the drop-in must still answer — the
+        # documented torch-operator composition on the same device (never the CPU); STRICT would turn it into an error
+        monkeypatch.setenv("LAMA_B200_STRICT", "0")
     with torch.no_grad():
         y = m(torch.from_numpy(a["x"]).to(DEV)).cpu().numpy()
     assert _rel_err(y, a["y"]) < TOL[math_mode]

@@ -351,3 +351,38 @@ def test_empty_batch_returns_empty_outputs_without_launching():
     fu = M.FourierUnit(8, 8).eval()
     (yf,) = E.run_module(fu, "fourier_unit", (torch.empty(0, 8, 16, 16),))
     assert tuple(yf.shape) == (0, 8, 16, 16)
+
+
+def test_storage_slots_never_alias_live_buffers(monkeypatch):
+    """engine.assign_storage_slots: buffers share storage only when (a) their storage is byte-identical and (b) the
+    last op touching the earlier one comes strictly before the first op touching the later one; constants keep their
+    own storage.  big-lama folds onto a dozen slots (bs64 1024x1024 = BASELINE config 4 on one GPU must fit 180 GB)."""
+    from lama_b200.testing import BIG_LAMA_KWARGS
+    gen = M.FFCResNetGenerator(**BIG_LAMA_KWARGS).eval()
+    with torch.no_grad():
+        prog = E.build_module_program(gen, "generator", ((64, 4, 1024, 1024),), L.MATH_BF16X3)
+    slots = E.assign_storage_slots(prog)
+    first, last = {}, {}
+    for i, op in enumerate(prog.ops):
+        r, w = E.op_views(op)
+        for tv in r + w:
+            first.setdefault(tv.buf.name, i)
+            last[tv.buf.name] = i
+    by_slot = {}
+    for b in prog.bufs:
+        by_slot.setdefault(slots[b.name], []).append(b)
+    for members in by_slot.values():
+        assert len({E.storage_key(b) for b in members}) == 1
+        members = sorted(members, key=lambda b: first[b.name])
+        for a, b in zip(members, members[1:]):
+            assert last[a.name] < first[b.name], (a.name, b.name)
+            assert a.name not in prog.consts and b.name not in prog.consts
+
+    def nbytes(b):
+        if b.tile:
+            return -(-(b.B * b.H * b.W) // 128) * 128 * b.C * 4
+        return b.B * (b.H + 2 * b.pad) * (b.W + 2 * b.pad) * b.C * 4
+    pooled = sum(nbytes(m[0]) for m in by_slot.values())
+    assert len(by_slot) <= 16 and pooled < 80e9 < sum(nbytes(b) for b in prog.bufs)
+    monkeypatch.setenv("LAMA_B200_POOL", "0")
+    assert len(set(E.assign_storage_slots(prog).values())) == len(prog.bufs)

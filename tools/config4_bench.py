@@ -122,6 +122,8 @@ def main():
             "scatter_bytes": B * 4 * S * S * 4, "gather_bytes": B * 3 * S * S * 4,
             "scaling": "weak (equal per-GPU batch)" if args.per_gpu_batch else "strong (fixed global batch)",
             "launches_per_step": ex.launches_per_run, "result_ok": ok,
+            "activation_storage_gb_per_gpu": round(ex.storage_bytes / 1e9, 2),
+            "torch_peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2),
             "timer": "CUDA events on the launch stream, barrier + synchronize both sides, max over ranks",
         }), flush=True)
     if world > 1:
