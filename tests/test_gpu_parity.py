@@ -404,13 +404,15 @@ def _finish_borders(prog):
 def test_fourier_unit_golden(name, ci, co, math_mode, monkeypatch):
     a, sd = load_golden(name)
     m = _load(M.FourierUnit(ci, co), sd)
+    tol = TOL[math_mode]
     if not m.native_supported():
         # channel count outside the kernels' granularity (multiples of 4): the drop-in must still answer — the
         # documented torch-operator composition on the same device (never the CPU); STRICT would turn it into an error
         monkeypatch.setenv("LAMA_B200_STRICT", "0")
+        tol = 1e-3           # torch's own GPU convolution (TF32 by default), as the reference would run it
     with torch.no_grad():
         y = m(torch.from_numpy(a["x"]).to(DEV)).cpu().numpy()
-    assert _rel_err(y, a["y"]) < TOL[math_mode]
+    assert _rel_err(y, a["y"]) < tol
 
 
 def test_spectral_transform_golden(math_mode):
