@@ -36,6 +36,7 @@ constexpr int kTileABytes = BM * BK * 2;   // 16 KB per plane
 constexpr int kMaxStages = 8;
 constexpr int kAccStages = 4;     // TMEM accumulator ring: the MMA issuer may run 3 tiles ahead of the epilogue
 constexpr int kAccStride = 128;   // TMEM columns per accumulator stage (BN <= 128)
+constexpr int kStackMinKBlocks = 12;   // contractions at least this long use the stacked-product MMA pair (TcParams::stack)
 constexpr int kBarBytes = 1024;  // mbarriers + TMEM slot, padded so that the staging tiles stay 1024-byte aligned
 constexpr int kEpiBytes = kEpiWarps * 4096;
 
@@ -63,6 +64,13 @@ struct TcParams {
   int a_tiles_per_image[2];       // spatial mode: 128-pixel blocks per image (H * W / 128)
   int out_planar;                 // out is channel-group planar float32: stored straight from registers
   int hints;                      // L2 residency hints for the planar (FourierUnit chain) outputs
+  // Stacked products: the weight tile's hi and lo planes are adjacent in a pipeline stage, i.e. they ARE a K-major
+  // tile of 2*BN rows — a_hi x [w_hi | w_lo] is ONE MMA with N = 2*BN (columns [0,BN) = hi.hi, [BN,2BN) = hi.lo) and
+  // a_lo x w_hi a second one with N = BN into the first half; the epilogue adds the two halves.  Same tensor work as
+  // three N = BN MMAs, but 5 operand-tile reads from shared memory per K step instead of 6 (an SS MMA with N = 128
+  // reads 8 KB per 64 cycles = the whole 128 B/clk of the SM's shared memory).  Costs accumulator stages: 2 x 256
+  // columns instead of 4 x 128.
+  int stack, acc_stride, acc_stages;
   int desc_swap;             // bring-up: exchange LBO / SBO of the no-swizzle descriptor (FFCB_TC_DESC_SWAP)
   int debug;                 // bring-up knobs (FFCB_TC_DEBUG): 1 no global ld/st in epilogue, 2 no epilogue work,
                              // 4 no MMA issue, 8 no activation loads
@@ -384,7 +392,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
     // plus the UTCHMMA.  Descriptors are (lo, hi) 32-bit pairs: advancing along K only touches the 14-bit
     // start-address field of the low word.
     {
-      const uint32_t idesc = make_idesc(p.BN);
+      const uint32_t idesc = make_idesc(p.BN), idesc2 = make_idesc(2 * p.BN);
       constexpr uint32_t kHiSw = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);          // SBO 1024, v1, SWIZZLE_128B
       const uint32_t hi_il = (uint32_t)((p.desc_swap ? 2048 : 128) >> 4) | (1u << 14);     // SBO, v1, no swizzle
       const uint32_t lbo_il = (uint32_t)((p.desc_swap ? 128 : 2048) >> 4) << 16;           // LBO (low word)
@@ -395,7 +403,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
         int kb = 0;
         for (int sgi = 0; sgi < (IL ? p.nseg : 1); ++sgi) {
           const bool il = IL && p.a_il[p.seg[sgi].src] != 0;
@@ -417,9 +425,14 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
                 if (p.debug & 4) break;
                 const uint32_t wadv = (uint32_t)((k * UMMA_K * 2) >> 4);     // +32 B per UMMA_K inside the swizzle row
                 const uint32_t aadv = (uint32_t)k * a_step;                  // same, or two 2048-byte slabs (interleaved)
-                umma_bf16(d_tmem, desc64(a_hi + aadv, a_hiword), desc64(w_hi + wadv, kHiSw), idesc, (kb | k) != 0);
-                umma_bf16(d_tmem, desc64(a_lo + aadv, a_hiword), desc64(w_hi + wadv, kHiSw), idesc, 1);
-                umma_bf16(d_tmem, desc64(a_hi + aadv, a_hiword), desc64(w_lo + wadv, kHiSw), idesc, 1);
+                if (p.stack) {
+                  umma_bf16(d_tmem, desc64(a_hi + aadv, a_hiword), desc64(w_hi + wadv, kHiSw), idesc2, (kb | k) != 0);
+                  umma_bf16(d_tmem, desc64(a_lo + aadv, a_hiword), desc64(w_hi + wadv, kHiSw), idesc, 1);
+                } else {
+                  umma_bf16(d_tmem, desc64(a_hi + aadv, a_hiword), desc64(w_hi + wadv, kHiSw), idesc, (kb | k) != 0);
+                  umma_bf16(d_tmem, desc64(a_lo + aadv, a_hiword), desc64(w_hi + wadv, kHiSw), idesc, 1);
+                  umma_bf16(d_tmem, desc64(a_hi + aadv, a_hiword), desc64(w_lo + wadv, kHiSw), idesc, 1);
+                }
               }
               umma_commit(&empty[stage]);                 // smem stage reusable once these MMAs retire
               if (kb == total_kblocks - 1) umma_commit(&acc_full[acc]);
@@ -428,7 +441,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
-        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -480,7 +493,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
                    p.N - (n_tile * p.BN + half * 32), raw);
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kAccStride);
+      const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * p.acc_stride);
       for (int c0 = half * 32; c0 < c_end; c0 += 64) {
         const int n0 = n_tile * p.BN + c0;
         // residual / addend row of this pixel (32 channels) was requested one chunk ahead: raw[] holds it
@@ -488,6 +501,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         decode_addend(p.addend, raw, ad);
         uint32_t r[32];
         tmem_ld32(t_row + (uint32_t)c0, r);
+        if (p.stack) {       // + the a_hi x w_lo half of the stacked accumulator
+          uint32_t r2[32];
+          tmem_ld32(t_row + (uint32_t)(p.BN + c0), r2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
         fetch_addend(p.addend, has_add && valid && c0 + 64 < c_end, o_add + n0 + 64, p.N - (n0 + 64), raw);
         float v[32];
 #pragma unroll
@@ -577,7 +596,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
     if (elect_one()) tma_store_wait_all();
   }
@@ -713,6 +732,14 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   for (int i = 0; i < d->nseg; ++i) {
     p.seg[i] = d->seg[i];
     kpad += (d->seg[i].nch + BK - 1) / BK * BK;
+  }
+  {
+    // stacked products need two 256-column accumulator stages: long contractions only (the epilogue of a short-K
+    // tile would no longer hide behind the next tiles' MMAs); FFCB_TC_STACK=0|1 forces it off / on
+    const char* e = getenv("FFCB_TC_STACK");
+    p.stack = e ? (atoi(e) != 0) : (kpad / BK >= kStackMinKBlocks);
+    p.acc_stride = p.stack ? 256 : kAccStride;
+    p.acc_stages = p.stack ? 2 : kAccStages;
   }
 
   // ---- tiling: flat when every tap is (0,0) on dense unit-stride inputs, else spatial TW x TH
