@@ -62,6 +62,7 @@ struct TcParams {
   long long a_sg[2], a_lo[2];     // elements per 128-pixel block, hi -> lo plane offset
   int a_tiles_per_image[2];       // spatial mode: 128-pixel blocks per image (H * W / 128)
   int out_planar;                 // out is channel-group planar float32: stored straight from registers
+  int ring;                       // out has a 1-pixel reflected ring: the epilogue also writes the mirrored copies
   int hints;                      // L2 residency hints for the planar (FourierUnit chain) outputs
   // Stacked products: the weight tile's hi and lo planes are adjacent in a pipeline stage, i.e. they ARE a K-major
   // tile of 2*BN rows — a_hi x [w_hi | w_lo] is ONE MMA with N = 2*BN (columns [0,BN) = hi.hi, [BN,2BN) = hi.lo) and
@@ -531,6 +532,18 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += ad[j];
         }
+        if (!PO && p.ring && valid) {
+          // reflected ring of the output (it feeds a 3x3 reflect contraction next): pixels of rows 1 / H-2 and columns
+          // 1 / W-2 (6 % of a 64x64 plane) also land on the ring — out-of-line stores, no separate ring kernel
+          int my, mx;
+          if (ring_mirrors(p.out, y, x, my, mx) && !(p.debug & 1)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (n0 + 4 * q < p.N)
+                store4_ring_copies(p.out, b, y, x, my, mx, n0 + 4 * q,
+                                   make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+          }
+        }
         if constexpr (PO) {
           // channel-group planar float32 output (FourierUnit chain): the lane's pixel is contiguous with its
           // neighbours' inside every channel group, so plain 16-byte stores are whole lines — no staging tile.
@@ -704,6 +717,7 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   TcParams p;
   p.out = make_view(d->out);
   p.out_planar = d->out.cg != 0 ? 1 : 0;
+  p.ring = (d->out.reflect_border && d->out.pad == 1 && d->out.cg == 0 && d->out.H >= 4 && d->out.W >= 4) ? 1 : 0;
   if (d->out.cg != 0)
     FFCB_REQUIRE(d->out.fmt == FFCB_F32 && d->out.sx % 4 == 0 && d->out.sy % 4 == 0 && d->out.sb % 4 == 0,
                  "conv(tc): channel-group planar outputs are float32");

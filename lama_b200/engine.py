@@ -975,9 +975,19 @@ def insert_border_ops(prog: Program):
             wrote = op.out
         elif isinstance(op, RfftOp):
             wrote = op.spec
-        if wrote is not None and wrote.buf.reflect_border:
+        if wrote is not None and wrote.buf.reflect_border and not conv_writes_ring(prog, op):
             dirty[id(wrote.buf)] = wrote.buf
     prog.ops = out
+
+
+def conv_writes_ring(prog: Program, op) -> bool:
+    """The tcgen05 contraction writes the mirrored copies of rows 1 / H-2 and columns 1 / W-2 into a 1-pixel reflected
+    ring of its output itself (conv_tc.cu, TcParams::ring) — whole-plane outputs only (a sub-pixel phase or a window
+    does not own the ring)."""
+    if os.environ.get("LAMA_B200_RING_KERNEL", "0") == "1":        # A/B: always refresh rings with the ring kernel
+        return False
+    return (prog.math == L.MATH_BF16X3 and isinstance(op, ConvOp) and op.out.phase is None and op.out.win is None
+            and not op.out.window and op.out.buf.pad == 1 and op.out.buf.H >= 4 and op.out.buf.W >= 4)
 
 
 # ------------------------------------------------------------------------------------- executor

@@ -296,6 +296,47 @@ def test_conv_contract(case, math):
 
 
 
+@pytest.mark.parametrize("b,h,w,cin,n,c0", [(2, 64, 64, 64, 128, 0), (3, 9, 20, 64, 40, 0), (1, 32, 32, 128, 64, 64),
+                                            (2, 4, 4, 64, 64, 0)])
+def test_conv_tc_writes_the_reflected_ring_of_its_output(b, h, w, cin, n, c0):
+    """conv_tc.cu (TcParams::ring): a whole-plane output with a 1-pixel reflected ring gets its ring from the
+    contraction's own epilogue — no ffcb_fill_reflect_border launch in the program — bit-identical to reflecting the
+    interior (split-bf16 storage: the mirrored pixels are copies).  Covers a channel slice of a wider buffer, a ragged
+    plane and the smallest plane the rule covers; then a 3x3 reflect contraction consumes the ring."""
+    g = torch.Generator().manual_seed(b * 1000 + h)
+    x = torch.randn(b, h, w, cin, generator=g)
+    pk1 = P.pack_conv([(torch.randn(n, cin, 1, 1, generator=g) * 0.1, 0, 0, 0)], None, torch.randn(n, generator=g), act=L.ACT_RELU)
+    pk3 = P.pack_conv([(torch.randn(64, c0 + n, 3, 3, generator=g) * 0.05, 0, 0, 1)], None, torch.randn(64, generator=g), act=L.ACT_NONE)
+    prog = E.Program("conv", L.MATH_BF16X3)
+    X = prog.buf("x", b, h, w, cin, gemm=True)
+    Y = prog.buf("y", b, h, w, c0 + n, gemm=True, halo=True)
+    Z = prog.buf("z", b, h, w, 64)
+    prog.inputs["x0"] = (b, cin, h, w)
+    prog.ops.append(E.ToNHWC("x0", E.TV(X)))
+    if c0:
+        pk0 = P.pack_conv([(torch.randn(c0, cin, 1, 1, generator=g) * 0.1, 0, 0, 0)], None, torch.randn(c0, generator=g), act=L.ACT_NONE)
+        prog.ops.append(E.ConvOp(pk0, [E.TV(X), None], E.TV(Y, 0, c0)))
+    prog.ops.append(E.ConvOp(pk1, [E.TV(X), None], E.TV(Y, c0, n)))
+    prog.ops.append(E.ConvOp(pk3, [E.TV(Y), None], E.TV(Z)))
+    prog.ops.append(E.ToNCHW(E.TV(Z), "y0"))
+    prog.outputs = {"y0": (b, 64, h, w)}
+    E.insert_border_ops(prog)
+    assert not any(isinstance(o, E.BorderOp) for o in prog.ops), "the producing contractions own the ring"
+    ex = E.CudaExecutor(prog, torch.device(DEV))
+    out = ex.run({"x0": x.permute(0, 3, 1, 2).contiguous().to(DEV)})
+    torch.cuda.synchronize()
+    st = ex.storage[Y.name].cpu()                                   # [2][B][H+2][W+2][C] bf16 hi|lo
+    inner = st[:, :, 1:-1, 1:-1].float().permute(0, 1, 4, 2, 3).reshape(-1, c0 + n, h, w)
+    want_ring = torch.nn.functional.pad(inner, (1, 1, 1, 1), mode="reflect")
+    got = st.float().permute(0, 1, 4, 2, 3).reshape(-1, c0 + n, h + 2, w + 2)
+    assert torch.equal(got, want_ring), "ring != reflection of the interior"
+    y = P.apply_packed_reference(pk1, [x, None], (h, w))
+    if c0:
+        y = torch.cat([P.apply_packed_reference(pk0, [x, None], (h, w)), y], dim=-1)
+    want = P.apply_packed_reference(pk3, [y, None], (h, w))
+    assert _rel_err(out["y0"].cpu().permute(0, 2, 3, 1).numpy(), want.numpy()) < 2e-4
+
+
 # ------------------------------------------------------------------ channel-group planar FourierUnit chain (round 2)
 @pytest.mark.parametrize("residual", [True, False])
 @pytest.mark.parametrize("b,c,h", [(2, 8, 64), (3, 24, 64), (1, 192, 64), (3, 8, 32), (2, 40, 32)])
