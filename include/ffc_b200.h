@@ -112,8 +112,8 @@ typedef struct {
  * The out view's H,W are the output grid; input coordinates outside the input's interior are
  * zero (FFCB_BORDER_ZERO) or reflected without edge repeat (FFCB_BORDER_REFLECT, ffc.py:189
  * padding_mode='reflect').
- * Output ring (FFCB_MATH_BF16X3): when `out` is a whole plane with a 1-pixel reflected ring (out.reflect_border != 0,
- * out.pad == 1, H, W >= 4) the kernel also writes the mirrored copies of rows 1 / H-2 and columns 1 / W-2 into the
+ * Output ring (FFCB_MATH_BF16X3): when `out` is a whole split-bf16 plane with a 1-pixel reflected ring
+ * (out.reflect_border != 0, out.pad == 1, H, W >= 4) the kernel also writes the mirrored copies of rows 1 / H-2 and columns 1 / W-2 into the
  * ring, so the result can feed the next 3x3 reflect contraction without ffcb_fill_reflect_border.  The FP32 arm and
  * every other producer leave the ring to ffcb_fill_reflect_border.
  *

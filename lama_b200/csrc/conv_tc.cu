@@ -483,6 +483,15 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         valid = y < p.out.H && x < p.out.W;
       }
       const long long o_add = (has_add && valid) ? pix_off(p.addend, b, y, x) : 0;
+      // this pixel's mirror images in the output's reflected ring, as element offsets from the pixel itself (0: none)
+      int mir_dy = 0, mir_dx = 0;
+      if (!PO && p.ring && valid && !(p.debug & 1)) {
+        int my, mx;
+        if (ring_mirrors(p.out, y, x, my, mx)) {
+          if (my != -2) mir_dy = (my - y) * (int)p.out.sy;
+          if (mx != -2) mir_dx = (mx - x) * (int)p.out.sx;
+        }
+      }
       const int box_x = tc.x0 + (wq * 32) % p.TW, box_y = tc.y0 + (wq * 32) / p.TW;
       const int c_end = (p.debug & 2) ? 0 : p.BN;
 
@@ -532,18 +541,6 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += ad[j];
         }
-        if (!PO && p.ring && valid) {
-          // reflected ring of the output (it feeds a 3x3 reflect contraction next): pixels of rows 1 / H-2 and columns
-          // 1 / W-2 (6 % of a 64x64 plane) also land on the ring — out-of-line stores, no separate ring kernel
-          int my, mx;
-          if (ring_mirrors(p.out, y, x, my, mx) && !(p.debug & 1)) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (n0 + 4 * q < p.N)
-                store4_ring_copies(p.out, b, y, x, my, mx, n0 + 4 * q,
-                                   make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-          }
-        }
         if constexpr (PO) {
           // channel-group planar float32 output (FourierUnit chain): the lane's pixel is contiguous with its
           // neighbours' inside every channel group, so plain 16-byte stores are whole lines — no staging tile.
@@ -588,8 +585,26 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
               h[k] = pack_bf16(h0, h1);
               l[k] = pack_bf16(l0, l1);
             }
-            hi[c ^ sw] = make_uint4(h[0], h[1], h[2], h[3]);
-            lo[c ^ sw] = make_uint4(l[0], l[1], l[2], l[3]);
+            const uint4 h4 = make_uint4(h[0], h[1], h[2], h[3]), l4 = make_uint4(l[0], l[1], l[2], l[3]);
+            hi[c ^ sw] = h4;
+            lo[c ^ sw] = l4;
+            if ((mir_dy | mir_dx) != 0 && n0 + 8 * c < p.N) {
+              // reflected ring of the output (it feeds a 3x3 reflect contraction next): pixels of rows 1 / H-2 and
+              // columns 1 / W-2 also land on the ring (<= 3 copies, 16-byte stores) — no separate ring kernel
+              unsigned short* ob = reinterpret_cast<unsigned short*>(p.out.ptr) + pix_off(p.out, b, y, x) + (n0 + 8 * c);
+              if (mir_dy) {
+                *reinterpret_cast<uint4*>(ob + mir_dy) = h4;
+                *reinterpret_cast<uint4*>(ob + mir_dy + p.out.lo_off) = l4;
+              }
+              if (mir_dx) {
+                *reinterpret_cast<uint4*>(ob + mir_dx) = h4;
+                *reinterpret_cast<uint4*>(ob + mir_dx + p.out.lo_off) = l4;
+              }
+              if (mir_dy && mir_dx) {
+                *reinterpret_cast<uint4*>(ob + mir_dy + mir_dx) = h4;
+                *reinterpret_cast<uint4*>(ob + mir_dy + mir_dx + p.out.lo_off) = l4;
+              }
+            }
           }
         } else {
           // [32 rows][32 floats] = 128-byte rows, TMA SWIZZLE_128B: chunk c of row r lives at c ^ (r & 7)
@@ -717,7 +732,8 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   TcParams p;
   p.out = make_view(d->out);
   p.out_planar = d->out.cg != 0 ? 1 : 0;
-  p.ring = (d->out.reflect_border && d->out.pad == 1 && d->out.cg == 0 && d->out.H >= 4 && d->out.W >= 4) ? 1 : 0;
+  p.ring = (d->out.reflect_border && d->out.pad == 1 && d->out.cg == 0 && d->out.fmt == FFCB_BF16X2 && d->out.H >= 4 &&
+            d->out.W >= 4) ? 1 : 0;
   if (d->out.cg != 0)
     FFCB_REQUIRE(d->out.fmt == FFCB_F32 && d->out.sx % 4 == 0 && d->out.sy % 4 == 0 && d->out.sb % 4 == 0,
                  "conv(tc): channel-group planar outputs are float32");

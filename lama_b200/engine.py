@@ -987,7 +987,8 @@ def conv_writes_ring(prog: Program, op) -> bool:
     if os.environ.get("LAMA_B200_RING_KERNEL", "0") == "1":        # A/B: always refresh rings with the ring kernel
         return False
     return (prog.math == L.MATH_BF16X3 and isinstance(op, ConvOp) and op.out.phase is None and op.out.win is None
-            and not op.out.window and op.out.buf.pad == 1 and op.out.buf.H >= 4 and op.out.buf.W >= 4)
+            and not op.out.window and op.out.buf.pad == 1 and op.out.buf.fmt == L.BF16X2 and op.out.buf.H >= 4
+            and op.out.buf.W >= 4)
 
 
 # ------------------------------------------------------------------------------------- executor
