@@ -71,6 +71,12 @@ struct TcParams {
   // reads 8 KB per 64 cycles = the whole 128 B/clk of the SM's shared memory).  Costs accumulator stages: 2 x 256
   // columns instead of 4 x 128.
   int stack, acc_stride, acc_stages;
+  // Rows-resident mode (template RR; the 7x7 head's row contraction and the windowed 7x7 stem): every K segment is the
+  // SAME 64-channel block of one source shifted by dy only, so the activation tile is loaded ONCE per M tile as a
+  // (TH + R) x TW halo (TW = 16, TH = 8: a dy shift is a whole number of 1024-byte swizzle atoms, the MMA descriptor
+  // just starts (dy - dy0) * TW rows further down) and the (small) weight tiles of all segments stay resident in
+  // shared memory for the whole kernel.  L2 -> shared-memory traffic per tile: 56 KB instead of nseg x 32-40 KB.
+  int rr_dy0, rr_a_bytes, rr_w_bytes;
   int desc_swap;             // bring-up: exchange LBO / SBO of the no-swizzle descriptor (FFCB_TC_DESC_SWAP)
   int debug;                 // bring-up knobs (FFCB_TC_DEBUG): 1 no global ld/st in epilogue, 2 no epilogue work,
                              // 4 no MMA issue, 8 no activation loads
@@ -287,7 +293,7 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, long long m_t
 // IL: some K segment reads a channel-group planar ("interleaved") operand.  The instantiation without them is the
 // round-1 kernel instruction for instruction (one descriptor kind, no per-segment walk in the MMA issuer).
 // PO: the output is channel-group planar float32 (stored from registers instead of through the staging tile).
-template <bool IL, bool PO>
+template <bool IL, bool PO, bool RR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap map_in0,
                const __grid_constant__ CUtensorMap map_in1, const __grid_constant__ CUtensorMap map_w,
@@ -296,13 +302,16 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   // carve: stages of [A_hi | A_lo | W_hi | W_lo], then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int w_bytes = p.BN * BK * 2;
-  const int stage_bytes = 2 * kTileABytes + 2 * w_bytes;
+  const int stage_bytes = RR ? 2 * p.rr_a_bytes : 2 * kTileABytes + 2 * w_bytes;
+  uint8_t* w_res = smem;                                   // RR: resident weight tiles [seg][hi | lo]
+  if constexpr (RR) smem += p.rr_w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* acc_full = bars + 2 * kMaxStages;
   uint64_t* acc_empty = acc_full + kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+  uint64_t* w_bar = acc_empty + kAccStages + 1;             // RR: the resident weights have landed
   uint8_t* stage_tile = reinterpret_cast<uint8_t*>(bars) + kBarBytes;     // 8 x 4 KB epilogue staging (1024-B aligned)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -316,6 +325,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < kAccStages; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], kEpiWarps * 32); }
+    if constexpr (RR) mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -336,7 +346,33 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
 
   if (warp == 0) {
     // ================================================================ TMA producer (uniform control flow, one elected lane issues)
-    {
+    if constexpr (RR) {
+      const ffcb_kseg g0 = p.seg[0];
+      const CUtensorMap* map = g0.src ? &map_in1 : &map_in0;
+      if (elect_one()) {
+        mbar_expect_tx(w_bar, (uint32_t)p.rr_w_bytes);
+        for (int s = 0; s < p.nseg; ++s) {
+          tma_load_3d(w_res + (size_t)s * 2 * w_bytes, &map_w, w_bar, s * BK, 0, 0);
+          tma_load_3d(w_res + (size_t)s * 2 * w_bytes + w_bytes, &map_w, w_bar, s * BK, 0, 1);
+        }
+      }
+      __syncwarp();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(p, t);
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* st = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+          const int cx = tc.x0 + g0.dx + p.coord_off[g0.src], cy = tc.y0 + p.rr_dy0 + p.coord_off[g0.src];
+          tma_load_5d(st, map, &full[stage], g0.c0, cx, cy, tc.b, 0);
+          tma_load_5d(st + p.rr_a_bytes, map, &full[stage], g0.c0, cx, cy, tc.b, 1);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    } else {
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -400,10 +436,44 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if constexpr (RR) mbar_wait(w_bar, 0);
       for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+        if constexpr (RR) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t wr = smem_u32(w_res);
+            for (int sgi = 0; sgi < p.nseg; ++sgi) {
+              const uint32_t a_off = (uint32_t)((p.seg[sgi].dy - p.rr_dy0) * p.TW * (BK * 2));
+              const uint32_t a_hi = ((st + a_off) & 0x3FFFF) >> 4;
+              const uint32_t a_lo = ((st + a_off + (uint32_t)p.rr_a_bytes) & 0x3FFFF) >> 4;
+              const uint32_t w_hi = ((wr + (uint32_t)(sgi * 2 * w_bytes)) & 0x3FFFF) >> 4;
+              const uint32_t w_lo = ((wr + (uint32_t)(sgi * 2 * w_bytes + w_bytes)) & 0x3FFFF) >> 4;
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint32_t adv = (uint32_t)((k * UMMA_K * 2) >> 4);
+                if (p.stack) {
+                  umma_bf16(d_tmem, desc64(a_hi + adv, kHiSw), desc64(w_hi + adv, kHiSw), idesc2, (sgi | k) != 0);
+                  umma_bf16(d_tmem, desc64(a_lo + adv, kHiSw), desc64(w_hi + adv, kHiSw), idesc, 1);
+                } else {
+                  umma_bf16(d_tmem, desc64(a_hi + adv, kHiSw), desc64(w_hi + adv, kHiSw), idesc, (sgi | k) != 0);
+                  umma_bf16(d_tmem, desc64(a_lo + adv, kHiSw), desc64(w_hi + adv, kHiSw), idesc, 1);
+                  umma_bf16(d_tmem, desc64(a_hi + adv, kHiSw), desc64(w_lo + adv, kHiSw), idesc, 1);
+                }
+              }
+            }
+            umma_commit(&empty[stage]);
+            umma_commit(&acc_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
         int kb = 0;
         for (int sgi = 0; sgi < (IL ? p.nseg : 1); ++sgi) {
           const bool il = IL && p.a_il[p.seg[sgi].src] != 0;
@@ -792,9 +862,36 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   // the epilogue stores 32-pixel boxes through a tensor map: a flattened pixel axis needs a dense output too
   flat = flat && (d->out.cg != 0 || (d->out.sy == (int64_t)W * d->out.sx && d->out.sb == (int64_t)H * d->out.sy));
   p.flat = flat ? 1 : 0;
+  // rows-resident mode (TcParams::rr_*): every segment = the same 64-channel block of one channels-last source, shifted
+  // by dy only (the 7x7 head's row contraction, the windowed 7x7 stem); FFCB_TC_ROWS=0 disables it
+  bool rr = false;
+  int rr_dy_min = 0, rr_dy_max = 0;
+  p.rr_dy0 = p.rr_a_bytes = p.rr_w_bytes = 0;
+  {
+    const char* e = getenv("FFCB_TC_ROWS");
+    rr = !flat && d->stride == 1 && d->nseg >= 3 && p.num_n_tiles == 1 && (e ? atoi(e) != 0 : true) &&
+         d->in[d->seg[0].src].cg == 0;
+    rr_dy_min = rr_dy_max = d->seg[0].dy;
+    for (int i = 0; i < d->nseg && rr; ++i) {
+      const ffcb_kseg& g = d->seg[i];
+      rr = g.src == d->seg[0].src && g.c0 == d->seg[0].c0 && g.nch == BK && g.dx == d->seg[0].dx;
+      for (int j = 0; j < i && rr; ++j) rr = d->seg[j].dy != g.dy;
+      if (g.dy < rr_dy_min) rr_dy_min = g.dy;
+      if (g.dy > rr_dy_max) rr_dy_max = g.dy;
+    }
+    rr = rr && (rr_dy_max - rr_dy_min) <= 8;
+  }
   if (flat) {
     p.TW = BM; p.TH = 1; p.tiles_x = p.tiles_y = 1;
     p.num_m_tiles = ((long long)d->out.B * H * W + BM - 1) / BM;
+  } else if (rr) {
+    p.TW = 16; p.TH = BM / 16;              // a dy shift = 16 rows of 128 B = two whole swizzle atoms
+    p.tiles_x = (W + p.TW - 1) / p.TW;
+    p.tiles_y = (H + p.TH - 1) / p.TH;
+    p.num_m_tiles = (long long)d->out.B * p.tiles_x * p.tiles_y;
+    p.rr_dy0 = rr_dy_min;
+    p.rr_a_bytes = (p.TH + rr_dy_max - rr_dy_min) * p.TW * BK * 2;
+    p.rr_w_bytes = d->nseg * 2 * p.BN * BK * 2;
   } else {
     int tw = 1;
     while (tw < W && tw < BM) tw <<= 1;      // smallest power of two >= W, capped at 128
@@ -836,6 +933,7 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
       cuuint64_t str[4] = {(cuuint64_t)t.sx * esz, (cuuint64_t)t.sy * esz, (cuuint64_t)t.sb * esz,
                            (cuuint64_t)t.lo_off * esz};
       cuuint32_t box[5] = {BK, (cuuint32_t)(p.TW * d->stride), (cuuint32_t)(p.TH * d->stride), 1, 1};
+      if (rr) box[2] = (cuuint32_t)(p.TH + rr_dy_max - rr_dy_min);      // the whole halo of the tile in one box
       cuuint32_t es[5] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1, 1};
       p.coord_off[s] = off;
       if ((rc = encode(&maps[s], base, 5, dims, str, box, es, "spatial activations"))) return rc;
@@ -879,8 +977,8 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
   }
 
   // ---- launch
-  const int stage_bytes = 2 * kTileABytes + 2 * p.BN * BK * 2;
-  const int bar_bytes = kBarBytes + kEpiBytes;
+  const int stage_bytes = rr ? 2 * p.rr_a_bytes : 2 * kTileABytes + 2 * p.BN * BK * 2;
+  const int bar_bytes = kBarBytes + kEpiBytes + (rr ? p.rr_w_bytes : 0);
   int stages = (227 * 1024 - 1024 - bar_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   FFCB_REQUIRE(stages >= 2, "conv(tc): BN=%d leaves fewer than 2 pipeline stages", p.BN);
@@ -897,7 +995,8 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     kernel<<<grid, kThreads, smem, stream>>>(p, maps[0], maps[1], maps[2], maps[3]);
     return FFCB_OK;
   };
-  if (any_il) rc = p.out_planar ? launch(conv_tc_kernel<true, true>) : launch(conv_tc_kernel<true, false>);
+  if (rr) rc = launch(conv_tc_kernel<false, false, true>);
+  else if (any_il) rc = p.out_planar ? launch(conv_tc_kernel<true, true>) : launch(conv_tc_kernel<true, false>);
   else rc = p.out_planar ? launch(conv_tc_kernel<false, true>) : launch(conv_tc_kernel<false, false>);
   if (rc) return rc;
   FFCB_LAUNCH_CHECK("conv_tc_kernel");
