@@ -837,8 +837,9 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     // the short-K ones included); FFCB_TC_STACK=0 keeps three N = BN MMAs and four 128-column accumulator stages
     const char* e = getenv("FFCB_TC_STACK");
     p.stack = e ? (atoi(e) != 0) : 1;
-    p.acc_stride = p.stack ? 256 : kAccStride;
-    p.acc_stages = p.stack ? 2 : kAccStages;
+    // accumulator ring: a stacked accumulator is 2*BN columns wide — narrow tiles keep four stages
+    p.acc_stride = !p.stack ? kAccStride : (2 * p.BN <= 64 ? 64 : (2 * p.BN <= 128 ? 128 : 256));
+    p.acc_stages = 512 / p.acc_stride < kAccStages ? 512 / p.acc_stride : kAccStages;
   }
 
   // ---- tiling: flat when every tap is (0,0) on dense unit-stride inputs, else spatial TW x TH
@@ -885,7 +886,11 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
     p.TW = BM; p.TH = 1; p.tiles_x = p.tiles_y = 1;
     p.num_m_tiles = ((long long)d->out.B * H * W + BM - 1) / BM;
   } else if (rr) {
-    p.TW = 16; p.TH = BM / 16;              // a dy shift = 16 rows of 128 B = two whole swizzle atoms
+    // a dy shift = TW rows of 128 B must be whole 1024-byte swizzle atoms: TW = 8 (tall tiles: the smallest halo,
+    // 22 rows x 8 pixels = 44 KB per stage for a 7-tap column) or 16; FFCB_TC_ROWS_TW overrides
+    const char* etw = getenv("FFCB_TC_ROWS_TW");
+    p.TW = (etw && atoi(etw) == 16) ? 16 : 8;
+    p.TH = BM / p.TW;
     p.tiles_x = (W + p.TW - 1) / p.TW;
     p.tiles_y = (H + p.TH - 1) / p.TH;
     p.num_m_tiles = (long long)d->out.B * p.tiles_x * p.tiles_y;
