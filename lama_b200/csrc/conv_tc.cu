@@ -447,7 +447,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           if (elect_one()) {
             const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
             const uint32_t wr = smem_u32(w_res);
-            for (int sgi = 0; sgi < p.nseg; ++sgi) {
+            for (int sgi = 0; sgi < ((p.debug & 4) ? 0 : p.nseg); ++sgi) {
               const uint32_t a_off = (uint32_t)((p.seg[sgi].dy - p.rr_dy0) * p.TW * (BK * 2));
               const uint32_t a_hi = ((st + a_off) & 0x3FFFF) >> 4;
               const uint32_t a_lo = ((st + a_off + (uint32_t)p.rr_a_bytes) & 0x3FFFF) >> 4;

@@ -24,6 +24,12 @@ names = [n for n, _f, _a in ex.calls]
 # ops of the 9th residual block (second FFC_BN_ACT: with residual addends)
 want = ["ffcb_conv:convl2l+convg2l+bn_l+act", "ffcb_conv:st.conv1+bn+relu", "ffcb_conv:fu.conv_layer+bn+relu",
         "ffcb_conv:convl2g+st.conv2+bn_g+act", "ffcb_rfft2", "ffcb_irfft2"]
+if os.environ.get("TC_OPS"):       # e.g. TC_OPS="stem 7x7,head 7x7 rows,convT phase 11": last call whose name contains each
+    want = []
+    for sub in os.environ["TC_OPS"].split(","):
+        cand = [n for n in names if sub in n]
+        assert cand, (sub, sorted(set(names)))
+        want.append(cand[-1])
 idx = {}
 for w in want:
     cand = [i for i, n in enumerate(names) if n == w]
