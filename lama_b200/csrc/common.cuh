@@ -95,6 +95,16 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
+// hi / lo bf16 pairs of two values (round to nearest even, lo = bf16(v - hi)): the packed conversion (F2FP.PACK_AB)
+// instead of two scalar F2F — same bits, but F2F issues at 1/8 of the packed instruction's rate
+__device__ __forceinline__ void split_pair(float a, float b, unsigned& hi, unsigned& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const unsigned*>(&h);
+  lo = *reinterpret_cast<const unsigned*>(&l);
+}
+
 __device__ __forceinline__ float bf16_bits_to_float(unsigned short u) {
   return __uint_as_float(((unsigned)u) << 16);
 }
@@ -124,11 +134,12 @@ __device__ __forceinline__ void store4(const View& v, long long off, float4 r) {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(v.ptr) + off) = r;
     return;
   }
-  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-  split_bf16(r.x, h0, l0); split_bf16(r.y, h1, l1); split_bf16(r.z, h2, l2); split_bf16(r.w, h3, l3);
+  unsigned h0, l0, h1, l1;
+  split_pair(r.x, r.y, h0, l0);
+  split_pair(r.z, r.w, h1, l1);
   unsigned short* p = reinterpret_cast<unsigned short*>(v.ptr);
-  *reinterpret_cast<uint2*>(p + off) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
-  *reinterpret_cast<uint2*>(p + off + v.lo_off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+  *reinterpret_cast<uint2*>(p + off) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(p + off + v.lo_off) = make_uint2(l0, l1);
 }
 
 // scalar access (tails, odd layouts)

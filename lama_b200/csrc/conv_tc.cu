@@ -648,13 +648,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           for (int c = 0; c < 4; ++c) {
             unsigned h[4], l[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(v[8 * c + 2 * k], h0, l0);
-              split_bf16(v[8 * c + 2 * k + 1], h1, l1);
-              h[k] = pack_bf16(h0, h1);
-              l[k] = pack_bf16(l0, l1);
-            }
+            for (int k = 0; k < 4; ++k) split_pair(v[8 * c + 2 * k], v[8 * c + 2 * k + 1], h[k], l[k]);
             const uint4 h4 = make_uint4(h[0], h[1], h[2], h[3]), l4 = make_uint4(l[0], l[1], l[2], l[3]);
             hi[c ^ sw] = h4;
             lo[c ^ sw] = l4;

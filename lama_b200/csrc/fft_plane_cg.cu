@@ -40,15 +40,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint64
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// hi / lo bf16 pairs of a complex value (round to nearest even, lo = bf16(v - hi))
-__device__ __forceinline__ void split_pair(float a, float b, unsigned& hi, unsigned& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  const float2 hf = __bfloat1622float2(h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<const unsigned*>(&h);
-  lo = *reinterpret_cast<const unsigned*>(&l);
-}
-
 // grid: (C/4/sets, B).  A plane set = 4-channel group of the real input = 8-channel (4 complex) group of the spectrum.
 // DENSE: every tensor is the engine's dense [group][image][y][x][cg] allocation, so in-plane offsets are compile-time
 // constants (one base pointer per thread + immediates instead of 64-bit address arithmetic per access — the kernels
