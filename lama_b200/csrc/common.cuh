@@ -218,13 +218,6 @@ __device__ __forceinline__ bool ring_mirrors(const View& v, int y, int x, int& m
   return (my != -2) | (mx != -2);
 }
 
-// Out-of-line (keeps the hot epilogue small: the tcgen05 kernel is instruction-cache sensitive).
-static __device__ __noinline__ void store4_ring_copies(const View& v, int b, int y, int x, int my, int mx, int c, float4 r) {
-  if (my != -2) store4(v, pix_off(v, b, my, x) + c, r);
-  if (mx != -2) store4(v, pix_off(v, b, y, mx) + c, r);
-  if (my != -2 && mx != -2) store4(v, pix_off(v, b, my, mx) + c, r);
-}
-
 static __device__ __noinline__ float slow_act(float v, int act) {
   return act == FFCB_ACT_SIGMOID ? __fdividef(1.f, 1.f + __expf(-v)) : tanhf(v);
 }
