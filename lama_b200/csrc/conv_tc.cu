@@ -38,7 +38,6 @@ constexpr int kAccStages = 4;     // TMEM accumulator ring: the MMA issuer may r
 constexpr int kAccStride = 128;   // TMEM columns per accumulator stage (BN <= 128)
 constexpr int kBarBytes = 1024;  // mbarriers + TMEM slot, padded so that the staging tiles stay 1024-byte aligned
 constexpr int kEpiBytes = kEpiWarps * 4096;
-constexpr bool kEpi2Default = false;   // double-buffered epilogue staging for BN <= 64 (TcParams::epi2)
 
 struct TcParams {
   View out, addend;
@@ -72,7 +71,6 @@ struct TcParams {
   // reads 8 KB per 64 cycles = the whole 128 B/clk of the SM's shared memory).  Costs accumulator stages: 2 x 256
   // columns instead of 4 x 128.
   int stack, acc_stride, acc_stages;
-  int epi2;                       // two staging tiles per epilogue warp: a store may still be reading one while the next chunk fills the other
   // Rows-resident mode (template RR; the 7x7 head's row contraction and the windowed 7x7 stem): every K segment is the
   // SAME 64-channel block of one source shifted by dy only, so the activation tile is loaded ONCE per M tile as a
   // (TH + R) x TW halo (TW = 16, TH = 8: a dy shift is a whole number of 1024-byte swizzle atoms, the MMA descriptor
@@ -134,7 +132,6 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -528,8 +525,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
     const int e = warp - 4;
     const int wq = e & 3;                    // TMEM lane quarter (== warp id % 4, the hardware rule)
     const int half = e >> 2;
-    uint8_t* stg = stage_tile + (size_t)e * (p.epi2 ? 8192 : 4096);
-    uint32_t stg_flip = 0;            // epi2: byte offset (0 / 4096) of the staging tile the next chunk uses
+    uint8_t* stg = stage_tile + (size_t)e * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int HW = p.out.H * p.out.W;
@@ -641,17 +637,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           continue;
         }
         // the previous TMA store of this warp must have finished reading the staging tile
-        if (p.epi2) {
-          if (elect_one()) tma_store_wait_read1();  // the store before the previous one has released this tile
-        } else {
-          if (elect_one()) tma_store_wait_read();   // (elect.sync is deterministic: always the lane that committed)
-        }
+        if (elect_one()) tma_store_wait_read();     // (elect.sync is deterministic: always the lane that committed)
         __syncwarp();
-        uint8_t* cur = stg + stg_flip;
         if (out_split) {
           // [plane][32 rows][32 bf16] = 64-byte rows, TMA SWIZZLE_64B: 16-byte chunk c of row r lives at c ^ ((r>>1)&3)
-          uint4* hi = reinterpret_cast<uint4*>(cur) + lane * 4;
-          uint4* lo = reinterpret_cast<uint4*>(cur + 2048) + lane * 4;
+          uint4* hi = reinterpret_cast<uint4*>(stg) + lane * 4;
+          uint4* lo = reinterpret_cast<uint4*>(stg + 2048) + lane * 4;
           const int sw = (lane >> 1) & 3;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -681,7 +672,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           }
         } else {
           // [32 rows][32 floats] = 128-byte rows, TMA SWIZZLE_128B: chunk c of row r lives at c ^ (r & 7)
-          float4* dst = reinterpret_cast<float4*>(cur) + lane * 8;
+          float4* dst = reinterpret_cast<float4*>(stg) + lane * 8;
           const int sw = lane & 7;
 #pragma unroll
           for (int c = 0; c < 8; ++c) dst[c ^ sw] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
@@ -689,11 +680,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         fence_async_smem();
         __syncwarp();
         if (!(p.debug & 1) && elect_one()) {
-          if (p.flat) tma_store_3d(&map_out, cur, n0, (int)tc.m0 + wq * 32, 0);
-          else tma_store_5d(&map_out, cur, n0, box_x, box_y, tc.b, 0);
+          if (p.flat) tma_store_3d(&map_out, stg, n0, (int)tc.m0 + wq * 32, 0);
+          else tma_store_5d(&map_out, stg, n0, box_x, box_y, tc.b, 0);
           tma_store_commit();
         }
-        if (p.epi2) stg_flip ^= 4096u;
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
@@ -987,13 +977,7 @@ int conv_tc(const ffcb_conv_desc* d, cudaStream_t stream) {
 
   // ---- launch
   const int stage_bytes = rr ? 2 * p.rr_a_bytes : 2 * kTileABytes + 2 * p.BN * BK * 2;
-  {
-    // second staging tile per epilogue warp: only where the epilogue sets the pace (narrow tiles: short tiles of MMA
-    // work per TMA store) and shared memory allows; FFCB_TC_EPI2=0|1 forces it off / on for BN <= 64
-    const char* e = getenv("FFCB_TC_EPI2");
-    p.epi2 = (p.BN <= 64 && !p.out_planar && (e ? atoi(e) != 0 : kEpi2Default)) ? 1 : 0;
-  }
-  const int bar_bytes = kBarBytes + kEpiBytes * (p.epi2 ? 2 : 1) + (rr ? p.rr_w_bytes : 0);
+  const int bar_bytes = kBarBytes + kEpiBytes + (rr ? p.rr_w_bytes : 0);
   int stages = (227 * 1024 - 1024 - bar_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   FFCB_REQUIRE(stages >= 2, "conv(tc): BN=%d leaves fewer than 2 pipeline stages", p.BN);
