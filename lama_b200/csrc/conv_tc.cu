@@ -15,10 +15,16 @@
 //                tile-blocked inputs (ffcb_tensor.tile, the FourierUnit chain) need no map: the "interleaved"
 //                K-major operand tile [K/8][pixel][8] is one contiguous 16 KB run, fetched with a 1-D bulk copy;
 //   weights    : 3-D map (Kpad, N, plane), K-major.
-// Warp roles (256 threads, persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = MMA issuer
-// (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> shift /
-// addend / activation -> split-bf16 or fp32 NHWC stores, incl. the reflect ring).  TMEM accumulator
-// stages (a ring of four 128-column accumulators) let the MMA issuer run up to three tiles ahead of the epilogue.
+// The three products are issued as TWO MMAs per K step ("stacked": the hi and lo planes of a weight tile are adjacent
+// in a pipeline stage and read as one K-major tile of 2*BN rows): a_hi x [w_hi | w_lo] with N = 2*BN and a_lo x w_hi with
+// N = BN into the first half of the accumulator; the epilogue adds the halves (TcParams::stack).
+// Warp roles (384 threads, persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = MMA issuer (both walk the
+// pipeline in warp-uniform control flow, one lane chosen by elect.sync issues), warp 2 = TMEM allocator, warps 4-11 =
+// epilogue (TMEM -> registers -> shift / addend / activation -> split-bf16 or fp32 NHWC tiles staged for a TMA store,
+// or planar float32 stored straight from registers; the reflected ring of a whole-plane output is written here too).
+// The TMEM accumulator ring (two 256-column stages, four for narrow tiles) lets the MMA issuer run ahead of the
+// epilogue.  Template parameters select the operand / output kinds (IL, PO) and the rows-resident mode of the 7x7
+// shell layers (RR: one halo load per M tile, resident weight tiles).
 #include <cuda.h>
 #include <stdlib.h>
 
