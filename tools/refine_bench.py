@@ -32,8 +32,11 @@ def main():
     kw = dict(modulo=8, n_iters=args.iters, lr=0.002, min_side=512, max_scales=3, px_budget=1800000)
     out = {}
     res = {}
-    for mode, env in (("native_block_gradients", "1"), ("torch_autograd_blocks", "0")):
+    for mode, env in (("native_block_gradients", "1"), ("torch_autograd_blocks", "0"), ("torch_autograd_blocks_fp32", "0")):
         os.environ["LAMA_B200_NATIVE_GRAD"] = env
+        tf32 = mode != "torch_autograd_blocks_fp32"          # the third arm: torch without TF32 = the arithmetic yardstick
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
         os.environ["LAMA_B200_STRICT"] = "0"
         R.refine_predict(img, mask, gen, **dict(kw, n_iters=2))          # warm-up: programs, cuDNN plans
         torch.cuda.synchronize()
@@ -41,10 +44,12 @@ def main():
         res[mode] = R.refine_predict(img, mask, gen, **kw)
         torch.cuda.synchronize()
         out[mode + "_s"] = time.perf_counter() - t0
-    d = (res["native_block_gradients"] - res["torch_autograd_blocks"]).abs()
-    out["max_abs_difference"] = float(d.max())
-    out["mean_abs_difference"] = float(d.mean())
-    out["mean_abs_difference_in_hole"] = float(d[mask.expand_as(d) > 0].mean())
+    def diff(a, b):
+        d = (res[a] - res[b]).abs()
+        return {"max": float(d.max()), "mean": float(d.mean()), "mean_in_hole": float(d[mask.expand_as(d) > 0].mean())}
+    out["native_vs_torch_fp32"] = diff("native_block_gradients", "torch_autograd_blocks_fp32")
+    out["torch_tf32_vs_torch_fp32"] = diff("torch_autograd_blocks", "torch_autograd_blocks_fp32")
+    out["native_vs_torch_tf32"] = diff("native_block_gradients", "torch_autograd_blocks")
     out["note"] = ("Adam's normalised steps turn a sign flip of a near-zero gradient into a full +-lr move of that feature "
                    "every iteration, so the two arithmetic paths drift apart element-wise (max) while agreeing on average")
     out.update(image=[S, S], n_iters=args.iters, scales="pyramid of refinement.py:176-226 (min_side 512)",
